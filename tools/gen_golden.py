@@ -1,0 +1,174 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (CPU, via
+tools/refshim.py) on seeded synthetic inputs.  Build-container only.
+
+    python tools/gen_golden.py
+
+Golden files hold outputs only (inputs are regenerated from the seed by
+visiondepth3d_b200.synth), plus versions of the third-party libs used.
+"""
+import os
+import sys
+import threading
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import refshim  # noqa: E402
+from visiondepth3d_b200.synth import synth_frame  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+
+
+class Var:
+    def __init__(self, v):
+        self.v = v
+
+    def get(self):
+        return self.v
+
+
+def run_pixel_shift(r3d, torch, w, h, iw, ih, n_frames, kind, **kw):
+    """pixel_shift_cuda on n_frames consecutive frames (floating-window state carries)."""
+    refshim.reset_singletons(r3d)
+    out = {}
+    for i in range(n_frames):
+        fr, dp = synth_frame(i, iw, ih, kind)
+        ft = r3d.frame_to_tensor(fr)
+        dt = r3d.depth_to_tensor(dp)
+        l, r, s = r3d.pixel_shift_cuda(ft, dt, w, h, 4.5, -1.5, -6.0, return_shift_map=True, **kw)
+        out[f"left{i}"] = l
+        out[f"right{i}"] = r
+        out[f"shift{i}"] = s.numpy().astype(np.float16 if False else np.float32)
+    return out
+
+
+def run_loop(r3d, torch, cv2, src_w, src_h, n_frames, kind, rp):
+    """Drive the body of render_sbs_3d in memory by writing lossless-ish input is not
+    possible (codecs are lossy) -> we run the real render_sbs_3d with cv2 capture
+    monkey-patched to an in-memory frame source and the writer to a collector."""
+    refshim.reset_singletons(r3d)
+    frames = [synth_frame(i, src_w, src_h, kind) for i in range(n_frames)]
+
+    class Cap:
+        def __init__(self, which):
+            self.which = which
+            self.pos = 0
+
+        def isOpened(self):
+            return True
+
+        def get(self, prop):
+            if prop == cv2.CAP_PROP_FRAME_COUNT:
+                return float(n_frames)
+            if prop == cv2.CAP_PROP_FPS:
+                return 24.0
+            if prop == cv2.CAP_PROP_POS_FRAMES:
+                return float(self.pos)
+            return 0.0
+
+        def set(self, prop, v):
+            if prop == cv2.CAP_PROP_POS_FRAMES:
+                self.pos = int(v)
+            return True
+
+        def read(self):
+            if self.pos >= n_frames:
+                return False, None
+            f = frames[self.pos][self.which].copy()
+            self.pos += 1
+            return True, f
+
+        def release(self):
+            pass
+
+    collected = []
+
+    class Writer:
+        def __init__(self, *a, **k):
+            pass
+
+        def isOpened(self):
+            return True
+
+        def write(self, f):
+            collected.append(f.copy())
+
+        def release(self):
+            pass
+
+    real_cap, real_wr = cv2.VideoCapture, cv2.VideoWriter
+    cv2.VideoCapture = lambda path: Cap(0 if path == "rgb" else 1)
+    cv2.VideoWriter = Writer
+    try:
+        r3d.render_sbs_3d(
+            "rgb", "depth", "out.avi", "XVID", 24.0, rp["output_width"], rp["output_height"],
+            4.5, -1.5, -6.0, rp["sharpness_factor"], rp["output_format"], Var("Default (16:9)"),
+            r3d.aspect_ratios, rp["dof_strength"],
+            feather_strength=rp["feather_strength"], blur_ksize=rp["blur_ksize"],
+            use_subject_tracking=rp["use_subject_tracking"],
+            use_floating_window=rp["use_floating_window"],
+            max_pixel_shift_percent=0.02, suspend_flag=threading.Event(),
+            cancel_flag=threading.Event(),
+            preserve_original_aspect=rp["preserve_original_aspect"],
+            zero_parallax_strength=rp["zero_parallax_strength"],
+            color_saturation=rp.get("color_saturation", 1.0),
+            color_contrast=rp.get("color_contrast", 1.0),
+            color_brightness=rp.get("color_brightness", 0.0),
+        )
+    finally:
+        cv2.VideoCapture, cv2.VideoWriter = real_cap, real_wr
+    return {f"final{i}": f for i, f in enumerate(collected)}
+
+
+def main():
+    mods = refshim.load_reference(("render_3d",))
+    r3d = mods["render_3d"]
+    import cv2
+    import torch
+    import torchvision
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(OUT, exist_ok=True)
+    meta = dict(torch=torch.__version__, torchvision=torchvision.__version__, cv2=cv2.__version__,
+                numpy=np.__version__)
+
+    # A. pixel_shift_cuda, identity resize, GUI-style params, 3 consecutive frames
+    g = run_pixel_shift(r3d, torch, 320, 180, 320, 180, 3, "smooth",
+                        blur_ksize=9, feather_strength=10.0, zero_parallax_strength=0.01)
+    np.savez_compressed(os.path.join(OUT, "ps_smooth_320x180.npz"), **g, **meta)
+    # B. 2x upsample inside pixel_shift (Half-SBS style), no floating window
+    g = run_pixel_shift(r3d, torch, 320, 180, 160, 90, 2, "smooth",
+                        blur_ksize=5, feather_strength=4.0, enable_floating_window=False,
+                        convergence_strength=0.5)
+    np.savez_compressed(os.path.join(OUT, "ps_up2_320x180.npz"), **g, **meta)
+    # C. noise content (adversarial LSB), edge masking off, even blur ksize
+    g = run_pixel_shift(r3d, torch, 192, 108, 192, 108, 1, "noise",
+                        blur_ksize=4, feather_strength=10.0, enable_edge_masking=False,
+                        use_subject_tracking=False)
+    np.savez_compressed(os.path.join(OUT, "ps_noise_192x108.npz"), **g, **meta)
+
+    # D. full loop, Half-SBS (config-2 shape scaled down 6x: 320x180 source)
+    base = dict(output_width=320, output_height=180, sharpness_factor=0.2, output_format="Half-SBS",
+                dof_strength=0.0, feather_strength=10.0, blur_ksize=9, use_subject_tracking=True,
+                use_floating_window=True, preserve_original_aspect=False, zero_parallax_strength=0.01)
+    g = run_loop(r3d, torch, cv2, 320, 180, 6, "smooth", base)
+    np.savez_compressed(os.path.join(OUT, "loop_halfsbs_320x180.npz"), **g, **meta)
+    # E. full loop, Full-SBS preserve aspect (config-3 shape scaled down), DOF on + colour grade
+    rp = dict(base, output_format="Full-SBS", preserve_original_aspect=True, dof_strength=2.0,
+              color_saturation=1.1, color_contrast=1.05, color_brightness=0.02)
+    g = run_loop(r3d, torch, cv2, 320, 180, 5, "smooth", rp)
+    np.savez_compressed(os.path.join(OUT, "loop_fullsbs_dof_320x180.npz"), **g, **meta)
+    # F. anaglyph + interlaced formats, render defaults (no tracking)
+    rp = dict(base, output_format="Red-Cyan Anaglyph", preserve_original_aspect=True,
+              use_subject_tracking=False, use_floating_window=False, feather_strength=0.0, blur_ksize=1)
+    g = run_loop(r3d, torch, cv2, 256, 144, 3, "smooth", rp)
+    np.savez_compressed(os.path.join(OUT, "loop_anaglyph_256x144.npz"), **g, **meta)
+    rp = dict(rp, output_format="Passive Interlaced")
+    g = run_loop(r3d, torch, cv2, 256, 144, 3, "smooth", rp)
+    np.savez_compressed(os.path.join(OUT, "loop_interlaced_256x144.npz"), **g, **meta)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
