@@ -1,0 +1,180 @@
+/* vd3d.h -- C ABI of libvd3d.so, the B200 (sm_100a) depth->stereo engine.
+ *
+ * The reference (VisionDepth3D) has no FFI: its boundary is the Python function
+ * surface of core/render_3d.py and the `pipe` callable of core/render_depth.py
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference function it
+ * replaces; visiondepth3d_b200/render_3d.py and render_depth.py bind them with
+ * ctypes and re-expose the reference's names and signatures.
+ *
+ * Conventions: every function returns 0 on success or a negative vd3d_status;
+ * nothing throws; a ctx is not re-entrant, distinct ctxs are independent.
+ * Image pointers may be host or device memory as stated by `mem`
+ * (VD3D_MEM_HOST / VD3D_MEM_DEVICE); outputs are caller-owned buffers.
+ * There is no CPU fallback: without a CUDA device vd3d_create fails.
+ */
+#ifndef VD3D_H
+#define VD3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vd3d_ctx vd3d_ctx;
+
+typedef enum {
+  VD3D_OK = 0,
+  VD3D_ERR_CUDA = -1,        /* CUDA runtime error; see vd3d_last_error */
+  VD3D_ERR_ARG = -2,         /* bad argument */
+  VD3D_ERR_UNSUPPORTED = -3, /* valid in the reference, not implemented here */
+  VD3D_ERR_NOMEM = -4,
+  VD3D_ERR_STATE = -5        /* call sequence error (e.g. weights not loaded) */
+} vd3d_status;
+
+enum { VD3D_MEM_HOST = 0, VD3D_MEM_DEVICE = 1 };
+
+/* output_format of render_sbs_3d / format_3d_output (core/render_3d.py:837-860) */
+enum {
+  VD3D_FMT_HALF_SBS = 0,
+  VD3D_FMT_FULL_SBS = 1,
+  VD3D_FMT_ANAGLYPH = 2,   /* "Red-Cyan Anaglyph" */
+  VD3D_FMT_INTERLACED = 3, /* "Passive Interlaced" */
+  VD3D_FMT_VR = 4          /* unsupported (cv2 INTER_LINEAR upscale to 1440x1600) */
+};
+
+/* which temporal state vd3d_reset_state clears */
+enum {
+  VD3D_STATE_GLOBAL = 1, /* module singletons: depth_ema_norm, conv_ema,
+                            floating_window_tracker, bar_easer
+                            (core/render_3d.py:284-285,500,511) */
+  VD3D_STATE_CLIP = 2    /* per-render objects created at core/render_3d.py:1174-1182 */
+};
+
+/* kwargs of pixel_shift_cuda (core/render_3d.py:561-590).  Shifts are Python
+ * floats (double) in the reference and are rounded to fp32 where a tensor op
+ * consumes them, which the kernels reproduce. */
+typedef struct {
+  double fg_shift, mg_shift, bg_shift;
+  int32_t blur_ksize;
+  double feather_strength;
+  double max_pixel_shift_percent;
+  double parallax_balance;
+  double zero_parallax_strength;
+  int32_t use_subject_tracking;
+  int32_t enable_floating_window;
+  int32_t enable_feathering;
+  int32_t enable_edge_masking;
+  double convergence_strength;
+  int32_t enable_dynamic_convergence;
+  double depth_pop_gamma, depth_pop_mid;
+  double depth_stretch_lo, depth_stretch_hi;
+  double fg_pop_multiplier, bg_push_multiplier;
+  double subject_lock_strength;
+} vd3d_shift_params;
+
+/* arguments of render_sbs_3d (core/render_3d.py:933-985) that reach the frame loop */
+typedef struct {
+  int32_t output_width, output_height;
+  double fg_shift, mg_shift, bg_shift;
+  double sharpness_factor;
+  int32_t output_format;      /* VD3D_FMT_* */
+  double aspect_ratio;        /* aspect_ratios[selected_aspect_ratio.get()] */
+  double dof_strength;
+  double feather_strength;
+  int32_t blur_ksize;
+  int32_t use_subject_tracking, use_floating_window;
+  double max_pixel_shift_percent;
+  int32_t preserve_original_aspect;
+  double zero_parallax_strength;
+  int32_t enable_edge_masking, enable_feathering;
+  int32_t original_video_width, original_video_height; /* 0 = None */
+  double convergence_strength;
+  int32_t enable_dynamic_convergence;
+  double ipd_factor;
+  double color_saturation, color_contrast, color_brightness;
+} vd3d_render_params;
+
+/* sizes derived at core/render_3d.py:1074-1138,1250-1259 */
+typedef struct {
+  int32_t crop_x0, crop_y0, crop_w, crop_h;
+  int32_t target_eye_w, target_eye_h;
+  int32_t resized_width, resized_height;
+  int32_t per_eye_w, per_eye_h;
+  int32_t out_width, out_height;
+} vd3d_size_plan;
+
+/* per-frame scalars, for parity tests and progress reporting */
+typedef struct {
+  float pct_lo, pct_hi;       /* DepthPercentileEMA state after this frame */
+  float subj_raw, stretch_lo, stretch_hi, subj_shaped;
+  float subj_norm;            /* estimate_subject_depth(depth_tensor) (1334/1390) */
+  double dyn_scale, fg, mg, bg;
+  double zero_parallax_offset;
+  double focal_depth, motion_metric;
+  double stable_zero;
+  int32_t bar_width, bar_side; /* side: 0 none, 1 right, 2 left */
+} vd3d_frame_info;
+
+/* sizeof() of the ABI structs, so bindings can verify their layout:
+ * 0 vd3d_shift_params, 1 vd3d_render_params, 2 vd3d_size_plan, 3 vd3d_frame_info */
+int vd3d_struct_size(int which);
+
+/* ---- lifecycle ------------------------------------------------------- */
+int vd3d_create(int device, vd3d_ctx** out);
+void vd3d_destroy(vd3d_ctx* ctx);
+const char* vd3d_last_error(vd3d_ctx* ctx); /* ctx may be NULL: last create error */
+int vd3d_reset_state(vd3d_ctx* ctx, uint32_t which);
+/* pinned host memory for the end-to-end path */
+void* vd3d_host_alloc(size_t bytes);
+void vd3d_host_free(void* p);
+/* the stream all work of this ctx is enqueued on (cudaStream_t) */
+void* vd3d_stream(vd3d_ctx* ctx);
+int vd3d_sync(vd3d_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench: gpu_launches) */
+uint64_t vd3d_launch_count(vd3d_ctx* ctx);
+/* replay the per-frame kernel sequence from a captured CUDA graph (default 1) */
+int vd3d_set_graphs(vd3d_ctx* ctx, int enable);
+
+/* ---- DIBR ------------------------------------------------------------ */
+/* pixel_shift_cuda (core/render_3d.py:561-712).
+ * rgb: f32 planar RGB [3,in_h,in_w] in 0..1; depth: f32 [in_h,in_w];
+ * left/right: u8 BGR interleaved [height,width,3]; shift: f32 [height,width] or NULL.
+ * Mutates the floating-window tracker held by ctx (the module singleton). */
+int vd3d_pixel_shift(vd3d_ctx* ctx, const float* rgb, const float* depth, int in_h, int in_w,
+                     int width, int height, const vd3d_shift_params* p, uint8_t* left_bgr,
+                     uint8_t* right_bgr, float* shift, int mem, vd3d_frame_info* info);
+
+/* sizing rules of render_sbs_3d (core/render_3d.py:1074-1138,1236-1259) */
+int vd3d_plan_sizes(int src_w, int src_h, const vd3d_render_params* rp, vd3d_size_plan* out);
+
+/* one iteration of the render_sbs_3d frame loop (core/render_3d.py:1227-1419):
+ * frame_to_tensor/depth_to_tensor, aspect crop, resize, TemporalDepthFilter,
+ * DepthPercentileEMA, ShiftSmoother, dynamic parallax scale, pixel_shift_cuda,
+ * FocalDepthTracker, DOF, colour grade, floating-window bars, sharpen, eye fit,
+ * format_3d_output.  frame/depth: u8 BGR [src_h,src_w,3] (depth may also be one
+ * channel: depth_channels = 1); out: u8 BGR [out_height,out_width,3]. */
+int vd3d_render_frame(vd3d_ctx* ctx, const uint8_t* frame_bgr, const uint8_t* depth, int depth_channels,
+                      int src_h, int src_w, const vd3d_render_params* rp, uint8_t* out_bgr, int mem,
+                      vd3d_frame_info* info);
+
+/* Throughput form of the same loop: n frames, host or device arrays of
+ * frame pointers; H2D of frame i+1 and D2H of frame i-1 overlap the kernels of
+ * frame i on separate streams.  State carries across calls exactly as across
+ * loop iterations.  infos may be NULL. */
+int vd3d_render_clip(vd3d_ctx* ctx, int n, const uint8_t* const* frames, const uint8_t* const* depths,
+                     int depth_channels, int src_h, int src_w, const vd3d_render_params* rp,
+                     uint8_t* const* outs, int mem, vd3d_frame_info* infos);
+
+/* stage entry points (same kernels, exposed for stage-isolated parity tests) */
+/* apply_sharpening (717-732) on u8 BGR [h,w,3] */
+int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem);
+/* apply_dof_cuda (769-834) + apply_color_grade (734-767) + tensor_to_frame on a u8 BGR eye;
+ * depth01: f32 [dh,dw] resized bilinearly to [h,w] as at 1347-1350; max_sigma<=0 skips DOF */
+int vd3d_dof_grade(vd3d_ctx* ctx, const uint8_t* eye_bgr, int h, int w, const float* depth01, int dh, int dw,
+                   double focal, double max_sigma, double sat, double con, double bri, uint8_t* dst, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VD3D_H */

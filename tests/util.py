@@ -1,0 +1,40 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+
+def u8_diff(a, b):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return int(d.max()), float((d > 0).mean()), float((d > 1).mean())
+
+
+# Parameter sets used by tools/gen_golden.py (kept in one place so the oracle and the
+# CUDA path are driven exactly like the reference was).
+PS_CASES = {
+    "ps_smooth_320x180.npz": dict(w=320, h=180, iw=320, ih=180, n=3, kind="smooth",
+                                  kw=dict(blur_ksize=9, feather_strength=10.0, zero_parallax_strength=0.01)),
+    "ps_up2_320x180.npz": dict(w=320, h=180, iw=160, ih=90, n=2, kind="smooth",
+                               kw=dict(blur_ksize=5, feather_strength=4.0, enable_floating_window=False,
+                                       convergence_strength=0.5)),
+    "ps_noise_192x108.npz": dict(w=192, h=108, iw=192, ih=108, n=1, kind="noise",
+                                 kw=dict(blur_ksize=4, feather_strength=10.0, enable_edge_masking=False,
+                                         use_subject_tracking=False)),
+}
+
+_BASE = dict(output_width=320, output_height=180, sharpness_factor=0.2, output_format="Half-SBS",
+             dof_strength=0.0, feather_strength=10.0, blur_ksize=9, use_subject_tracking=True,
+             use_floating_window=True, preserve_original_aspect=False, zero_parallax_strength=0.01)
+LOOP_CASES = {
+    "loop_halfsbs_320x180.npz": dict(sw=320, sh=180, n=6, kind="smooth", rp=dict(_BASE)),
+    "loop_fullsbs_dof_320x180.npz": dict(
+        sw=320, sh=180, n=5, kind="smooth",
+        rp=dict(_BASE, output_format="Full-SBS", preserve_original_aspect=True, dof_strength=2.0,
+                color_saturation=1.1, color_contrast=1.05, color_brightness=0.02)),
+    "loop_anaglyph_256x144.npz": dict(
+        sw=256, sh=144, n=3, kind="smooth",
+        rp=dict(_BASE, output_format="Red-Cyan Anaglyph", preserve_original_aspect=True,
+                use_subject_tracking=False, use_floating_window=False, feather_strength=0.0, blur_ksize=1)),
+    "loop_interlaced_256x144.npz": dict(
+        sw=256, sh=144, n=3, kind="smooth",
+        rp=dict(_BASE, output_format="Passive Interlaced", preserve_original_aspect=True,
+                use_subject_tracking=False, use_floating_window=False, feather_strength=0.0, blur_ksize=1)),
+}

@@ -1,0 +1,1158 @@
+// dibr_kernels.cu -- see dibr_kernels.cuh.  Compiled with -fmad=false.
+#include "dibr_kernels.cuh"
+#include "dibr_launch.h"
+
+#include <math.h>
+
+namespace vd3d {
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+// cv2.cvtColor(BGR2GRAY) on u8: (B*3735 + G*19235 + R*9798 + 2^14) >> 15
+__device__ __forceinline__ float depth_src01(const uint8_t* __restrict__ p, int ch, int pitch_px, int y, int x) {
+  const uint8_t* q = p + ((size_t)y * pitch_px + x) * ch;
+  int g;
+  if (ch == 1) {
+    g = q[0];
+  } else {
+    g = (q[0] * 3735 + q[1] * 19235 + q[2] * 9798 + (1 << 14)) >> 15;
+  }
+  return (float)g / 255.0f;
+}
+
+// F.interpolate(bilinear, align_corners=False) axis set-up (torch 2.11 rounding:
+// src = fma(scale, dst+0.5, -0.5), clamped at 0)
+struct RsAxis {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ RsAxis rs_axis(int d, int insz, int outsz) {
+  RsAxis a;
+  float scale = (float)insz / (float)outsz;
+  float s = __fmaf_rn(scale, (float)d + 0.5f, -0.5f);
+  s = fmaxf(s, 0.f);
+  a.i0 = (int)s;
+  if (a.i0 > insz - 1) a.i0 = insz - 1;
+  a.i1 = a.i0 + (a.i0 < insz - 1 ? 1 : 0);
+  a.l1 = s - (float)a.i0;
+  a.l0 = 1.f - a.l1;
+  return a;
+}
+// value = fma(row(y0), ly0, row(y1)*ly1), row = fma(a, lx0, b*lx1)
+__device__ __forceinline__ float rs_combine(float v00, float v01, float v10, float v11, const RsAxis& ax,
+                                            const RsAxis& ay) {
+  float r0 = __fmaf_rn(v00, ax.l0, v01 * ax.l1);
+  float r1 = __fmaf_rn(v10, ax.l0, v11 * ax.l1);
+  return __fmaf_rn(r0, ay.l0, r1 * ay.l1);
+}
+
+__device__ __forceinline__ float bilinear_f32(const float* __restrict__ src, int sh, int sw, int oh, int ow, int y,
+                                              int x) {
+  if (sh == oh && sw == ow) return src[(size_t)y * sw + x];
+  RsAxis ax = rs_axis(x, sw, ow), ay = rs_axis(y, sh, oh);
+  const float* r0 = src + (size_t)ay.i0 * sw;
+  const float* r1 = src + (size_t)ay.i1 * sw;
+  return rs_combine(r0[ax.i0], r0[ax.i1], r1[ax.i0], r1[ax.i1], ax, ay);
+}
+
+__device__ __forceinline__ uint8_t trunc_u8(float v01) {
+  // tensor_to_frame (core/render_3d.py:289-291): (v*255).astype(uint8), v in [0,1]
+  float t = v01 * 255.0f;
+  int i = (int)t;
+  return (uint8_t)(i < 0 ? 0 : (i > 255 ? 255 : i));
+}
+
+__device__ __forceinline__ uint8_t rhe_u8(float v) {  // cvRound + saturate_cast<uchar>
+  int i = __float2int_rn(v);
+  return (uint8_t)(i < 0 ? 0 : (i > 255 ? 255 : i));
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+// apply_color_grade (core/render_3d.py:734-767) on one pixel
+__device__ __forceinline__ void grade_px(float& r, float& g, float& b, float sat, float con, float bri) {
+  float luma = ((0.2126f * r) + (0.7152f * g)) + (0.0722f * b);
+  float c[3] = {r, g, b};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float s = luma + ((c[i] - luma) * sat);
+    s = 0.5f + ((s - 0.5f) * con);
+    s = s + bri;
+    c[i] = clamp01(s);
+  }
+  r = c[0];
+  g = c[1];
+  b = c[2];
+}
+
+// ---------------------------------------------------------------------------
+// K1 ingest: depth_to_tensor + aspect crop + resize + TemporalDepthFilter (alpha .5)
+//            (+ frame_to_tensor + resize of RGB when a resize is needed)
+// core/render_3d.py:135-143, 220-229, 1236-1266
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ingest(IngestArgs a) {
+  int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= a.tw || y >= a.th) return;
+  float cur;
+  RsAxis ax, ay;
+  bool fast = (a.tw == a.cw && a.th == a.ch) && !a.rgb_s;
+  if (fast) {
+    cur = depth_src01(a.depth, a.depth_ch, a.src_w, a.cy0 + y, a.cx0 + x);
+  } else {  // same-size axes degenerate to i0 = d, l1 = 0: an exact identity
+    ax = rs_axis(x, a.cw, a.tw);
+    ay = rs_axis(y, a.ch, a.th);
+    float v00 = depth_src01(a.depth, a.depth_ch, a.src_w, a.cy0 + ay.i0, a.cx0 + ax.i0);
+    float v01 = depth_src01(a.depth, a.depth_ch, a.src_w, a.cy0 + ay.i0, a.cx0 + ax.i1);
+    float v10 = depth_src01(a.depth, a.depth_ch, a.src_w, a.cy0 + ay.i1, a.cx0 + ax.i0);
+    float v11 = depth_src01(a.depth, a.depth_ch, a.src_w, a.cy0 + ay.i1, a.cx0 + ax.i1);
+    cur = rs_combine(v00, v01, v10, v11, ax, ay);
+  }
+  size_t o = (size_t)y * a.tw + x;
+  float prev = a.st->tdf_init ? a.tdf[o] : cur;
+  float nv = (a.alpha * prev) + (a.one_minus_alpha * cur);
+  a.tdf[o] = nv;
+  if (a.rgb_s) {  // resized RGB planes
+    size_t plane = (size_t)a.th * a.tw;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {  // c: 0=R 1=G 2=B ; source is BGR
+      int sc = 2 - c;
+      const uint8_t* f = a.frame + sc;
+      float v00 = (float)f[((size_t)(a.cy0 + ay.i0) * a.src_w + a.cx0 + ax.i0) * 3] / 255.0f;
+      float v01 = (float)f[((size_t)(a.cy0 + ay.i0) * a.src_w + a.cx0 + ax.i1) * 3] / 255.0f;
+      float v10 = (float)f[((size_t)(a.cy0 + ay.i1) * a.src_w + a.cx0 + ax.i0) * 3] / 255.0f;
+      float v11 = (float)f[((size_t)(a.cy0 + ay.i1) * a.src_w + a.cx0 + ax.i1) * 3] / 255.0f;
+      a.rgb_s[c * plane + o] = rs_combine(v00, v01, v10, v11, ax, ay);
+    }
+  }
+}
+
+// generic planar f32 resize [C,sh,sw] -> [C,oh,ow] (pixel_shift_cuda:595-596)
+__global__ void __launch_bounds__(256) k_resize_planar(const float* __restrict__ src, int C, int sh, int sw,
+                                                       float* __restrict__ dst, int oh, int ow) {
+  int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= ow || y >= oh) return;
+  for (int c = 0; c < C; ++c)
+    dst[((size_t)c * oh + y) * ow + x] = bilinear_f32(src + (size_t)c * sh * sw, sh, sw, oh, ow, y, x);
+}
+
+// ---------------------------------------------------------------------------
+// radix select: exact k-th order statistics on fp32 in [0,1] (bit pattern is
+// monotone for non-negative floats).  pass 1: bits[29:18], pass 2: bits[17:6],
+// pass 3: bits[5:0].  Replaces torch.quantile's sort (core/render_3d.py:249-250,
+// 536-537) and torch.median / torch.histc (157-170).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void warp_hist_add(uint32_t* hist, bool on, uint32_t bin, bool shared) {
+  unsigned act = __activemask();
+  if (!__any_sync(act, on)) return;
+  unsigned key = on ? bin : 0xFFFFFFFFu;
+  unsigned m = __match_any_sync(act, key);
+  if (on && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(m));
+  (void)shared;
+}
+
+__device__ __forceinline__ bool in_job(const SelJob& j, int y, int x, float v) {
+  if (y < j.y0 || y >= j.y1 || x < j.x0 || x >= j.x1) return false;
+  if (j.masked) return (v > 0.05f) && (v < 0.95f);
+  return true;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256) k_sel_pass(SelJob a, SelJob b, int nb) {
+  __shared__ uint32_t sh[2][4096];
+  __shared__ uint32_t sh64[2][64];
+  if (PASS == 1) {
+    for (int i = threadIdx.x; i < 4096; i += 256) {
+      sh[0][i] = 0;
+      sh[1][i] = 0;
+    }
+    if (threadIdx.x < 64) {
+      sh64[0][threadIdx.x] = 0;
+      sh64[1][threadIdx.x] = 0;
+    }
+    __syncthreads();
+  }
+  const int rw = a.x1 - a.x0;
+  const int rw_pad = (rw + 31) & ~31;
+  for (int y = a.y0 + blockIdx.x; y < a.y1; y += gridDim.x) {
+    const float* row = a.data + (size_t)y * a.W;
+    for (int xi = threadIdx.x; xi < rw_pad; xi += 256) {
+      int x = a.x0 + xi;
+      bool inb = xi < rw;
+      float v = inb ? clamp01(row[x]) : 0.f;
+      uint32_t key = __float_as_uint(v) & 0x7FFFFFFFu;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        if (jj == 1 && !nb) break;
+        const SelJob& j = jj ? b : a;
+        bool on = inb && in_job(j, y, x, v);
+        if (PASS == 1) {
+          warp_hist_add(sh[jj], on, key >> 18, true);
+          if (j.hist64) {
+            int b64 = (int)(v * 64.0f);
+            b64 = b64 > 63 ? 63 : b64;
+            warp_hist_add(sh64[jj], on, (uint32_t)b64, true);
+          }
+        } else {
+          for (int t = 0; t < j.ntargets; ++t) {
+            const SelTarget& tg = j.tg[t];
+            if (PASS == 2) {
+              if (tg.alias >= 0) continue;
+              bool m = on && ((key >> 18) == tg.p1);
+              warp_hist_add(j.hist2 + t * 4096, m, (key >> 6) & 4095u, false);
+            } else {
+              if (tg.alias2 >= 0) continue;
+              bool m = on && ((key >> 18) == tg.p1) && (((key >> 6) & 4095u) == tg.p2);
+              warp_hist_add(j.hist3 + t * 64, m, key & 63u, false);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (PASS == 1) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += 256) {
+      if (sh[0][i]) atomicAdd(&a.hist1[i], sh[0][i]);
+      if (nb && sh[1][i]) atomicAdd(&b.hist1[i], sh[1][i]);
+    }
+    if (threadIdx.x < 64) {
+      if (a.hist64 && sh64[0][threadIdx.x]) atomicAdd(&a.hist64[threadIdx.x], sh64[0][threadIdx.x]);
+      if (nb && b.hist64 && sh64[1][threadIdx.x]) atomicAdd(&b.hist64[threadIdx.x], sh64[1][threadIdx.x]);
+    }
+  }
+}
+
+// one block per job: find, for every target, the bin holding its rank
+template <int PASS>
+__global__ void __launch_bounds__(1024) k_sel_find(SelJob a, SelJob b) {
+  const SelJob& j = blockIdx.x ? b : a;
+  constexpr int NB = (PASS == 3) ? 64 : 4096;
+  __shared__ uint32_t cum[4096];
+  __shared__ uint32_t part[1024];
+  const int tid = threadIdx.x;
+  for (int t = 0; t < j.ntargets; ++t) {
+    SelTarget& tg = j.tg[t];
+    const uint32_t* hist;
+    uint32_t rank;
+    if (PASS == 1) {
+      if (t > 0) break;  // pass-1 histogram is shared: handled below for all targets at once
+      hist = j.hist1;
+      rank = 0;
+    } else if (PASS == 2) {
+      if (tg.alias >= 0) continue;
+      hist = j.hist2 + t * 4096;
+      rank = tg.r1;
+    } else {
+      if (tg.alias2 >= 0) continue;
+      hist = j.hist3 + t * 64;
+      rank = tg.r2;
+    }
+    // inclusive scan of hist into cum
+    constexpr int PER = NB / 1024 > 0 ? NB / 1024 : 1;
+    uint32_t loc[PER];
+    uint32_t s = 0;
+    for (int k = 0; k < PER; ++k) {
+      int i = tid * PER + k;
+      uint32_t v = (i < NB) ? hist[i] : 0u;
+      s += v;
+      loc[k] = s;
+    }
+    part[tid] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      uint32_t v = (tid >= off) ? part[tid - off] : 0u;
+      __syncthreads();
+      part[tid] += v;
+      __syncthreads();
+    }
+    uint32_t base = tid ? part[tid - 1] : 0u;
+    for (int k = 0; k < PER; ++k) {
+      int i = tid * PER + k;
+      if (i < NB) cum[i] = base + loc[k];
+    }
+    __syncthreads();
+    if (PASS == 1) {
+      uint32_t n = cum[NB - 1];
+      if (tid == 0) *j.count = n;
+      // all targets search the shared histogram
+      for (int tt = 0; tt < j.ntargets; ++tt) {
+        uint32_t r = j.tg[tt].rank;
+        if (j.rank_from_count && tt == 0) r = n ? (n - 1) / 2 : 0;
+        for (int k = 0; k < PER; ++k) {
+          int i = tid * PER + k;
+          uint32_t lo = i ? cum[i - 1] : 0u;
+          if (r >= lo && r < cum[i]) {
+            j.tg[tt].p1 = i;
+            j.tg[tt].r1 = r - lo;
+            if (j.rank_from_count && tt == 0) j.tg[tt].rank = r;
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int tt = 0; tt < j.ntargets; ++tt) {
+          j.tg[tt].alias = -1;
+          for (int u = 0; u < tt; ++u)
+            if (j.tg[u].p1 == j.tg[tt].p1 && j.tg[u].alias < 0) {
+              j.tg[tt].alias = u;
+              break;
+            }
+        }
+      }
+    } else {
+      // this histogram may serve several aliased targets
+      for (int tt = t; tt < j.ntargets; ++tt) {
+        SelTarget& g = j.tg[tt];
+        bool mine = (tt == t) || (PASS == 2 ? g.alias == t : g.alias2 == t);
+        if (!mine) continue;
+        uint32_t r = (PASS == 2) ? g.r1 : g.r2;
+        for (int k = 0; k < PER; ++k) {
+          int i = tid * PER + k;
+          if (i >= NB) continue;
+          uint32_t lo = i ? cum[i - 1] : 0u;
+          if (r >= lo && r < cum[i]) {
+            if (PASS == 2) {
+              g.p2 = i;
+              g.r2 = r - lo;
+            } else {
+              g.bits = (g.p1 << 18) | (g.p2 << 6) | (uint32_t)i;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    (void)rank;
+  }
+  if (PASS == 2) {
+    __syncthreads();
+    if (tid == 0) {
+      for (int tt = 0; tt < j.ntargets; ++tt) {
+        j.tg[tt].alias2 = -1;
+        for (int u = 0; u < tt; ++u)
+          if (j.tg[u].p1 == j.tg[tt].p1 && j.tg[u].p2 == j.tg[tt].p2 && j.tg[u].alias2 < 0) {
+            j.tg[tt].alias2 = u;
+            break;
+          }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float torch_lerp(float a, float b, float w) {
+  float diff = b - a;
+  return (fabsf(w) < 0.5f) ? (a + (w * diff)) : (b - (diff * (1.0f - w)));
+}
+
+// estimate_subject_depth (core/render_3d.py:145-172) from the histc bins + lower median
+__device__ float subject_from_job(const SelJob& j) {
+  uint32_t n = *j.count;
+  if (n < 20) return 0.5f;
+  uint32_t best = 0;
+  int peak = 0;
+  for (int i = 0; i < 64; ++i) {
+    uint32_t c = j.hist64[i];
+    if (c > best) {
+      best = c;
+      peak = i;
+    }
+  }
+  float subj = ((float)peak + 0.5f) * (1.0f / 64.0f);
+  float med = __uint_as_float(j.tg[0].bits);
+  float v = (0.7f * subj) + (0.3f * med);
+  return clamp01(v);
+}
+
+// ---------------------------------------------------------------------------
+// scalar kernels (one thread): the reference's Python-side control flow
+// ---------------------------------------------------------------------------
+// DepthPercentileEMA.normalize state update (core/render_3d.py:249-262)
+__global__ void k_fin_pct(SelJob j, float w_lo, float w_hi, float alpha, float one_minus_alpha, DevState* st,
+                          FrameScalars* fs) {
+  float lo = torch_lerp(__uint_as_float(j.tg[0].bits), __uint_as_float(j.tg[1].bits), w_lo);
+  float hi = torch_lerp(__uint_as_float(j.tg[2].bits), __uint_as_float(j.tg[3].bits), w_hi);
+  fs->q_lo = lo;
+  fs->q_hi = hi;
+  if ((hi - lo) < 1e-5f) {
+    fs->pct_flat = 1;
+    fs->n_lo = 0.f;
+    fs->n_den = 1.f;
+    return;
+  }
+  fs->pct_flat = 0;
+  if (!st->pct_init) {
+    st->pct_lo = lo;
+    st->pct_hi = hi;
+    st->pct_init = 1;
+  } else {
+    st->pct_lo = (alpha * st->pct_lo) + (one_minus_alpha * lo);
+    st->pct_hi = (alpha * st->pct_hi) + (one_minus_alpha * hi);
+  }
+  fs->n_lo = st->pct_lo;
+  fs->n_den = (st->pct_hi - st->pct_lo) + 1e-6f;
+}
+
+// ShiftSmoother, compute_dynamic_parallax_scale, FocalDepthTracker, motion metric,
+// ConvergenceEMA, FloatingBarEaser (core/render_3d.py:412-427,463-511,895-929,1269-1276,1334-1403)
+__global__ void k_fin_norm(SelJob subj_job, LoopArgs la, DevState* st, FrameScalars* fs) {
+  st->tdf_init = 1;
+  // dynamic parallax scale
+  double n = (double)la.crop_count;
+  double mean64 = fs->sum / n;
+  float mean = (float)mean64;
+  float var = (float)((fs->sumsq - fs->sum * mean64) / (n - 1.0));
+  float nv = var / (mean + 1e-5f);
+  nv = clamp01(nv);
+  float scale = la.dyn_min + (nv * la.dyn_span);
+  double dyn = (double)scale;
+  fs->dyn = dyn;
+  // ShiftSmoother(alpha=0.15)
+  if (!st->sm_init) {
+    st->sm_fg = la.fg;
+    st->sm_mg = la.mg;
+    st->sm_bg = la.bg;
+    st->sm_init = 1;
+  } else {
+    st->sm_fg = 0.15 * la.fg + (1 - 0.15) * st->sm_fg;
+    st->sm_mg = 0.15 * la.mg + (1 - 0.15) * st->sm_mg;
+    st->sm_bg = 0.15 * la.bg + (1 - 0.15) * st->sm_bg;
+  }
+  double fg = st->sm_fg * dyn, mg = st->sm_mg * dyn, bg = st->sm_bg * dyn;
+  if (la.ipd != 0.0) {
+    fg *= la.ipd;
+    mg *= la.ipd;
+    bg *= la.ipd;
+  }
+  fs->fg = fg;
+  fs->mg = mg;
+  fs->bg = bg;
+  // candidate focal / floating-window subject
+  float sd = subject_from_job(subj_job);
+  fs->subj_norm = sd;
+  // motion metric
+  double motion = 0.0;
+  if (st->have_prev_depth) {
+    float mad = (float)(fs->mad_sum / (double)la.npix);
+    motion = fmax(0.0, fmin(1.0, (double)mad * 4.0));
+  }
+  fs->motion = motion;
+  st->have_prev_depth = 1;
+  // FocalDepthTracker
+  st->focal_alpha = 0.10 + 0.20 * fmax(0.0, fmin(1.0, motion));
+  double c = (double)sd;
+  if (!st->focal_init) {
+    st->focal = c;
+    st->focal_init = 1;
+  } else {
+    if (fabs(c - st->focal) < 0.03) c = st->focal;
+    double nf = (1.0 - st->focal_alpha) * st->focal + st->focal_alpha * c;
+    double delta = nf - st->focal;
+    if (delta > 0.02)
+      nf = st->focal + 0.02;
+    else if (delta < -0.02)
+      nf = st->focal - 0.02;
+    st->focal = fmax(0.0, fmin(1.0, nf));
+  }
+  fs->focal = st->focal;
+  // floating-window bars
+  float half = (float)((double)la.resized_width / 2 + 1e-6);
+  float rz = (((-sd) * (float)fg) + ((-sd) * (float)mg)) + (sd * (float)bg);
+  double raw_zero = (double)(rz / half);
+  if (!st->conv_init) {
+    st->conv_val = raw_zero;
+    st->conv_init = 1;
+  } else {
+    st->conv_val = 0.97 * st->conv_val + (1 - 0.97) * raw_zero;
+  }
+  double stable = st->conv_val;
+  fs->stable_zero = stable;
+  int bar = 0, side = 0;
+  if (la.use_floating_window && la.use_subject_tracking) {
+    int raw_bar = (int)(fabs(stable) * la.resized_width * 0.75);
+    st->bar_prev = (int)(0.85 * st->bar_prev + (1 - 0.85) * raw_bar);
+    bar = max(min(st->bar_prev, 80), 0);
+    if (stable > 0.005)
+      side = 1;
+    else if (stable < -0.005)
+      side = 2;
+  }
+  fs->bar_width = bar;
+  fs->bar_side = side;
+}
+
+__global__ void k_set_ranks(SelTarget* tg, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  tg[0].rank = r0;
+  tg[1].rank = r1;
+  tg[2].rank = r2;
+  tg[3].rank = r3;
+}
+
+__global__ void k_set_shifts(FrameScalars* fs, double fg, double mg, double bg) {
+  fs->fg = fg;
+  fs->mg = mg;
+  fs->bg = bg;
+}
+
+// shape_depth_for_pop scalars (core/render_3d.py:534-553)
+__global__ void k_fin_d0(SelJob qjob, SelJob sjob, float w_lo, float w_hi, FrameScalars* fs) {
+  float subj = subject_from_job(sjob);
+  fs->subj_raw = subj;
+  float lo = torch_lerp(__uint_as_float(qjob.tg[0].bits), __uint_as_float(qjob.tg[1].bits), w_lo);
+  float hi = torch_lerp(__uint_as_float(qjob.tg[2].bits), __uint_as_float(qjob.tg[3].bits), w_hi);
+  fs->st_lo = lo;
+  fs->st_hi = hi;
+  subj = clamp01(subj);
+  if ((hi - lo) < 1e-5f) {
+    fs->st_flat = 1;
+    fs->st_den = 1.f;
+    fs->st_subj = subj;
+  } else {
+    fs->st_flat = 0;
+    float den = (hi - lo) + 1e-6f;
+    fs->st_den = den;
+    fs->st_subj = clamp01((subj - lo) / den);
+  }
+}
+
+// zero-parallax offset, FloatingWindowTracker, clamp, convergence, mask strength
+// (core/render_3d.py:633-678)
+__global__ void k_fin_shape(SelJob sjob, ShiftArgs sa, DevState* st, FrameScalars* fs) {
+  float subj = subject_from_job(sjob);
+  fs->subj = subj;
+  const vd3d_shift_params& p = sa.p;
+  float fg = (float)fs->fg, mg = (float)fs->mg, bg = (float)fs->bg;
+  float fgm = (float)p.fg_pop_multiplier, bgm = (float)p.bg_push_multiplier;
+  float pb = (float)p.parallax_balance;
+  double half = (double)sa.W / 2.0;
+  fs->c_fg = fg;
+  fs->c_mg = mg;
+  fs->c_bg = bg;
+  fs->c_fgm = fgm;
+  fs->c_bgm = bgm;
+  fs->c_pb = pb;
+  fs->c_half = (float)half;
+  fs->c_mid = (float)p.depth_pop_mid;
+  fs->c_gamma = (float)p.depth_pop_gamma;
+  double zpo = 0.0;
+  fs->use_zpo = p.use_subject_tracking ? 1 : 0;
+  if (p.use_subject_tracking) {
+    float a = subj * pb;
+    float t1 = ((-a) * fg) * fgm;
+    float t2 = (-a) * mg;
+    float t3 = (a * bg) * bgm;
+    float z = ((t1 + t2) + t3) / (float)half;
+    z = z * (float)p.subject_lock_strength;
+    z = z - (float)p.zero_parallax_strength;
+    if (p.enable_floating_window) {
+      float sw = fminf(fmaxf(1.0f - (subj * 2.0f), 0.5f), 1.0f);
+      z = z * sw;
+      z = fminf(fmaxf(z, -0.35f), 0.35f);
+      double cur = (double)z;
+      // FloatingWindowTracker.smooth_offset(threshold=0.0015), alpha=0.97
+      if (fabs(cur - st->fw_prev) < 0.0015) {
+        zpo = st->fw_prev;
+      } else {
+        st->fw_prev = 0.97 * st->fw_prev + (1 - 0.97) * cur;
+        st->fw_count += 1;
+        if (st->fw_count >= 100) {
+          st->fw_prev = fmax(fmin(st->fw_prev, 1.0), -1.0);
+          st->fw_count = 0;
+        }
+        zpo = st->fw_prev;
+      }
+    } else {
+      zpo = (double)z;
+    }
+  }
+  fs->zpo = zpo;
+  fs->c_zpo = (float)zpo;
+  fs->c_max = (float)(((double)sa.W * p.max_pixel_shift_percent) / half);
+  fs->use_conv = (p.convergence_strength != 0.0) ? 1 : 0;
+  fs->c_conv = 0.f;
+  if (fs->use_conv) {
+    double conv = p.enable_dynamic_convergence ? (double)(subj * (float)p.convergence_strength)
+                                               : p.convergence_strength;
+    fs->c_conv = (float)(conv / half);
+  }
+  double ms = fmin(fmax(p.feather_strength / 10.0, 0.05), 0.3);
+  fs->c_m1 = (float)(1.0 - ms);
+  fs->c_m2 = (float)ms;
+}
+
+// ---------------------------------------------------------------------------
+// K2 normalise + centre statistics + motion (core/render_3d.py:247,261-262,418-423,928)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_normalize(const float* __restrict__ tdf, float* __restrict__ dn,
+                                                   const float* __restrict__ dn_prev, int th, int tw,
+                                                   const DevState* st, FrameScalars* fs) {
+  __shared__ double red[3][8];
+  int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  double s = 0, s2 = 0, mad = 0;
+  if (x < tw && y < th) {
+    size_t o = (size_t)y * tw + x;
+    float d = clamp01(tdf[o]);
+    float v = fs->pct_flat ? d : clamp01((d - fs->n_lo) / fs->n_den);
+    dn[o] = v;
+    if (y >= th / 4 && y < th * 3 / 4 && x >= tw / 4 && x < tw * 3 / 4) {
+      s = (double)v;
+      s2 = (double)v * (double)v;
+    }
+    if (st->have_prev_depth) mad = (double)fabsf(v - dn_prev[o]);
+  }
+  for (int off = 16; off; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    mad += __shfl_xor_sync(0xffffffffu, mad, off);
+  }
+  int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    red[0][w] = s;
+    red[1][w] = s2;
+    red[2][w] = mad;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    double* dst = threadIdx.x == 0 ? &fs->sum : (threadIdx.x == 1 ? &fs->sumsq : &fs->mad_sum);
+    if (t != 0.0) atomicAdd(dst, t);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3 d0 = clamp01(enhance_curvature(resize(depth))) (core/render_3d.py:596-601)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_d0(const float* __restrict__ src, int sh, int sw, float* __restrict__ d0,
+                                            int H, int W, const float* __restrict__ xs,
+                                            const float* __restrict__ ys, float strength) {
+  int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  float d = bilinear_f32(src, sh, sw, H, W, y, x);
+  float xx = xs[x], yy = ys[y];
+  float r2 = (xx * xx) + (yy * yy);
+  float curv = 1.0f - r2;
+  d = d + (curv * strength);
+  d0[(size_t)y * W + x] = clamp01(d);
+}
+
+// K4 shape_depth_for_pop elementwise part (core/render_3d.py:542,555-558), in place
+__global__ void __launch_bounds__(256) k_shape(float* __restrict__ d, int n, const FrameScalars* fs, float mid,
+                                               float gamma) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float v = d[i];  // already clamped
+  float ds = fs->st_flat ? v : clamp01((v - fs->st_lo) / fs->st_den);
+  float centered = (ds - fs->st_subj) + mid;
+  float x = centered - mid;
+  float ax = fabsf(x);
+  float pw = powf(ax, gamma);
+  float sg = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+  d[i] = clamp01((sg * pw) + mid);
+}
+
+// ---------------------------------------------------------------------------
+// K5 shift map + suppress_artifacts_with_edge_mask (core/render_3d.py:198-216,620-680)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_shift(const float* __restrict__ d, float* __restrict__ shift, int H, int W,
+                                               const FrameScalars* fs, int edge_mask, float feather) {
+  __shared__ float sd[13][38];   // d over x in [bx-3, bx+34), y in [by-3, by+10)
+  __shared__ float sm[12][36];   // 1 - sigmoid(...) over x in [bx-2, bx+34), y in [by-2, by+10)
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+  const int tid = threadIdx.x;
+  if (edge_mask) {
+    for (int i = tid; i < 13 * 37; i += 256) {
+      int ty = i / 37, tx = i % 37;
+      int gy = by - 3 + ty, gx = bx - 3 + tx;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = d[(size_t)gy * W + gx];
+      sd[ty][tx] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < 12 * 36; i += 256) {
+      int ty = i / 36, tx = i % 36;
+      int gy = by - 2 + ty, gx = bx - 2 + tx;
+      float m = 0.f;  // zero padding of avg_pool2d
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        float c = sd[ty + 1][tx + 1];
+        float dx = (gx > 0) ? fabsf(c - sd[ty + 1][tx]) : 0.f;
+        float dy = (gy > 0) ? fabsf(c - sd[ty][tx + 1]) : 0.f;
+        float g = sqrtf((dx * dx) + (dy * dy));
+        float z = ((g - 0.02f) * feather) * 5.0f;
+        float e = 1.0f / (1.0f + expf(-z));
+        m = 1.0f - e;
+      }
+      sm[ty][tx] = m;
+    }
+    __syncthreads();
+  }
+  int lx = tid & 31, ly = tid >> 5;
+  int x = bx + lx, y = by + ly;
+  if (x >= W || y >= H) return;
+  float v = edge_mask ? sd[ly + 3][lx + 3] : d[(size_t)y * W + x];
+  float fgw = clamp01(powf(1.0f - v, 1.5f));
+  float mgw = clamp01(1.0f - (fabsf(v - fs->c_mid) * 3.0f));
+  float bgw = clamp01(v);
+  float raw = (((fgw * fs->c_fg) * fs->c_fgm) + (mgw * fs->c_mg)) + ((bgw * fs->c_bg) * fs->c_bgm);
+  float total = (raw * fs->c_pb) / fs->c_half;
+  if (fs->use_zpo) total = total - fs->c_zpo;
+  total = fminf(fmaxf(total, -fs->c_max), fs->c_max);
+  if (fs->use_conv) total = total - fs->c_conv;
+  float fin = total;
+  if (edge_mask) {
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) acc = acc + sm[ly + dy][lx + dx];
+    float smooth = acc / 25.0f;
+    float sup = total * smooth;
+    fin = (fs->c_m1 * total) + (fs->c_m2 * sup);
+  }
+  shift[(size_t)y * W + x] = fin;
+}
+
+// ---------------------------------------------------------------------------
+// horizontal-parallax sampling set-up (F.grid_sample bilinear/border/align_corners=True)
+// ---------------------------------------------------------------------------
+struct Tap {
+  int x0, x1, y0, y1;
+  float nw, ne, sw, se;
+};
+__device__ __forceinline__ Tap make_tap(float gx, float gy, int H, int W) {
+  Tap t;
+  float ix = (gx + 1.0f) * ((float)(W - 1) / 2.0f);
+  float iy = (gy + 1.0f) * ((float)(H - 1) / 2.0f);
+  ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+  float fx = floorf(ix), fy = floorf(iy);
+  float wx = ix - fx, ex = 1.0f - wx;
+  float ny = iy - fy, sy = 1.0f - ny;
+  t.x0 = (int)fx;
+  t.y0 = (int)fy;
+  t.x1 = min(t.x0 + 1, W - 1);
+  t.y1 = min(t.y0 + 1, H - 1);
+  t.nw = sy * ex;
+  t.ne = sy * wx;
+  t.sw = ny * ex;
+  t.se = ny * wx;
+  return t;
+}
+__device__ __forceinline__ float tap_apply(const Tap& t, float v00, float v01, float v10, float v11) {
+  float o = v00 * t.nw;
+  o = __fmaf_rn(v01, t.ne, o);
+  o = __fmaf_rn(v10, t.sw, o);
+  o = __fmaf_rn(v11, t.se, o);
+  return o;
+}
+__device__ __forceinline__ float sample_plane(const float* __restrict__ p, int W, const Tap& t) {
+  const float* r0 = p + (size_t)t.y0 * W;
+  const float* r1 = p + (size_t)t.y1 * W;
+  return tap_apply(t, r0[t.x0], r0[t.x1], r1[t.x0], r1[t.x1]);
+}
+
+// K6 warped depth (both eyes) -> feather edge mask clamp(|grad| * strength)
+// (core/render_3d.py:700-701, 347-352).  e2[y][x] = (left, right)
+__global__ void __launch_bounds__(256) k_warp_edges(const float* __restrict__ d, const float* __restrict__ shift,
+                                                    float2* __restrict__ e2, int H, int W,
+                                                    const float* __restrict__ xs, const float* __restrict__ ys,
+                                                    float feather) {
+  __shared__ float wl[9][33], wr[9][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 9 * 33; i += 256) {
+    int ty = i / 33, tx = i % 33;
+    int gy = by - 1 + ty, gx = bx - 1 + tx;
+    float a = 0.f, b = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      float sv = shift[(size_t)gy * W + gx];
+      float xv = xs[gx], yv = ys[gy];
+      Tap tl = make_tap(xv + sv, yv, H, W);
+      Tap tr = make_tap(xv - sv, yv, H, W);
+      a = sample_plane(d, W, tl);
+      b = sample_plane(d, W, tr);
+    }
+    wl[ty][tx] = a;
+    wr[ty][tx] = b;
+  }
+  __syncthreads();
+  int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  int x = bx + lx, y = by + ly;
+  if (x >= W || y >= H) return;
+  float2 o;
+  {
+    float c = wl[ly + 1][lx + 1];
+    float dx = (x > 0) ? (c - wl[ly + 1][lx]) : 0.f;
+    float dy = (y > 0) ? (c - wl[ly][lx + 1]) : 0.f;
+    float g = sqrtf((dx * dx) + (dy * dy));
+    o.x = clamp01(g * feather);
+  }
+  {
+    float c = wr[ly + 1][lx + 1];
+    float dx = (x > 0) ? (c - wr[ly + 1][lx]) : 0.f;
+    float dy = (y > 0) ? (c - wr[ly][lx + 1]) : 0.f;
+    float g = sqrtf((dx * dx) + (dy * dy));
+    o.y = clamp01(g * feather);
+  }
+  e2[(size_t)y * W + x] = o;
+}
+
+// ---------------------------------------------------------------------------
+// K7 compose: warp RGB (both eyes), feather blend, truncate to u8, optional colour grade
+// (core/render_3d.py:697-698, 355-374, 289-291, 1373-1386)
+// SRC_U8: sample the BGR u8 frame directly (identity-resize path) else f32 RGB planes
+// ---------------------------------------------------------------------------
+template <bool SRC_U8>
+__device__ __forceinline__ void fetch_rgb(const ComposeArgs& a, int y, int x, float* rgb) {
+  if (SRC_U8) {
+    const uint8_t* q = a.src_u8 + ((size_t)(a.cy0 + y) * a.src_pitch + a.cx0 + x) * 3;
+    rgb[0] = (float)q[2] / 255.0f;
+    rgb[1] = (float)q[1] / 255.0f;
+    rgb[2] = (float)q[0] / 255.0f;
+  } else {
+    size_t plane = (size_t)a.H * a.W;
+    size_t o = (size_t)y * a.W + x;
+    rgb[0] = a.src_f32[o];
+    rgb[1] = a.src_f32[plane + o];
+    rgb[2] = a.src_f32[2 * plane + o];
+  }
+}
+
+template <bool SRC_U8>
+__global__ void __launch_bounds__(256) k_compose(ComposeArgs a) {
+  extern __shared__ float2 tile[];  // (32+k-1) x (8+k-1)
+  const int k = a.feather ? a.k : 1;
+  const int p = k / 2;
+  const int tw = 32 + k - 1, th = 8 + k - 1;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+  const int H = a.H, W = a.W;
+  if (a.feather) {
+    for (int i = threadIdx.x; i < tw * th; i += 256) {
+      int ty = i / tw, tx = i % tw;
+      int gy = by - p + ty, gx = bx - p + tx;
+      float2 v = make_float2(0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = a.e2[(size_t)gy * W + gx];
+      tile[i] = v;
+    }
+    __syncthreads();
+  }
+  int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  int x = bx + lx, y = by + ly;
+  if (x >= W || y >= H) return;
+  float sv = a.shift[(size_t)y * W + x];
+  float xv = a.xs[x], yv = a.ys[y];
+  Tap tl = make_tap(xv + sv, yv, H, W);
+  Tap tr = make_tap(xv - sv, yv, H, W);
+  float bl = 0.f, br = 0.f;
+  if (a.feather) {
+    float al = 0.f, ar = 0.f;
+    for (int dy = 0; dy < k; ++dy) {
+      const float2* row = tile + (ly + dy) * tw + lx;
+      for (int dx = 0; dx < k; ++dx) {
+        float2 v = row[dx];
+        al = al + v.x;
+        ar = ar + v.y;
+      }
+    }
+    float kk = (float)(k * k);
+    bl = al / kk;
+    br = ar / kk;
+  }
+  float o[3];
+  fetch_rgb<SRC_U8>(a, y, x, o);
+  float l00[3], l01[3], l10[3], l11[3];
+  uint8_t outl[3], outr[3];
+#pragma unroll
+  for (int eye = 0; eye < 2; ++eye) {
+    const Tap& t = eye ? tr : tl;
+    float b = eye ? br : bl;
+    fetch_rgb<SRC_U8>(a, t.y0, t.x0, l00);
+    fetch_rgb<SRC_U8>(a, t.y0, t.x1, l01);
+    fetch_rgb<SRC_U8>(a, t.y1, t.x0, l10);
+    fetch_rgb<SRC_U8>(a, t.y1, t.x1, l11);
+    float c[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float s = tap_apply(t, l00[ch], l01[ch], l10[ch], l11[ch]);
+      if (a.feather) s = clamp01((s * (1.0f - b)) + (o[ch] * b));
+      c[ch] = s;
+    }
+    uint8_t* dst = eye ? outr : outl;
+    uint8_t r8 = trunc_u8(c[0]), g8 = trunc_u8(c[1]), b8 = trunc_u8(c[2]);
+    if (a.grade) {  // frame_to_tensor -> apply_color_grade -> tensor_to_frame
+      float r = (float)r8 / 255.0f, g = (float)g8 / 255.0f, bb = (float)b8 / 255.0f;
+      grade_px(r, g, bb, a.sat, a.con, a.bri);
+      r8 = trunc_u8(r);
+      g8 = trunc_u8(g);
+      b8 = trunc_u8(bb);
+    }
+    dst[0] = b8;
+    dst[1] = g8;
+    dst[2] = r8;
+  }
+  size_t oo = ((size_t)y * W + x) * 3;
+  a.left[oo] = outl[0];
+  a.left[oo + 1] = outl[1];
+  a.left[oo + 2] = outl[2];
+  a.right[oo] = outr[0];
+  a.right[oo + 1] = outr[1];
+  a.right[oo + 2] = outr[2];
+}
+
+// ---------------------------------------------------------------------------
+// K8 DOF + colour grade on a u8 eye (core/render_3d.py:769-834, 1342-1369)
+// blockIdx.z selects the eye.  Gaussian levels: row-major fma chain, reflect padding.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dof(DofArgs a) {
+  extern __shared__ float dtile[];  // 3 planes of (32+2R) x (8+2R)
+  const int R = a.halo;
+  const int tw = 32 + 2 * R, th = 8 + 2 * R;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+  const int H = a.H, W = a.W;
+  const uint8_t* src = blockIdx.z ? a.src_r : a.src_l;
+  uint8_t* dst = blockIdx.z ? a.dst_r : a.dst_l;
+  for (int i = threadIdx.x; i < tw * th; i += 256) {
+    int ty = i / tw, tx = i % tw;
+    int gy = by - R + ty, gx = bx - R + tx;
+    // torch reflect padding (no edge repeat); clamp afterwards for tiles past the image
+    if (gy < 0) gy = -gy;
+    if (gy >= H) gy = 2 * H - 2 - gy;
+    if (gx < 0) gx = -gx;
+    if (gx >= W) gx = 2 * W - 2 - gx;
+    gy = min(max(gy, 0), H - 1);
+    gx = min(max(gx, 0), W - 1);
+    const uint8_t* q = src + ((size_t)gy * W + gx) * 3;
+    dtile[i] = (float)q[2] / 255.0f;
+    dtile[tw * th + i] = (float)q[1] / 255.0f;
+    dtile[2 * tw * th + i] = (float)q[0] / 255.0f;
+  }
+  __syncthreads();
+  int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  int x = bx + lx, y = by + ly;
+  if (x >= W || y >= H) return;
+  float c[3];
+  int ctr = (ly + R) * tw + lx + R;
+  if (a.nlevels > 1) {
+    float d = bilinear_f32(a.depth, a.dh, a.dw, H, W, y, x);
+    float focal = a.fs ? (float)a.fs->focal : a.focal;  // torch.tensor(float(focal_depth))
+    float diff = fabsf(d - focal);
+    float bw = clamp01(diff / a.focus_w);
+    float bidx = fminf(fmaxf(bw * (float)(a.nlevels - 1), 0.f), a.idx_max);
+    int lo = (int)floorf(bidx);
+    lo = min(max(lo, 0), a.nlevels - 2);
+    float al = bidx - (float)lo;
+    float one_m = 1.0f - al;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float* pl = dtile + ch * tw * th;
+      float v[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        int lvl = lo + s;
+        int ks = a.ksize[lvl];
+        if (ks <= 1) {
+          v[s] = pl[ctr];
+        } else {
+          int pr = ks / 2;
+          const float* kw = a.kern + a.koff[lvl];
+          float acc = 0.f;
+          for (int dy = 0; dy < ks; ++dy) {
+            const float* row = pl + (ly + R - pr + dy) * tw + (lx + R - pr);
+            for (int dx = 0; dx < ks; ++dx) acc = __fmaf_rn(row[dx], kw[dy * ks + dx], acc);
+          }
+          v[s] = acc;
+        }
+      }
+      c[ch] = clamp01((one_m * v[0]) + (al * v[1]));
+    }
+  } else {
+    c[0] = dtile[ctr];
+    c[1] = dtile[tw * th + ctr];
+    c[2] = dtile[2 * tw * th + ctr];
+  }
+  grade_px(c[0], c[1], c[2], a.sat, a.con, a.bri);
+  size_t oo = ((size_t)y * W + x) * 3;
+  dst[oo] = trunc_u8(c[2]);
+  dst[oo + 1] = trunc_u8(c[1]);
+  dst[oo + 2] = trunc_u8(c[0]);
+}
+
+// ---------------------------------------------------------------------------
+// K9 post: floating-window bars, sharpen, eye fit, pack
+// (core/render_3d.py:885-892, 717-732, 1409-1419, 837-883)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t eye_px(const uint8_t* __restrict__ eye, int W, int y, int x, int ch, int bar_lo,
+                                          int bar_hi) {
+  if (x >= bar_lo && x < bar_hi) return 0;  // apply_side_mask
+  return eye[((size_t)y * W + x) * 3 + ch];
+}
+
+__device__ __forceinline__ int sharp_px(const uint8_t* __restrict__ eye, int H, int W, int y, int x, int ch,
+                                        int bar_lo, int bar_hi, float kc, float ke, int do_sharpen) {
+  if (!do_sharpen) return eye_px(eye, W, y, x, ch, bar_lo, bar_hi);
+  int ym = reflect101(y - 1, H), yp = reflect101(y + 1, H);
+  int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+  float acc = 0.f;  // cv2.filter2D: row-major taps, fma chain, delta 0
+  acc = __fmaf_rn((float)eye_px(eye, W, ym, x, ch, bar_lo, bar_hi), ke, acc);
+  acc = __fmaf_rn((float)eye_px(eye, W, y, xm, ch, bar_lo, bar_hi), ke, acc);
+  acc = __fmaf_rn((float)eye_px(eye, W, y, x, ch, bar_lo, bar_hi), kc, acc);
+  acc = __fmaf_rn((float)eye_px(eye, W, y, xp, ch, bar_lo, bar_hi), ke, acc);
+  acc = __fmaf_rn((float)eye_px(eye, W, yp, x, ch, bar_lo, bar_hi), ke, acc);
+  return (int)rhe_u8(acc);
+}
+
+// value of the fitted (resized / padded) eye image at (ex, ey) in per-eye coordinates
+__device__ __forceinline__ int fitted_px(const PostArgs& a, const uint8_t* eye, int ey, int ex, int ch, int bar_lo,
+                                         int bar_hi) {
+  int fx = ex - a.fit_x0, fy = ey - a.fit_y0;
+  if (fx < 0 || fy < 0 || fx >= a.fit_w || fy >= a.fit_h) return 0;  // pad_to_aspect_ratio canvas
+  if (a.sx == 1 && a.sy == 1) return sharp_px(eye, a.H, a.W, fy, fx, ch, bar_lo, bar_hi, a.kc, a.ke, a.sharpen);
+  int sum = 0;
+  for (int j = 0; j < a.sy; ++j)
+    for (int i = 0; i < a.sx; ++i)
+      sum += sharp_px(eye, a.H, a.W, fy * a.sy + j, fx * a.sx + i, ch, bar_lo, bar_hi, a.kc, a.ke, a.sharpen);
+  if (a.sx == 2 && a.sy == 2) return (sum + 2) >> 2;  // cv2 INTER_AREA 2x2 integer fast path
+  return (int)rhe_u8((float)sum * a.inv_area);
+}
+
+__global__ void __launch_bounds__(256) k_post(PostArgs a) {
+  int ox = blockIdx.x * 32 + (threadIdx.x & 31);
+  int oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ox >= a.out_w || oy >= a.out_h) return;
+  int bar_lo = 0, bar_hi = 0;
+  if (a.fs) {
+    int bw = a.fs->bar_width;
+    if (a.fs->bar_side == 1) {
+      bar_lo = a.W - bw;
+      bar_hi = a.W;
+    } else if (a.fs->bar_side == 2) {
+      bar_lo = 0;
+      bar_hi = bw;
+    }
+  }
+  uint8_t o[3];
+  if (a.fmt == VD3D_FMT_HALF_SBS || a.fmt == VD3D_FMT_FULL_SBS) {
+    int eye = ox / a.per_eye_w;
+    int ex = ox - eye * a.per_eye_w;
+    const uint8_t* e = eye ? a.right : a.left;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) o[ch] = (uint8_t)fitted_px(a, e, oy, ex, ch, bar_lo, bar_hi);
+  } else if (a.fmt == VD3D_FMT_INTERLACED) {
+    const uint8_t* e = (oy & 1) ? a.right : a.left;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) o[ch] = (uint8_t)fitted_px(a, e, oy, ox, ch, bar_lo, bar_hi);
+  } else {  // Dubois anaglyph on channel indices 0,1,2 as split from the BGR arrays (862-883)
+    float l[3], r[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      l[ch] = (float)fitted_px(a, a.left, oy, ox, ch, bar_lo, bar_hi) / 255.0f;
+      r[ch] = (float)fitted_px(a, a.right, oy, ox, ch, bar_lo, bar_hi) / 255.0f;
+    }
+    float red = ((0.4561f * l[0]) + (0.5005f * l[1])) + (0.1762f * l[2]);
+    float grn = ((0.3764f * r[0]) + (0.7616f * r[1])) - (0.1876f * r[2]);
+    float blu = ((-0.0401f * r[0]) - (0.1126f * r[1])) + (1.2723f * r[2]);
+    o[0] = trunc_u8(clamp01(red));
+    o[1] = trunc_u8(clamp01(grn));
+    o[2] = trunc_u8(clamp01(blu));
+  }
+  size_t oo = ((size_t)oy * a.out_w + ox) * 3;
+  a.out[oo] = o[0];
+  a.out[oo + 1] = o[1];
+  a.out[oo + 2] = o[2];
+}
+
+// ---------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------
+static inline dim3 grid2d(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
+
+void launch_ingest(const IngestArgs& a, cudaStream_t s) { k_ingest<<<grid2d(a.tw, a.th), 256, 0, s>>>(a); }
+
+void launch_resize_planar(const float* src, int C, int sh, int sw, float* dst, int oh, int ow, cudaStream_t s) {
+  k_resize_planar<<<grid2d(ow, oh), 256, 0, s>>>(src, C, sh, sw, dst, oh, ow);
+}
+
+void launch_select(const SelJob& a, const SelJob* b, int nblocks, cudaStream_t s) {
+  SelJob bb = b ? *b : a;
+  int nb = b ? 1 : 0;
+  k_sel_pass<1><<<nblocks, 256, 0, s>>>(a, bb, nb);
+  k_sel_find<1><<<1 + nb, 1024, 0, s>>>(a, bb);
+  k_sel_pass<2><<<nblocks, 256, 0, s>>>(a, bb, nb);
+  k_sel_find<2><<<1 + nb, 1024, 0, s>>>(a, bb);
+  k_sel_pass<3><<<nblocks, 256, 0, s>>>(a, bb, nb);
+  k_sel_find<3><<<1 + nb, 1024, 0, s>>>(a, bb);
+}
+
+void launch_fin_pct(const SelJob& j, float w_lo, float w_hi, float alpha, float oma, DevState* st, FrameScalars* fs,
+                    cudaStream_t s) {
+  k_fin_pct<<<1, 1, 0, s>>>(j, w_lo, w_hi, alpha, oma, st, fs);
+}
+void launch_normalize(const float* tdf, float* dn, const float* dn_prev, int th, int tw, const DevState* st,
+                      FrameScalars* fs, cudaStream_t s) {
+  k_normalize<<<grid2d(tw, th), 256, 0, s>>>(tdf, dn, dn_prev, th, tw, st, fs);
+}
+void launch_fin_norm(const SelJob& j, const LoopArgs& la, DevState* st, FrameScalars* fs, cudaStream_t s) {
+  k_fin_norm<<<1, 1, 0, s>>>(j, la, st, fs);
+}
+void launch_set_ranks(SelTarget* tg, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, cudaStream_t s) {
+  k_set_ranks<<<1, 1, 0, s>>>(tg, r0, r1, r2, r3);
+}
+void launch_set_shifts(FrameScalars* fs, double fg, double mg, double bg, cudaStream_t s) {
+  k_set_shifts<<<1, 1, 0, s>>>(fs, fg, mg, bg);
+}
+void launch_d0(const float* src, int sh, int sw, float* d0, int H, int W, const float* xs, const float* ys,
+               float strength, cudaStream_t s) {
+  k_d0<<<grid2d(W, H), 256, 0, s>>>(src, sh, sw, d0, H, W, xs, ys, strength);
+}
+void launch_fin_d0(const SelJob& q, const SelJob& sj, float w_lo, float w_hi, FrameScalars* fs, cudaStream_t s) {
+  k_fin_d0<<<1, 1, 0, s>>>(q, sj, w_lo, w_hi, fs);
+}
+void launch_shape(float* d, int n, const FrameScalars* fs, float mid, float gamma, cudaStream_t s) {
+  k_shape<<<(n + 255) / 256, 256, 0, s>>>(d, n, fs, mid, gamma);
+}
+void launch_fin_shape(const SelJob& sj, const ShiftArgs& sa, DevState* st, FrameScalars* fs, cudaStream_t s) {
+  k_fin_shape<<<1, 1, 0, s>>>(sj, sa, st, fs);
+}
+void launch_shift(const float* d, float* shift, int H, int W, const FrameScalars* fs, int edge_mask, float feather,
+                  cudaStream_t s) {
+  k_shift<<<grid2d(W, H), 256, 0, s>>>(d, shift, H, W, fs, edge_mask, feather);
+}
+void launch_warp_edges(const float* d, const float* shift, float2* e2, int H, int W, const float* xs,
+                       const float* ys, float feather, cudaStream_t s) {
+  k_warp_edges<<<grid2d(W, H), 256, 0, s>>>(d, shift, e2, H, W, xs, ys, feather);
+}
+int compose_smem_bytes(int k) { return (32 + k - 1) * (8 + k - 1) * (int)sizeof(float2); }
+cudaError_t init_kernel_attributes() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_compose<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_compose<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_dof, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  return e;
+}
+void launch_compose(const ComposeArgs& a, cudaStream_t s) {
+  int smem = a.feather ? compose_smem_bytes(a.k) : 0;
+  if (a.src_u8)
+    k_compose<true><<<grid2d(a.W, a.H), 256, smem, s>>>(a);
+  else
+    k_compose<false><<<grid2d(a.W, a.H), 256, smem, s>>>(a);
+}
+void launch_dof(const DofArgs& a, int eyes, cudaStream_t s) {
+  int smem = 3 * (32 + 2 * a.halo) * (8 + 2 * a.halo) * (int)sizeof(float);
+  dim3 g = grid2d(a.W, a.H);
+  g.z = eyes;
+  k_dof<<<g, 256, smem, s>>>(a);
+}
+void launch_post(const PostArgs& a, cudaStream_t s) { k_post<<<grid2d(a.out_w, a.out_h), 256, 0, s>>>(a); }
+
+}  // namespace vd3d

@@ -1,0 +1,1046 @@
+// vd3d_api.cu -- host side of libvd3d.so: context, workspaces, the per-frame kernel
+// sequence of render_sbs_3d / pixel_shift_cuda (core/render_3d.py:561-712,1227-1419),
+// and the C ABI declared in include/vd3d.h.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "dibr_launch.h"
+
+using namespace vd3d;
+
+namespace {
+
+std::string g_create_error;
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct JobMem {  // device memory of one selection job
+  uint32_t* hist1;
+  uint32_t* hist2;
+  uint32_t* hist3;
+  uint32_t* hist64;
+  uint32_t* count;
+  SelTarget* tg;
+};
+
+constexpr int kJobs = 5;  // pct, subj(norm), quantile(d0), subj(d0), subj(shaped)
+constexpr size_t kJobWords = 4096 + 4 * 4096 + 4 * 64 + 64 + 64;  // + count (padded)
+
+}  // namespace
+
+struct vd3d_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int use_graphs = 1;
+
+  DevState* st = nullptr;
+  FrameScalars* fs = nullptr;
+  vd3d_frame_info* info_pinned = nullptr;
+  FrameScalars* fs_pinned = nullptr;
+  DevState* st_pinned = nullptr;
+  uint32_t* jobwords = nullptr;  // kJobs * kJobWords, zeroed every frame
+  SelTarget* tgs = nullptr;      // kJobs * 4
+  JobMem jm[kJobs];
+
+  // linspace tables
+  Buf xs, ys;
+  int xs_n = 0, ys_n = 0;
+  // planes
+  Buf tdf, dn0, dn1, rgb_s, frameB, d, shift, e2, eyeL, eyeR, eyeL2, eyeR2;
+  Buf in_frame[2], in_depth[2], out_dev[2], in_rgbf, in_depthf;
+  Buf dof_kern;
+  int tdf_w = 0, tdf_h = 0;
+  int frame_parity = 0;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  // dof kernel cache
+  double dof_sigma_cached = -1.0;
+  int dof_nlevels = 0, dof_ksize[8] = {0}, dof_koff[8] = {0}, dof_halo = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                    \
+  do {                                                                              \
+    cudaError_t _e = (call);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      char _b[512];                                                                 \
+      snprintf(_b, sizeof _b, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      ctx->err = _b;                                                                \
+      return VD3D_ERR_CUDA;                                                         \
+    }                                                                               \
+  } while (0)
+
+int fail(vd3d_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+int ensure(vd3d_ctx* ctx, Buf& b, size_t bytes) {
+  if (b.cap >= bytes) return VD3D_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  CK(cudaMalloc(&b.p, bytes));
+  b.cap = bytes;
+  return VD3D_OK;
+}
+
+// torch.linspace(-1, 1, n) fp32: step=(end-start)/(n-1); i<n/2: fma(step,i,start) else fma(-step,n-1-i,end)
+void linspace32(float start, float end, int n, std::vector<float>& out) {
+  out.resize(n);
+  if (n == 1) {
+    out[0] = start;
+    return;
+  }
+  float step = (end - start) / (float)(n - 1);
+  for (int i = 0; i < n; ++i)
+    out[i] = (i < n / 2) ? fmaf(step, (float)i, start) : fmaf(-step, (float)(n - 1 - i), end);
+}
+
+int ensure_axes(vd3d_ctx* ctx, int W, int H) {
+  std::vector<float> v;
+  if (ctx->xs_n != W) {
+    int r = ensure(ctx, ctx->xs, sizeof(float) * W);
+    if (r) return r;
+    linspace32(-1.f, 1.f, W, v);
+    CK(cudaMemcpyAsync(ctx->xs.p, v.data(), sizeof(float) * W, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->xs_n = W;
+  }
+  if (ctx->ys_n != H) {
+    int r = ensure(ctx, ctx->ys, sizeof(float) * H);
+    if (r) return r;
+    linspace32(-1.f, 1.f, H, v);
+    CK(cudaMemcpyAsync(ctx->ys.p, v.data(), sizeof(float) * H, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ys_n = H;
+  }
+  return VD3D_OK;
+}
+
+// torch.quantile rank arithmetic: rank = fp32(q) * (n-1) in fp32
+void quantile_rank(double q, long long n, uint32_t& lo, uint32_t& hi, float& w) {
+  float rank = (float)q * (float)(n - 1);
+  float fl = floorf(rank), ce = ceilf(rank);
+  lo = (uint32_t)fl;
+  hi = (uint32_t)ce;
+  w = rank - fl;
+}
+
+SelJob make_job(const JobMem& m, const float* data, int W, int x0, int x1, int y0, int y1, int masked, int nt,
+                int rank_from_count, bool hist64) {
+  SelJob j;
+  j.data = data;
+  j.W = W;
+  j.x0 = x0;
+  j.x1 = x1;
+  j.y0 = y0;
+  j.y1 = y1;
+  j.masked = masked;
+  j.ntargets = nt;
+  j.rank_from_count = rank_from_count;
+  j.hist1 = m.hist1;
+  j.hist2 = m.hist2;
+  j.hist3 = m.hist3;
+  j.hist64 = hist64 ? m.hist64 : nullptr;
+  j.tg = m.tg;
+  j.count = m.count;
+  return j;
+}
+
+int sel_blocks(int rows) {
+  int b = 148 * 4;
+  return rows < b ? rows : b;
+}
+
+// ---------------------------------------------------------------------------
+// pixel_shift core: from a depth plane [sh,sw] (already normalised) and an RGB source
+// to the two u8 eyes.  Shared by vd3d_pixel_shift and vd3d_render_frame.
+// ---------------------------------------------------------------------------
+struct CoreIn {
+  const float* depth;  // f32 [sh, sw]
+  int sh, sw;
+  const uint8_t* src_u8;  // identity path
+  int src_pitch, cx0, cy0;
+  const float* src_f32;  // RGB planes [3,H,W]
+  int W, H;
+  vd3d_shift_params p;
+  int grade;
+  float sat, con, bri;
+  uint8_t* left;
+  uint8_t* right;
+};
+
+int run_core(vd3d_ctx* ctx, const CoreIn& in) {
+  cudaStream_t s = ctx->stream;
+  const int W = in.W, H = in.H;
+  int r;
+  if ((r = ensure_axes(ctx, W, H))) return r;
+  if ((r = ensure(ctx, ctx->d, sizeof(float) * (size_t)W * H))) return r;
+  if ((r = ensure(ctx, ctx->shift, sizeof(float) * (size_t)W * H))) return r;
+  const float* xs = (const float*)ctx->xs.p;
+  const float* ys = (const float*)ctx->ys.p;
+  float* d = (float*)ctx->d.p;
+  float* shift = (float*)ctx->shift.p;
+
+  launch_d0(in.depth, in.sh, in.sw, d, H, W, xs, ys, 0.08f, s);
+  ctx->launches += 1;
+  // quantiles (depth_stretch_lo/hi) over the full map + subject estimate on the centre crop
+  uint32_t l0, l1, h0, h1;
+  float wlo, whi;
+  quantile_rank(in.p.depth_stretch_lo, (long long)W * H, l0, l1, wlo);
+  quantile_rank(in.p.depth_stretch_hi, (long long)W * H, h0, h1, whi);
+  launch_set_ranks(ctx->jm[2].tg, l0, l1, h0, h1, s);
+  SelJob qj = make_job(ctx->jm[2], d, W, 0, W, 0, H, 0, 4, 0, false);
+  SelJob s0 = make_job(ctx->jm[3], d, W, W / 5, W * 4 / 5, H / 5, H * 4 / 5, 1, 1, 1, true);
+  launch_select(qj, &s0, sel_blocks(H), s);
+  launch_fin_d0(qj, s0, wlo, whi, ctx->fs, s);
+  launch_shape(d, W * H, ctx->fs, (float)in.p.depth_pop_mid, (float)in.p.depth_pop_gamma, s);
+  SelJob s1 = make_job(ctx->jm[4], d, W, W / 5, W * 4 / 5, H / 5, H * 4 / 5, 1, 1, 1, true);
+  launch_select(s1, nullptr, sel_blocks(H * 4 / 5 - H / 5), s);
+  ShiftArgs sa;
+  sa.p = in.p;
+  sa.W = W;
+  sa.H = H;
+  launch_fin_shape(s1, sa, ctx->st, ctx->fs, s);
+  launch_shift(d, shift, H, W, ctx->fs, in.p.enable_edge_masking ? 1 : 0, (float)in.p.feather_strength, s);
+  ctx->launches += 1 + 6 + 1 + 1 + 6 + 1 + 1;
+  int feather = in.p.enable_feathering ? 1 : 0;
+  if (feather) {
+    if (in.p.blur_ksize < 1 || in.p.blur_ksize > 63) return fail(ctx, VD3D_ERR_UNSUPPORTED, "blur_ksize must be in [1,63]");
+    if ((r = ensure(ctx, ctx->e2, sizeof(float2) * (size_t)W * H))) return r;
+    launch_warp_edges(d, shift, (float2*)ctx->e2.p, H, W, xs, ys, (float)in.p.feather_strength, s);
+    ctx->launches += 1;
+  }
+  ComposeArgs ca;
+  ca.src_u8 = in.src_u8;
+  ca.src_pitch = in.src_pitch;
+  ca.cx0 = in.cx0;
+  ca.cy0 = in.cy0;
+  ca.src_f32 = in.src_f32;
+  ca.shift = shift;
+  ca.e2 = (const float2*)ctx->e2.p;
+  ca.xs = xs;
+  ca.ys = ys;
+  ca.H = H;
+  ca.W = W;
+  ca.k = in.p.blur_ksize;
+  ca.feather = feather;
+  ca.grade = in.grade;
+  ca.sat = in.sat;
+  ca.con = in.con;
+  ca.bri = in.bri;
+  ca.left = in.left;
+  ca.right = in.right;
+  launch_compose(ca, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  return VD3D_OK;
+}
+
+int begin_frame(vd3d_ctx* ctx) {
+  CK(cudaMemsetAsync(ctx->jobwords, 0, sizeof(uint32_t) * kJobs * kJobWords, ctx->stream));
+  CK(cudaMemsetAsync(ctx->fs, 0, sizeof(FrameScalars), ctx->stream));
+  return VD3D_OK;
+}
+
+int fetch_info(vd3d_ctx* ctx, vd3d_frame_info* info) {
+  CK(cudaMemcpyAsync(ctx->fs_pinned, ctx->fs, sizeof(FrameScalars), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->st_pinned, ctx->st, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const FrameScalars& f = *ctx->fs_pinned;
+  const DevState& t = *ctx->st_pinned;
+  info->pct_lo = t.pct_lo;
+  info->pct_hi = t.pct_hi;
+  info->subj_raw = f.subj_raw;
+  info->stretch_lo = f.st_lo;
+  info->stretch_hi = f.st_hi;
+  info->subj_shaped = f.subj;
+  info->subj_norm = f.subj_norm;
+  info->dyn_scale = f.dyn;
+  info->fg = f.fg;
+  info->mg = f.mg;
+  info->bg = f.bg;
+  info->zero_parallax_offset = f.zpo;
+  info->focal_depth = f.focal;
+  info->motion_metric = f.motion;
+  info->stable_zero = f.stable_zero;
+  info->bar_width = f.bar_width;
+  info->bar_side = f.bar_side;
+  return VD3D_OK;
+}
+
+// torchvision _get_gaussian_kernel2d for the DOF levels (core/render_3d.py:798-806)
+int ensure_dof_kernels(vd3d_ctx* ctx, double max_sigma, int num_levels) {
+  if (ctx->dof_sigma_cached == max_sigma && ctx->dof_nlevels == num_levels) return VD3D_OK;
+  std::vector<float> sig;
+  linspace32(0.f, (float)max_sigma, num_levels, sig);
+  std::vector<float> all;
+  int halo = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    float s = sig[l];
+    int ks = 1;
+    if ((double)s != 0.0) ks = (int)(2 * ceil(2 * (double)s) + 1);
+    if (ks > 17) return fail(ctx, VD3D_ERR_UNSUPPORTED, "dof_strength too large (Gaussian ksize > 17)");
+    ctx->dof_ksize[l] = ks;
+    ctx->dof_koff[l] = (int)all.size();
+    if (ks > 1) {
+      std::vector<float> x, pdf(ks);
+      float half = (float)((ks - 1) * 0.5);
+      linspace32(-half, half, ks, x);
+      float sum = 0.f;
+      for (int i = 0; i < ks; ++i) {
+        float q = x[i] / (float)(double)s;
+        float e = -0.5f * (q * q);
+        pdf[i] = (float)exp((double)e);
+      }
+      for (int i = 0; i < ks; ++i) sum += pdf[i];
+      for (int i = 0; i < ks; ++i) pdf[i] = pdf[i] / sum;
+      for (int y = 0; y < ks; ++y)
+        for (int xx = 0; xx < ks; ++xx) all.push_back(pdf[y] * pdf[xx]);
+      if (ks / 2 > halo) halo = ks / 2;
+    }
+  }
+  if (all.empty()) all.push_back(1.f);
+  int r = ensure(ctx, ctx->dof_kern, sizeof(float) * all.size());
+  if (r) return r;
+  CK(cudaMemcpyAsync(ctx->dof_kern.p, all.data(), sizeof(float) * all.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->dof_sigma_cached = max_sigma;
+  ctx->dof_nlevels = num_levels;
+  ctx->dof_halo = halo;
+  return VD3D_OK;
+}
+
+void sharpen_coeffs(double factor, float& kc, float& ke) {
+  // apply_sharpening: fp32 kernel [[0,-1,0],[-1,5+f,-1],[0,-1,0]] / sum (core/render_3d.py:719-728)
+  float c = (float)(5.0 + factor);
+  float ks = c - 4.0f;
+  kc = c;
+  ke = -1.0f;
+  if (ks != 0.f) {
+    kc = c / ks;
+    ke = -1.0f / ks;
+  }
+}
+
+struct FitPlan {
+  int fit_x0, fit_y0, fit_w, fit_h, sx, sy;
+};
+
+// eye fit: cv2.resize INTER_AREA (Half-SBS) or pad_to_aspect_ratio (core/render_3d.py:101-131,1409-1417)
+int plan_fit(vd3d_ctx* ctx, int fmt, int W, int H, int pw, int ph, FitPlan& f) {
+  int nw, nh;
+  if (fmt == VD3D_FMT_HALF_SBS) {
+    nw = pw;
+    nh = ph;
+    f.fit_x0 = f.fit_y0 = 0;
+  } else {
+    double ta = (double)pw / (double)ph;
+    double ca = (double)W / (double)H;
+    if (ca > ta) {
+      nw = pw;
+      nh = (int)(pw / ca);
+    } else {
+      nh = ph;
+      nw = (int)(ca * ph);
+    }
+    f.fit_x0 = (pw - nw) / 2;
+    f.fit_y0 = (ph - nh) / 2;
+  }
+  if (nw <= 0 || nh <= 0) return fail(ctx, VD3D_ERR_ARG, "degenerate eye size");
+  if (W % nw != 0 || H % nh != 0)
+    return fail(ctx, VD3D_ERR_UNSUPPORTED, "eye fit needs a non-integer INTER_AREA factor");
+  f.fit_w = nw;
+  f.fit_h = nh;
+  f.sx = W / nw;
+  f.sy = H / nh;
+  return VD3D_OK;
+}
+
+int copy_in(vd3d_ctx* ctx, Buf& b, const void* src, size_t bytes, int mem, cudaStream_t s, const void** dev) {
+  if (mem == VD3D_MEM_DEVICE) {
+    *dev = src;
+    return VD3D_OK;
+  }
+  int r = ensure(ctx, b, bytes);
+  if (r) return r;
+  CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
+  *dev = b.p;
+  return VD3D_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int vd3d_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(vd3d_shift_params);
+    case 1: return (int)sizeof(vd3d_render_params);
+    case 2: return (int)sizeof(vd3d_size_plan);
+    case 3: return (int)sizeof(vd3d_frame_info);
+    default: return -1;
+  }
+}
+
+int vd3d_create(int device, vd3d_ctx** out) {
+  if (!out) return VD3D_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                     " (libvd3d has no CPU fallback)";
+    return VD3D_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_error = "bad device index";
+    return VD3D_ERR_ARG;
+  }
+  vd3d_ctx* ctx = new vd3d_ctx();
+  ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t er) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(er);
+    delete ctx;
+    return VD3D_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming);
+  }
+  if ((e = cudaMalloc(&ctx->st, sizeof(DevState))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->fs, sizeof(FrameScalars))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->jobwords, sizeof(uint32_t) * kJobs * kJobWords)) != cudaSuccess)
+    return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&ctx->tgs, sizeof(SelTarget) * kJobs * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+  cudaMemset(ctx->st, 0, sizeof(DevState));
+  cudaMemset(ctx->fs, 0, sizeof(FrameScalars));
+  cudaMemset(ctx->jobwords, 0, sizeof(uint32_t) * kJobs * kJobWords);
+  cudaMemset(ctx->tgs, 0, sizeof(SelTarget) * kJobs * 4);
+  for (int j = 0; j < kJobs; ++j) {
+    uint32_t* b = ctx->jobwords + (size_t)j * kJobWords;
+    ctx->jm[j].hist1 = b;
+    ctx->jm[j].hist2 = b + 4096;
+    ctx->jm[j].hist3 = b + 4096 + 4 * 4096;
+    ctx->jm[j].hist64 = b + 4096 + 4 * 4096 + 4 * 64;
+    ctx->jm[j].count = b + 4096 + 4 * 4096 + 4 * 64 + 64;
+    ctx->jm[j].tg = ctx->tgs + j * 4;
+  }
+  if ((e = cudaMallocHost(&ctx->fs_pinned, sizeof(FrameScalars))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost(&ctx->st_pinned, sizeof(DevState))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = init_kernel_attributes()) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+  *out = ctx;
+  return VD3D_OK;
+}
+
+void vd3d_destroy(vd3d_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  Buf* bufs[] = {&ctx->xs,    &ctx->ys,    &ctx->tdf,   &ctx->dn0,   &ctx->dn1,      &ctx->rgb_s,
+                 &ctx->frameB, &ctx->d,     &ctx->shift, &ctx->e2,    &ctx->eyeL,     &ctx->eyeR,
+                 &ctx->eyeL2, &ctx->eyeR2, &ctx->in_frame[0], &ctx->in_frame[1], &ctx->in_depth[0],
+                 &ctx->in_depth[1], &ctx->out_dev[0], &ctx->out_dev[1], &ctx->in_rgbf, &ctx->in_depthf,
+                 &ctx->dof_kern};
+  for (Buf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  cudaFree(ctx->st);
+  cudaFree(ctx->fs);
+  cudaFree(ctx->jobwords);
+  cudaFree(ctx->tgs);
+  cudaFreeHost(ctx->fs_pinned);
+  cudaFreeHost(ctx->st_pinned);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(ctx->ev_h2d[i]);
+    cudaEventDestroy(ctx->ev_done[i]);
+    cudaEventDestroy(ctx->ev_d2h[i]);
+  }
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->s_h2d);
+  cudaStreamDestroy(ctx->s_d2h);
+  delete ctx;
+}
+
+const char* vd3d_last_error(vd3d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int vd3d_reset_state(vd3d_ctx* ctx, uint32_t which) {
+  if (!ctx) return VD3D_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  DevState h;
+  CK(cudaMemcpy(&h, ctx->st, sizeof h, cudaMemcpyDeviceToHost));
+  if (which & VD3D_STATE_GLOBAL) {
+    h.pct_lo = h.pct_hi = 0.f;
+    h.pct_init = 0;
+    h.conv_val = 0.0;
+    h.conv_init = 0;
+    h.fw_prev = 0.0;
+    h.fw_count = 0;
+    h.bar_prev = 0;
+  }
+  if (which & VD3D_STATE_CLIP) {
+    h.tdf_init = 0;
+    h.sm_fg = h.sm_mg = h.sm_bg = 0.0;
+    h.sm_init = 0;
+    h.focal = 0.0;
+    h.focal_alpha = 0.15;
+    h.focal_init = 0;
+    h.have_prev_depth = 0;
+    ctx->frame_parity = 0;
+  }
+  CK(cudaMemcpy(ctx->st, &h, sizeof h, cudaMemcpyHostToDevice));
+  return VD3D_OK;
+}
+
+void* vd3d_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void vd3d_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+void* vd3d_stream(vd3d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int vd3d_sync(vd3d_ctx* ctx) {
+  if (!ctx) return VD3D_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->s_d2h));
+  return VD3D_OK;
+}
+uint64_t vd3d_launch_count(vd3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int vd3d_set_graphs(vd3d_ctx* ctx, int enable) {
+  if (!ctx) return VD3D_ERR_ARG;
+  ctx->use_graphs = enable;
+  return VD3D_OK;
+}
+
+// ---------------------------------------------------------------------------
+int vd3d_pixel_shift(vd3d_ctx* ctx, const float* rgb, const float* depth, int in_h, int in_w, int width,
+                     int height, const vd3d_shift_params* p, uint8_t* left_bgr, uint8_t* right_bgr, float* shift,
+                     int mem, vd3d_frame_info* info) {
+  if (!ctx || !rgb || !depth || !p || !left_bgr || !right_bgr) return fail(ctx, VD3D_ERR_ARG, "null argument");
+  if (in_h < 2 || in_w < 2 || width < 2 || height < 2) return fail(ctx, VD3D_ERR_ARG, "image too small");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int W = width, H = height;
+  int r;
+  if ((r = begin_frame(ctx))) return r;
+  launch_set_shifts(ctx->fs, p->fg_shift, p->mg_shift, p->bg_shift, s);
+  ctx->launches += 2;
+  const void *rgb_d, *depth_d;
+  if ((r = copy_in(ctx, ctx->in_rgbf, rgb, sizeof(float) * 3 * (size_t)in_h * in_w, mem, s, &rgb_d))) return r;
+  if ((r = copy_in(ctx, ctx->in_depthf, depth, sizeof(float) * (size_t)in_h * in_w, mem, s, &depth_d))) return r;
+  const float* src_f32 = (const float*)rgb_d;
+  if (in_h != H || in_w != W) {
+    if ((r = ensure(ctx, ctx->frameB, sizeof(float) * 3 * (size_t)W * H))) return r;
+    launch_resize_planar((const float*)rgb_d, 3, in_h, in_w, (float*)ctx->frameB.p, H, W, s);
+    ctx->launches += 1;
+    src_f32 = (const float*)ctx->frameB.p;
+  }
+  uint8_t *l_d = left_bgr, *r_d = right_bgr;
+  size_t eye_bytes = (size_t)W * H * 3;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->eyeL, eye_bytes))) return r;
+    if ((r = ensure(ctx, ctx->eyeR, eye_bytes))) return r;
+    l_d = (uint8_t*)ctx->eyeL.p;
+    r_d = (uint8_t*)ctx->eyeR.p;
+  }
+  CoreIn ci;
+  ci.depth = (const float*)depth_d;
+  ci.sh = in_h;
+  ci.sw = in_w;
+  ci.src_u8 = nullptr;
+  ci.src_pitch = 0;
+  ci.cx0 = ci.cy0 = 0;
+  ci.src_f32 = src_f32;
+  ci.W = W;
+  ci.H = H;
+  ci.p = *p;
+  ci.grade = 0;
+  ci.sat = 1.f;
+  ci.con = 1.f;
+  ci.bri = 0.f;
+  ci.left = l_d;
+  ci.right = r_d;
+  if ((r = run_core(ctx, ci))) return r;
+  if (mem == VD3D_MEM_HOST) {
+    CK(cudaMemcpyAsync(left_bgr, l_d, eye_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(right_bgr, r_d, eye_bytes, cudaMemcpyDeviceToHost, s));
+  }
+  if (shift)
+    CK(cudaMemcpyAsync(shift, ctx->shift.p, sizeof(float) * (size_t)W * H,
+                       mem == VD3D_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s));
+  if (info) {
+    if ((r = fetch_info(ctx, info))) return r;
+  } else {
+    CK(cudaStreamSynchronize(s));
+  }
+  return VD3D_OK;
+}
+
+int vd3d_plan_sizes(int src_w, int src_h, const vd3d_render_params* rp, vd3d_size_plan* o) {
+  if (!rp || !o || src_w < 2 || src_h < 2) return VD3D_ERR_ARG;
+  double target_ratio = rp->aspect_ratio;
+  int cw = src_w, ch = src_h, cx0 = 0, cy0 = 0;
+  double cur = (double)src_w / (double)src_h;
+  if (fabs(cur - target_ratio) > 0.01) {
+    if (cur > target_ratio) {
+      cw = (int)(src_h * target_ratio);
+      cx0 = (src_w - cw) / 2;
+    } else {
+      ch = (int)(src_w / target_ratio);
+      cy0 = (src_h - ch) / 2;
+    }
+  }
+  int rw, rh, pw, ph, outw, outh, tew, teh;
+  int fmt = rp->output_format;
+  if (fmt == VD3D_FMT_VR) return VD3D_ERR_UNSUPPORTED;
+  if (rp->preserve_original_aspect) {
+    // original_video_* default to the FIRST frame tensor's size (pre-crop) (core/render_3d.py:1087-1092)
+    int ow = src_w, oh = src_h;
+    if (rp->original_video_width > 0 && rp->original_video_height > 0) {
+      ow = rp->original_video_width;
+      oh = rp->original_video_height;
+    }
+    rw = ow;
+    rh = oh;
+    if (fmt == VD3D_FMT_FULL_SBS) {
+      pw = rw; ph = rh; outw = rw * 2; outh = rh;
+    } else if (fmt == VD3D_FMT_HALF_SBS) {
+      pw = rw / 2; ph = rh; outw = rw; outh = rh;
+    } else {
+      pw = rw; ph = rh; outw = rw * 2; outh = rh;
+    }
+    tew = pw;
+    teh = ph;
+  } else {
+    rh = rp->output_height;
+    rw = (int)(rh * target_ratio);
+    if (rw % 2 != 0) rw += 1;
+    if (fmt == VD3D_FMT_FULL_SBS) {
+      pw = 1920; ph = 1080; outw = 3840; outh = 1080;
+    } else if (fmt == VD3D_FMT_HALF_SBS) {
+      pw = rw / 2; ph = rh; outw = rw; outh = rh;
+    } else {
+      pw = rw; ph = rh; outw = rw * 2; outh = rh;
+    }
+    tew = pw;
+    teh = (int)(pw / target_ratio);
+    if (teh % 2 != 0) teh += 1;
+  }
+  o->crop_x0 = cx0;
+  o->crop_y0 = cy0;
+  o->crop_w = cw;
+  o->crop_h = ch;
+  o->target_eye_w = tew;
+  o->target_eye_h = teh;
+  o->resized_width = rw;
+  o->resized_height = rh;
+  o->per_eye_w = pw;
+  o->per_eye_h = ph;
+  o->out_width = outw;
+  o->out_height = outh;
+  return VD3D_OK;
+}
+
+// enqueue one loop iteration on ctx->stream; inputs/outputs are DEVICE pointers
+static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* depth_d, int depth_channels,
+                         int src_h, int src_w, const vd3d_render_params* rp, const vd3d_size_plan& pl,
+                         uint8_t* out_d) {
+  cudaStream_t s = ctx->stream;
+  int r;
+  const int tw = pl.target_eye_w, th = pl.target_eye_h;
+  const int W = pl.resized_width, H = pl.resized_height;
+  if (tw < 8 || th < 8 || W < 8 || H < 8) return fail(ctx, VD3D_ERR_ARG, "frame too small");
+  size_t tpx = (size_t)tw * th;
+  if (ctx->tdf_w != tw || ctx->tdf_h != th) {
+    if ((r = ensure(ctx, ctx->tdf, sizeof(float) * tpx))) return r;
+    if ((r = ensure(ctx, ctx->dn0, sizeof(float) * tpx))) return r;
+    if ((r = ensure(ctx, ctx->dn1, sizeof(float) * tpx))) return r;
+    ctx->tdf_w = tw;
+    ctx->tdf_h = th;
+    if ((r = vd3d_reset_state(ctx, VD3D_STATE_CLIP))) return r;
+  }
+  bool ident = (tw == pl.crop_w && th == pl.crop_h && W == tw && H == th);
+  bool need_rgb_s = !ident;
+  if ((r = begin_frame(ctx))) return r;
+  ctx->launches += 2;
+
+  // ---- ingest + TemporalDepthFilter
+  IngestArgs ia;
+  ia.frame = frame_d;
+  ia.depth = depth_d;
+  ia.depth_ch = depth_channels;
+  ia.src_w = src_w;
+  ia.src_h = src_h;
+  ia.cx0 = pl.crop_x0;
+  ia.cy0 = pl.crop_y0;
+  ia.cw = pl.crop_w;
+  ia.ch = pl.crop_h;
+  ia.tw = tw;
+  ia.th = th;
+  ia.tdf = (float*)ctx->tdf.p;
+  ia.rgb_s = nullptr;
+  if (need_rgb_s) {
+    if ((r = ensure(ctx, ctx->rgb_s, sizeof(float) * 3 * tpx))) return r;
+    ia.rgb_s = (float*)ctx->rgb_s.p;
+  }
+  ia.alpha = 0.5f;
+  ia.one_minus_alpha = (float)(1 - 0.5);
+  ia.st = ctx->st;
+  launch_ingest(ia, s);
+  // ---- DepthPercentileEMA(p_lo=.02, p_hi=.98, alpha=.92)
+  uint32_t l0, l1, h0, h1;
+  float wlo, whi;
+  quantile_rank(0.02, (long long)tpx, l0, l1, wlo);
+  quantile_rank(0.98, (long long)tpx, h0, h1, whi);
+  launch_set_ranks(ctx->jm[0].tg, l0, l1, h0, h1, s);
+  SelJob pj = make_job(ctx->jm[0], (const float*)ctx->tdf.p, tw, 0, tw, 0, th, 0, 4, 0, false);
+  launch_select(pj, nullptr, sel_blocks(th), s);
+  launch_fin_pct(pj, wlo, whi, 0.92f, (float)(1 - 0.92), ctx->st, ctx->fs, s);
+  float* dn = (float*)(ctx->frame_parity ? ctx->dn1.p : ctx->dn0.p);
+  const float* dn_prev = (const float*)(ctx->frame_parity ? ctx->dn0.p : ctx->dn1.p);
+  launch_normalize((const float*)ctx->tdf.p, dn, dn_prev, th, tw, ctx->st, ctx->fs, s);
+  SelJob sn = make_job(ctx->jm[1], dn, tw, tw / 5, tw * 4 / 5, th / 5, th * 4 / 5, 1, 1, 1, true);
+  launch_select(sn, nullptr, sel_blocks(th * 4 / 5 - th / 5), s);
+  LoopArgs la;
+  la.fg = rp->fg_shift;
+  la.mg = rp->mg_shift;
+  la.bg = rp->bg_shift;
+  la.ipd = rp->ipd_factor;
+  la.resized_width = W;
+  la.use_floating_window = rp->use_floating_window;
+  la.use_subject_tracking = rp->use_subject_tracking;
+  la.crop_count = (long long)(th * 3 / 4 - th / 4) * (long long)(tw * 3 / 4 - tw / 4);
+  la.npix = (long long)tpx;
+  la.dyn_min = (float)0.90;
+  la.dyn_span = (float)(1.15 - 0.90);
+  launch_fin_norm(sn, la, ctx->st, ctx->fs, s);
+  ctx->launches += 1 + 1 + 6 + 1 + 1 + 6 + 1;
+
+  // ---- pixel_shift_cuda
+  size_t eye_bytes = (size_t)W * H * 3;
+  if ((r = ensure(ctx, ctx->eyeL, eye_bytes))) return r;
+  if ((r = ensure(ctx, ctx->eyeR, eye_bytes))) return r;
+  CoreIn ci;
+  ci.depth = dn;
+  ci.sh = th;
+  ci.sw = tw;
+  ci.src_u8 = nullptr;
+  ci.src_pitch = src_w;
+  ci.cx0 = pl.crop_x0;
+  ci.cy0 = pl.crop_y0;
+  ci.src_f32 = nullptr;
+  if (ident) {
+    ci.src_u8 = frame_d;
+  } else {
+    const float* base = (const float*)ctx->rgb_s.p;
+    if (W == tw && H == th) {
+      ci.src_f32 = base;
+    } else {
+      if ((r = ensure(ctx, ctx->frameB, sizeof(float) * 3 * (size_t)W * H))) return r;
+      launch_resize_planar(base, 3, th, tw, (float*)ctx->frameB.p, H, W, s);
+      ctx->launches += 1;
+      ci.src_f32 = (const float*)ctx->frameB.p;
+    }
+  }
+  ci.W = W;
+  ci.H = H;
+  vd3d_shift_params sp;
+  memset(&sp, 0, sizeof sp);
+  sp.fg_shift = sp.mg_shift = sp.bg_shift = 0.0;  // taken from FrameScalars (set by k_fin_norm)
+  sp.blur_ksize = rp->blur_ksize;
+  sp.feather_strength = rp->feather_strength;
+  sp.max_pixel_shift_percent = rp->max_pixel_shift_percent;
+  sp.parallax_balance = 0.8;  // never forwarded by render_sbs_3d (core/render_3d.py:1284-1331)
+  sp.zero_parallax_strength = rp->zero_parallax_strength;
+  sp.use_subject_tracking = rp->use_subject_tracking;
+  sp.enable_floating_window = rp->use_floating_window;
+  sp.enable_feathering = rp->enable_feathering;
+  sp.enable_edge_masking = rp->enable_edge_masking;
+  sp.convergence_strength = rp->convergence_strength;
+  sp.enable_dynamic_convergence = rp->enable_dynamic_convergence;
+  sp.depth_pop_gamma = 0.85;  // hard-coded at the call site (1299-1305)
+  sp.depth_pop_mid = 0.50;
+  sp.depth_stretch_lo = 0.05;
+  sp.depth_stretch_hi = 0.95;
+  sp.fg_pop_multiplier = 1.20;
+  sp.bg_push_multiplier = 1.10;
+  sp.subject_lock_strength = 1.00;
+  ci.p = sp;
+  bool dof = rp->dof_strength > 0.0;
+  ci.grade = dof ? 0 : 1;
+  ci.sat = (float)rp->color_saturation;
+  ci.con = (float)rp->color_contrast;
+  ci.bri = (float)rp->color_brightness;
+  ci.left = (uint8_t*)ctx->eyeL.p;
+  ci.right = (uint8_t*)ctx->eyeR.p;
+  if ((r = run_core(ctx, ci))) return r;
+
+  const uint8_t* eye_l = (const uint8_t*)ctx->eyeL.p;
+  const uint8_t* eye_r = (const uint8_t*)ctx->eyeR.p;
+  if (dof) {
+    if ((r = ensure_dof_kernels(ctx, rp->dof_strength, 5))) return r;
+    if ((r = ensure(ctx, ctx->eyeL2, eye_bytes))) return r;
+    if ((r = ensure(ctx, ctx->eyeR2, eye_bytes))) return r;
+    DofArgs da;
+    da.src_l = eye_l;
+    da.src_r = eye_r;
+    da.dst_l = (uint8_t*)ctx->eyeL2.p;
+    da.dst_r = (uint8_t*)ctx->eyeR2.p;
+    da.H = H;
+    da.W = W;
+    da.depth = dn;
+    da.dh = th;
+    da.dw = tw;
+    da.focal = 0.f;
+    da.fs = ctx->fs;  // focal comes from the FocalDepthTracker state on the device
+    da.focus_w = (float)(0.35 + 1e-6);
+    da.idx_max = (float)(5 - 1 - 1e-6);
+    da.nlevels = 5;
+    for (int i = 0; i < 8; ++i) {
+      da.ksize[i] = ctx->dof_ksize[i];
+      da.koff[i] = ctx->dof_koff[i];
+    }
+    da.kern = (const float*)ctx->dof_kern.p;
+    da.halo = ctx->dof_halo;
+    da.sat = ci.sat;
+    da.con = ci.con;
+    da.bri = ci.bri;
+    launch_dof(da, 2, s);
+    ctx->launches += 1;
+    eye_l = da.dst_l;
+    eye_r = da.dst_r;
+  }
+  // ---- bars + sharpen + fit + pack
+  FitPlan fp;
+  if ((r = plan_fit(ctx, rp->output_format, W, H, pl.per_eye_w, pl.per_eye_h, fp))) return r;
+  PostArgs pa;
+  pa.left = eye_l;
+  pa.right = eye_r;
+  pa.H = H;
+  pa.W = W;
+  pa.fs = ctx->fs;
+  pa.sharpen = 1;
+  sharpen_coeffs(rp->sharpness_factor, pa.kc, pa.ke);
+  pa.fmt = rp->output_format;
+  pa.per_eye_w = pl.per_eye_w;
+  pa.per_eye_h = pl.per_eye_h;
+  pa.fit_x0 = fp.fit_x0;
+  pa.fit_y0 = fp.fit_y0;
+  pa.fit_w = fp.fit_w;
+  pa.fit_h = fp.fit_h;
+  pa.sx = fp.sx;
+  pa.sy = fp.sy;
+  pa.inv_area = (float)(1.0 / (double)(fp.sx * fp.sy));
+  pa.out = out_d;
+  if (rp->output_format == VD3D_FMT_ANAGLYPH || rp->output_format == VD3D_FMT_INTERLACED) {
+    pa.out_w = pl.per_eye_w;
+    pa.out_h = pl.per_eye_h;
+  } else {
+    pa.out_w = pl.out_width;
+    pa.out_h = pl.out_height;
+  }
+  launch_post(pa, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  ctx->frame_parity ^= 1;
+  return VD3D_OK;
+}
+
+static size_t out_bytes(const vd3d_render_params* rp, const vd3d_size_plan& pl) {
+  if (rp->output_format == VD3D_FMT_ANAGLYPH || rp->output_format == VD3D_FMT_INTERLACED)
+    return (size_t)pl.per_eye_w * pl.per_eye_h * 3;
+  return (size_t)pl.out_width * pl.out_height * 3;
+}
+
+int vd3d_render_frame(vd3d_ctx* ctx, const uint8_t* frame_bgr, const uint8_t* depth, int depth_channels,
+                      int src_h, int src_w, const vd3d_render_params* rp, uint8_t* out_bgr, int mem,
+                      vd3d_frame_info* info) {
+  if (!ctx || !frame_bgr || !depth || !rp || !out_bgr) return fail(ctx, VD3D_ERR_ARG, "null argument");
+  if (depth_channels != 1 && depth_channels != 3) return fail(ctx, VD3D_ERR_ARG, "depth_channels must be 1 or 3");
+  CK(cudaSetDevice(ctx->device));
+  vd3d_size_plan pl;
+  int r = vd3d_plan_sizes(src_w, src_h, rp, &pl);
+  if (r) return fail(ctx, r, "unsupported output format / sizes");
+  cudaStream_t s = ctx->stream;
+  const void *f_d, *d_d;
+  size_t fb = (size_t)src_w * src_h * 3, db = (size_t)src_w * src_h * depth_channels;
+  if ((r = copy_in(ctx, ctx->in_frame[0], frame_bgr, fb, mem, s, &f_d))) return r;
+  if ((r = copy_in(ctx, ctx->in_depth[0], depth, db, mem, s, &d_d))) return r;
+  size_t ob = out_bytes(rp, pl);
+  uint8_t* o_d = out_bgr;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->out_dev[0], ob))) return r;
+    o_d = (uint8_t*)ctx->out_dev[0].p;
+  }
+  if ((r = enqueue_frame(ctx, (const uint8_t*)f_d, (const uint8_t*)d_d, depth_channels, src_h, src_w, rp, pl, o_d)))
+    return r;
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(out_bgr, o_d, ob, cudaMemcpyDeviceToHost, s));
+  if (info) return fetch_info(ctx, info);
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+
+int vd3d_render_clip(vd3d_ctx* ctx, int n, const uint8_t* const* frames, const uint8_t* const* depths,
+                     int depth_channels, int src_h, int src_w, const vd3d_render_params* rp,
+                     uint8_t* const* outs, int mem, vd3d_frame_info* infos) {
+  if (!ctx || !frames || !depths || !rp || !outs || n < 0) return fail(ctx, VD3D_ERR_ARG, "null argument");
+  if (depth_channels != 1 && depth_channels != 3) return fail(ctx, VD3D_ERR_ARG, "depth_channels must be 1 or 3");
+  CK(cudaSetDevice(ctx->device));
+  vd3d_size_plan pl;
+  int r = vd3d_plan_sizes(src_w, src_h, rp, &pl);
+  if (r) return fail(ctx, r, "unsupported output format / sizes");
+  size_t fb = (size_t)src_w * src_h * 3, db = (size_t)src_w * src_h * depth_channels;
+  size_t ob = out_bytes(rp, pl);
+  if (mem == VD3D_MEM_DEVICE) {
+    for (int i = 0; i < n; ++i) {
+      if ((r = enqueue_frame(ctx, frames[i], depths[i], depth_channels, src_h, src_w, rp, pl, outs[i]))) return r;
+      if (infos && (r = fetch_info(ctx, &infos[i]))) return r;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VD3D_OK;
+  }
+  for (int b = 0; b < 2; ++b) {
+    if ((r = ensure(ctx, ctx->in_frame[b], fb))) return r;
+    if ((r = ensure(ctx, ctx->in_depth[b], db))) return r;
+    if ((r = ensure(ctx, ctx->out_dev[b], ob))) return r;
+  }
+  // software pipeline over three streams: H2D(i+1) | kernels(i) | D2H(i-1)
+  for (int i = 0; i < n; ++i) {
+    int b = i & 1;
+    // the staging buffers of slot b are free once frame i-2 finished computing / copying out
+    if (i >= 2) {
+      CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
+    }
+    CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(ctx->in_depth[b].p, depths[i], db, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+    if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+    if ((r = enqueue_frame(ctx, (const uint8_t*)ctx->in_frame[b].p, (const uint8_t*)ctx->in_depth[b].p,
+                           depth_channels, src_h, src_w, rp, pl, (uint8_t*)ctx->out_dev[b].p)))
+      return r;
+    if (infos && (r = fetch_info(ctx, &infos[i]))) return r;
+    CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[b], 0));
+    CK(cudaMemcpyAsync(outs[i], ctx->out_dev[b].p, ob, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->s_d2h));
+  return VD3D_OK;
+}
+
+int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem) {
+  if (!ctx || !src || !dst || h < 2 || w < 2) return fail(ctx, VD3D_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t bytes = (size_t)h * w * 3;
+  const void* s_d;
+  int r;
+  if ((r = copy_in(ctx, ctx->eyeL, src, bytes, mem, s, &s_d))) return r;
+  uint8_t* o_d = dst;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->out_dev[0], bytes))) return r;
+    o_d = (uint8_t*)ctx->out_dev[0].p;
+  }
+  PostArgs pa;
+  memset(&pa, 0, sizeof pa);
+  pa.left = (const uint8_t*)s_d;
+  pa.right = (const uint8_t*)s_d;
+  pa.H = h;
+  pa.W = w;
+  pa.fs = nullptr;
+  pa.sharpen = 1;
+  sharpen_coeffs(factor, pa.kc, pa.ke);
+  pa.fmt = VD3D_FMT_INTERLACED;  // single-eye pass-through layout
+  pa.per_eye_w = w;
+  pa.per_eye_h = h;
+  pa.fit_w = w;
+  pa.fit_h = h;
+  pa.sx = pa.sy = 1;
+  pa.inv_area = 1.f;
+  pa.out = o_d;
+  pa.out_w = w;
+  pa.out_h = h;
+  launch_post(pa, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(dst, o_d, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+
+int vd3d_dof_grade(vd3d_ctx* ctx, const uint8_t* eye_bgr, int h, int w, const float* depth01, int dh, int dw,
+                   double focal, double max_sigma, double sat, double con, double bri, uint8_t* dst, int mem) {
+  if (!ctx || !eye_bgr || !dst || h < 2 || w < 2) return fail(ctx, VD3D_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t bytes = (size_t)h * w * 3;
+  const void *s_d, *dp_d = nullptr;
+  int r;
+  if ((r = copy_in(ctx, ctx->eyeL, eye_bgr, bytes, mem, s, &s_d))) return r;
+  bool dof = max_sigma > 0.0;
+  if (dof) {
+    if (!depth01) return fail(ctx, VD3D_ERR_ARG, "depth required for DOF");
+    if ((r = copy_in(ctx, ctx->in_depthf, depth01, sizeof(float) * (size_t)dh * dw, mem, s, &dp_d))) return r;
+    if ((r = ensure_dof_kernels(ctx, max_sigma, 5))) return r;
+  }
+  uint8_t* o_d = dst;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->out_dev[0], bytes))) return r;
+    o_d = (uint8_t*)ctx->out_dev[0].p;
+  }
+  DofArgs da;
+  memset(&da, 0, sizeof da);
+  da.src_l = da.src_r = (const uint8_t*)s_d;
+  da.dst_l = da.dst_r = o_d;
+  da.H = h;
+  da.W = w;
+  da.depth = (const float*)dp_d;
+  da.dh = dh;
+  da.dw = dw;
+  da.focal = (float)focal;
+  da.focus_w = (float)(0.35 + 1e-6);
+  da.idx_max = (float)(5 - 1 - 1e-6);
+  da.nlevels = dof ? 5 : 1;
+  if (dof) {
+    for (int i = 0; i < 8; ++i) {
+      da.ksize[i] = ctx->dof_ksize[i];
+      da.koff[i] = ctx->dof_koff[i];
+    }
+    da.kern = (const float*)ctx->dof_kern.p;
+    da.halo = ctx->dof_halo;
+  }
+  da.sat = (float)sat;
+  da.con = (float)con;
+  da.bri = (float)bri;
+  launch_dof(da, 1, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(dst, o_d, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+
+}  // extern "C"
