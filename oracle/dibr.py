@@ -375,8 +375,10 @@ def shape_for_pop(d01: np.ndarray, subj: np.float32, p: ShiftParams):
     mid = f32(p.depth_pop_mid)
     centered = ((ds - ss).astype(f32) + mid).astype(f32)
     x = (centered - mid).astype(f32)
-    shaped = ((np.sign(x) * np.power(np.abs(x), f32(p.depth_pop_gamma)).astype(f32)).astype(f32)
-              + mid).astype(f32)
+    # |x|^gamma: the correctly rounded fp32 value (fp64 pow, one rounding); torch's Sleef powf
+    # is within 1 ulp of it
+    pw = np.power(np.abs(x).astype(np.float64), np.float64(f32(p.depth_pop_gamma))).astype(f32)
+    shaped = ((np.sign(x) * pw).astype(f32) + mid).astype(f32)
     return np.clip(shaped, f32(0), f32(1)).astype(f32), lo, hi
 
 
@@ -384,7 +386,8 @@ def edge_suppress(d: np.ndarray, total_shift: np.ndarray, feather: float, thr=0.
     """suppress_artifacts_with_edge_mask (198-216)."""
     g = _grad_mag(d, absval=True)
     z = (((g - f32(thr)).astype(f32) * f32(feather)).astype(f32) * f32(5)).astype(f32)
-    edge = (f32(1) / (f32(1) + np.exp(-z).astype(f32)).astype(f32)).astype(f32)
+    ez = np.exp((-z).astype(np.float64)).astype(f32)  # correctly rounded fp32 exp
+    edge = (f32(1) / (f32(1) + ez).astype(f32)).astype(f32)
     smooth = avg_pool_same((f32(1) - edge).astype(f32), 5)
     return (total_shift * smooth).astype(f32)
 
@@ -416,7 +419,8 @@ def pixel_shift(gs: GlobalState, frame_t: np.ndarray, depth_t: np.ndarray,
     d_sh, lo, hi = shape_for_pop(d, subj_raw, p)
     subj = subject_depth(d_sh)
 
-    fgw = np.clip(np.power((f32(1) - d_sh).astype(f32), f32(1.5)).astype(f32), f32(0), f32(1))
+    omd = (f32(1) - d_sh).astype(f32).astype(np.float64)
+    fgw = np.clip((omd * np.sqrt(omd)).astype(f32), f32(0), f32(1))  # (1-d)^1.5 correctly rounded
     mgw = np.clip((f32(1) - (np.abs((d_sh - f32(p.depth_pop_mid)).astype(f32)) * f32(3)).astype(f32)
                    ).astype(f32), f32(0), f32(1))
     bgw = np.clip(d_sh, f32(0), f32(1))
@@ -492,8 +496,12 @@ def gaussian_kernel1d(ksize: int, sigma: float) -> np.ndarray:
     """torchvision _get_gaussian_kernel1d: pdf on linspace(-(k-1)/2,(k-1)/2,k), normalised."""
     half = (ksize - 1) * 0.5
     x = linspace32(ksize, -half, half)
-    pdf = np.exp((f32(-0.5) * ((x / f32(sigma)).astype(f32) ** 2).astype(f32)).astype(f32)).astype(f32)
-    return (pdf / pdf.sum(dtype=f32)).astype(f32)
+    q = (x / f32(sigma)).astype(f32)
+    pdf = np.exp((f32(-0.5) * (q * q).astype(f32)).astype(f32).astype(np.float64)).astype(f32)
+    tot = f32(0)
+    for v in pdf:  # sequential fp32 sum
+        tot = f32(tot + v)
+    return (pdf / tot).astype(f32)
 
 
 def gaussian_blur(img: np.ndarray, ksize: int, sigma: float) -> np.ndarray:

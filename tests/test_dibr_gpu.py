@@ -75,7 +75,7 @@ def test_pixel_shift_vs_oracle(R, size, pi, kind):
         assert np.abs(s.numpy() - os_).max() <= 1e-5
         for mine, ref in ((l, ol), (r, orr)):
             mx, f0, f1 = u8_diff(mine, ref)
-            assert mx <= 1 and f0 <= 0.005, (size, pi, kind, i, mx, f0)
+            assert mx <= 1 and f0 <= 0.002, (size, pi, kind, i, mx, f0)
 
 
 @pytest.mark.parametrize("name", sorted(PS_CASES))

@@ -656,7 +656,9 @@ __global__ void __launch_bounds__(256) k_shape(float* __restrict__ d, int n, con
   float centered = (ds - fs->st_subj) + mid;
   float x = centered - mid;
   float ax = fabsf(x);
-  float pw = powf(ax, gamma);
+  // |x|^gamma, correctly rounded (fp64 pow then one rounding) so that the CUDA path and the
+  // oracle agree bit for bit; torch's Sleef powf is within 1 ulp of the same value
+  float pw = (float)pow((double)ax, (double)gamma);
   float sg = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
   d[i] = clamp01((sg * pw) + mid);
 }
@@ -689,7 +691,7 @@ __global__ void __launch_bounds__(256) k_shift(const float* __restrict__ d, floa
         float dy = (gy > 0) ? fabsf(c - sd[ty][tx + 1]) : 0.f;
         float g = sqrtf((dx * dx) + (dy * dy));
         float z = ((g - 0.02f) * feather) * 5.0f;
-        float e = 1.0f / (1.0f + expf(-z));
+        float e = 1.0f / (1.0f + (float)exp((double)(-z)));  // exp correctly rounded via fp64
         m = 1.0f - e;
       }
       sm[ty][tx] = m;
@@ -700,7 +702,8 @@ __global__ void __launch_bounds__(256) k_shift(const float* __restrict__ d, floa
   int x = bx + lx, y = by + ly;
   if (x >= W || y >= H) return;
   float v = edge_mask ? sd[ly + 3][lx + 3] : d[(size_t)y * W + x];
-  float fgw = clamp01(powf(1.0f - v, 1.5f));
+  double omv = (double)(1.0f - v);
+  float fgw = clamp01((float)(omv * sqrt(omv)));  // (1-d)^1.5, correctly rounded via fp64
   float mgw = clamp01(1.0f - (fabsf(v - fs->c_mid) * 3.0f));
   float bgw = clamp01(v);
   float raw = (((fgw * fs->c_fg) * fs->c_fgm) + (mgw * fs->c_mg)) + ((bgw * fs->c_bg) * fs->c_bgm);
