@@ -133,6 +133,12 @@ void* vd3d_stream(vd3d_ctx* ctx);
 int vd3d_sync(vd3d_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench: gpu_launches) */
 uint64_t vd3d_launch_count(vd3d_ctx* ctx);
+/* device-side stage timing for the roofline report (CUDA events on the ctx stream):
+ * stage 0 = whole DIBR frame (ingest..pack), 1 = compose kernel, 2 = depth forward.
+ * vd3d_profile_collect synchronises, returns the summed time and sample count since the
+ * last collect, and resets. */
+int vd3d_profile(vd3d_ctx* ctx, int enable);
+int vd3d_profile_collect(vd3d_ctx* ctx, int stage, double* total_ms, int* count);
 /* replay the per-frame kernel sequence from a captured CUDA graph (default 1) */
 int vd3d_set_graphs(vd3d_ctx* ctx, int enable);
 

@@ -81,6 +81,7 @@ SYMBOLS = [
     "vd3d_host_free", "vd3d_stream", "vd3d_sync", "vd3d_launch_count", "vd3d_set_graphs",
     "vd3d_pixel_shift", "vd3d_plan_sizes", "vd3d_render_frame", "vd3d_render_clip",
     "vd3d_sharpen", "vd3d_dof_grade", "vd3d_struct_size",
+    "vd3d_profile", "vd3d_profile_collect",
 ]
 
 _lib = None
@@ -121,6 +122,10 @@ def load():
     lib.vd3d_sync.restype = i
     lib.vd3d_launch_count.argtypes = [vp]
     lib.vd3d_launch_count.restype = C.c_uint64
+    lib.vd3d_profile.argtypes = [vp, i]
+    lib.vd3d_profile.restype = i
+    lib.vd3d_profile_collect.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    lib.vd3d_profile_collect.restype = i
     lib.vd3d_set_graphs.argtypes = [vp, i]
     lib.vd3d_set_graphs.restype = i
     lib.vd3d_pixel_shift.argtypes = [vp, fp, fp, i, i, i, i, C.POINTER(ShiftParams), u8p, u8p, fp, i,

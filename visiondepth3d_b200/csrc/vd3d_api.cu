@@ -62,6 +62,10 @@ struct vd3d_ctx {
   int tdf_w = 0, tdf_h = 0;
   int frame_parity = 0;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  // optional per-stage device timing (bench.py roofline): event pairs on ctx->stream
+  int prof = 0;
+  std::vector<cudaEvent_t> prof_ev[4];  // stage -> [start, stop, start, stop, ...]
+  std::vector<cudaEvent_t> prof_pool;
   // dof kernel cache
   double dof_sigma_cached = -1.0;
   int dof_nlevels = 0, dof_ksize[8] = {0}, dof_koff[8] = {0}, dof_halo = 0;
@@ -79,6 +83,35 @@ namespace {
       return VD3D_ERR_CUDA;                                                         \
     }                                                                               \
   } while (0)
+
+cudaEvent_t prof_event(vd3d_ctx* ctx) {
+  cudaEvent_t e;
+  if (!ctx->prof_pool.empty()) {
+    e = ctx->prof_pool.back();
+    ctx->prof_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+struct ProfScope {  // records start now, stop at destruction
+  vd3d_ctx* c;
+  int stage;
+  ProfScope(vd3d_ctx* ctx, int st) : c(ctx), stage(st) {
+    if (c->prof) {
+      cudaEvent_t e = prof_event(c);
+      cudaEventRecord(e, c->stream);
+      c->prof_ev[stage].push_back(e);
+    }
+  }
+  ~ProfScope() {
+    if (c->prof) {
+      cudaEvent_t e = prof_event(c);
+      cudaEventRecord(e, c->stream);
+      c->prof_ev[stage].push_back(e);
+    }
+  }
+};
 
 int fail(vd3d_ctx* ctx, int code, const char* msg) {
   if (ctx) ctx->err = msg;
@@ -242,7 +275,10 @@ int run_core(vd3d_ctx* ctx, const CoreIn& in) {
   ca.bri = in.bri;
   ca.left = in.left;
   ca.right = in.right;
-  launch_compose(ca, s);
+  {
+    ProfScope ps(ctx, 1);
+    launch_compose(ca, s);
+  }
   ctx->launches += 1;
   CK(cudaGetLastError());
   return VD3D_OK;
@@ -527,6 +563,29 @@ int vd3d_sync(vd3d_ctx* ctx) {
   return VD3D_OK;
 }
 uint64_t vd3d_launch_count(vd3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int vd3d_profile(vd3d_ctx* ctx, int enable) {
+  if (!ctx) return VD3D_ERR_ARG;
+  ctx->prof = enable;
+  return VD3D_OK;
+}
+int vd3d_profile_collect(vd3d_ctx* ctx, int stage, double* total_ms, int* count) {
+  if (!ctx || stage < 0 || stage >= 4 || !total_ms || !count) return VD3D_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  double t = 0;
+  int n = 0;
+  auto& v = ctx->prof_ev[stage];
+  for (size_t i = 0; i + 1 < v.size(); i += 2) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+    t += ms;
+    ++n;
+  }
+  for (cudaEvent_t e : v) ctx->prof_pool.push_back(e);
+  v.clear();
+  *total_ms = t;
+  *count = n;
+  return VD3D_OK;
+}
 int vd3d_set_graphs(vd3d_ctx* ctx, int enable) {
   if (!ctx) return VD3D_ERR_ARG;
   ctx->use_graphs = enable;
@@ -668,6 +727,7 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
                          uint8_t* out_d) {
   cudaStream_t s = ctx->stream;
   int r;
+  ProfScope frame_scope(ctx, 0);
   const int tw = pl.target_eye_w, th = pl.target_eye_h;
   const int W = pl.resized_width, H = pl.resized_height;
   if (tw < 8 || th < 8 || W < 8 || H < 8) return fail(ctx, VD3D_ERR_ARG, "frame too small");
