@@ -180,6 +180,33 @@ int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor,
 int vd3d_dof_grade(vd3d_ctx* ctx, const uint8_t* eye_bgr, int h, int w, const float* depth01, int dh, int dw,
                    double focal, double max_sigma, double sat, double con, double bri, uint8_t* dst, int mem);
 
+/* ---- depth forward (Depth-Anything-V2: DINOv2 ViT + DPT neck/head) ----------
+ * Replaces model.forward inside transformers' depth-estimation pipeline as called by
+ * hf_batch_safe_pipe (core/render_depth.py:1106-1119).  GEMMs / 3x3 convs run on tcgen05
+ * tensor cores (f16 operands, fp32 accumulation in TMEM) fed by TMA. */
+typedef struct vd3d_depth vd3d_depth;
+typedef struct {
+  int32_t hidden, layers, heads; /* 384/12/6, 768/12/12, 1024/24/16 */
+  int32_t taps[4];               /* out_indices of the backbone (1-based layer numbers) */
+  int32_t neck[4];               /* neck_hidden_sizes */
+  int32_t fusion;                /* fusion_hidden_size */
+  int32_t image_h, image_w;      /* processed size, multiples of 14 (518 x 924 for 16:9) */
+} vd3d_depth_config;
+int vd3d_depth_create(const vd3d_depth_config* cfg, void* cuda_stream, vd3d_depth** out);
+void vd3d_depth_destroy(vd3d_depth* e);
+const char* vd3d_depth_last_error(vd3d_depth* e);
+uint64_t vd3d_depth_launch_count(vd3d_depth* e);
+/* upload one prepared weight tensor (names / layouts: visiondepth3d_b200/depth_weights.py) */
+int vd3d_depth_set_tensor(vd3d_depth* e, const char* name, const void* host_data, size_t bytes);
+/* pixel_values f32 [3,image_h,image_w] -> predicted_depth f32 [image_h,image_w] */
+int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_out, int mem);
+/* copy an internal activation buffer to the host (parity triage: "x", "tap0".., "f0".., "fused3") */
+int vd3d_depth_get_buffer(vd3d_depth* e, const char* name, void* host_out, size_t bytes);
+/* unit-test hooks for the tensor-core kernels */
+int vd3d_gemm_f16(vd3d_depth* e, const void* A_f16, const void* B_f16, int M, int N, int K, float* C_host, int bn);
+int vd3d_conv_f16(vd3d_depth* e, const void* in_nhwc_f16, int H, int W, int cin, const void* w_f16, int cout,
+                  int k3, const float* bias, int relu, float* out_host);
+
 #ifdef __cplusplus
 }
 #endif

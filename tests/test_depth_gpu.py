@@ -1,0 +1,85 @@
+"""GPU: the tcgen05 GEMM / implicit-GEMM conv kernels and the Depth-Anything-V2 forward
+against fp32 references (numpy matmul, torch conv2d, oracle/depth.py).
+
+Tolerances: GEMM/conv operands are f16 (10-bit mantissa) with fp32 accumulation, so unit
+kernels are compared with the SAME f16-rounded operands (error = accumulation order only,
+<= 2e-3 relative to the result scale); the full forward is gated at <= 1e-3 max-abs on the
+depth normalised to [0, 1] (north_star tolerance for float intermediates) and <= 1 LSB after
+the reference's min-max -> u8 quantisation (core/render_depth.py:605-611)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from visiondepth3d_b200.depth_engine import DepthEngine
+    return DepthEngine("vits", 70, 98)
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (128, 128, 128), (256, 384, 768), (2443, 1152, 384),
+                                   (100, 200, 72), (2442, 48 + 16, 384), (300, 32, 576), (129, 130, 8)])
+def test_gemm_matches_numpy(eng, shape):
+    M, N, K = shape
+    rng = np.random.default_rng(M * 7 + N)
+    A = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
+    B = (rng.standard_normal((N, K)) * 0.5).astype(np.float16)
+    ref = A.astype(np.float32) @ B.astype(np.float32).T
+    for bn in ((0,) if N < 64 else (0, 64, 32)):
+        out = eng.gemm(A, B, bn)
+        assert np.abs(out - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max()), (shape, bn)
+
+
+@pytest.mark.parametrize("case", [(37, 66, 64, 64, True), (74, 132, 128, 64, True), (19, 33, 64, 128, True),
+                                  (148, 264, 64, 64, True), (40, 50, 64, 32, True), (37, 66, 128, 64, False)])
+def test_conv_matches_torch(eng, case):
+    import torch
+    import torch.nn.functional as F
+    H, W, cin, cout, k3 = case
+    rng = np.random.default_rng(H * W)
+    x = (rng.standard_normal((H, W, cin)) * 0.5).astype(np.float16)
+    w = (rng.standard_normal((cout, cin, 3, 3) if k3 else (cout, cin, 1, 1)) * 0.1).astype(np.float16)
+    b = rng.standard_normal(cout).astype(np.float32)
+    xt = torch.from_numpy(x.astype(np.float32)).permute(2, 0, 1)[None]
+    ref = F.conv2d(xt, torch.from_numpy(w.astype(np.float32)), torch.from_numpy(b), padding=1 if k3 else 0)
+    ref = torch.relu(ref)[0].permute(1, 2, 0).numpy()
+    wk = w.transpose(0, 2, 3, 1).reshape(cout, -1)  # [Cout, tap, Cin]
+    out = eng.conv(x, wk, b, k3=k3, relu=True)
+    assert np.abs(out - ref).max() <= 3e-3 * max(1.0, np.abs(ref).max()), case
+
+
+def _model(name):
+    import torch
+    from transformers import DepthAnythingForDepthEstimation
+    from visiondepth3d_b200.depth_weights import hf_config
+    torch.manual_seed(0)
+    return DepthAnythingForDepthEstimation(hf_config(name)).eval().state_dict()
+
+
+def _depth_u8(d):
+    """convert_depth_to_grayscale tensor path (core/render_depth.py:605-611)."""
+    d = d.astype(np.float32)
+    return ((d - d.min()) / (d.max() - d.min() + np.float32(1e-6)) * 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("name,h,w", [("vits", 70, 98), ("vits", 518, 924), ("vitb", 518, 924)])
+def test_forward_matches_oracle(name, h, w):
+    import torch
+    from oracle import depth as OD
+    from visiondepth3d_b200.depth_engine import DepthEngine
+    from visiondepth3d_b200.depth_weights import CONFIGS
+    sd = _model(name)
+    e = DepthEngine(name, h, w)
+    e.load_state_dict(sd)
+    torch.manual_seed(2)
+    px = torch.randn(3, h, w)
+    with torch.no_grad():
+        ref = OD.forward(sd, CONFIGS[name], px).numpy()
+    out = e.forward(px.numpy())
+    scale = float(ref.max() - ref.min())
+    err = np.abs(out - ref).max() / scale
+    assert err <= 1e-3, (name, h, w, err)
+    du = np.abs(_depth_u8(out).astype(int) - _depth_u8(ref).astype(int))
+    assert du.max() <= 1
+    e.close()

@@ -15,6 +15,8 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path
 UNITS = [
     ("dibr_kernels.cu", ["-fmad=false"]),
     ("vd3d_api.cu", ["-fmad=false"]),
+    ("depth_kernels.cu", []),
+    ("depth_engine.cu", []),
 ]
 
 

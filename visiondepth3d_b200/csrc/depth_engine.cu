@@ -1,0 +1,640 @@
+// depth_engine.cu -- Depth-Anything-V2 (DINOv2 ViT + DPT neck/head) forward as a fixed
+// launch sequence of tcgen05 GEMMs and small fused kernels.  Host side: named device
+// tensors (pushed by the Python loader in HF state_dict terms), TMA tensor maps, buffers.
+//
+// Reference call path: core/render_depth.py:1106-1119 -> transformers pipeline
+// ("depth-estimation") -> DepthAnythingForDepthEstimation.forward (transformers 5.5.0,
+// models/depth_anything/modeling_depth_anything.py; backbone models/dinov2/modeling_dinov2.py).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vd3d.h"
+#include "depth_launch.h"
+#include "umma_gemm.cuh"
+
+using namespace vd3d;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+bool load_encode() {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return false;
+  g_encode = (EncodeTiledFn)fn;
+  return true;
+}
+
+struct DTensor {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct vd3d_depth {
+  vd3d_depth_config cfg;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::map<std::string, DTensor> w;    // weights by name
+  std::map<std::string, DTensor> buf;  // activations by name
+  uint64_t launches = 0;
+  int ph = 0, pw = 0, ntok = 0, npad = 0;
+  bool planned = false;
+};
+
+namespace {
+
+#define DCK(call)                                                                   \
+  do {                                                                              \
+    cudaError_t _e = (call);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      char _b[512];                                                                 \
+      snprintf(_b, sizeof _b, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      e->err = _b;                                                                  \
+      return VD3D_ERR_CUDA;                                                         \
+    }                                                                               \
+  } while (0)
+
+int dfail(vd3d_depth* e, int code, const std::string& msg) {
+  e->err = msg;
+  return code;
+}
+
+int get_buf(vd3d_depth* e, const std::string& name, size_t bytes, void** out, bool zero = false) {
+  DTensor& t = e->buf[name];
+  if (t.bytes < bytes) {
+    if (t.p) DCK(cudaFree(t.p));
+    DCK(cudaMalloc(&t.p, bytes));
+    t.bytes = bytes;
+    zero = true;
+  }
+  if (zero) DCK(cudaMemsetAsync(t.p, 0, t.bytes, e->stream));
+  *out = t.p;
+  return VD3D_OK;
+}
+
+template <typename T>
+int W(vd3d_depth* e, const std::string& name, const T** out, size_t min_count = 0) {
+  auto it = e->w.find(name);
+  if (it == e->w.end()) return dfail(e, VD3D_ERR_STATE, "missing weight tensor: " + name);
+  if (min_count && it->second.bytes < min_count * sizeof(T))
+    return dfail(e, VD3D_ERR_STATE, "weight tensor too small: " + name);
+  *out = (const T*)it->second.p;
+  return VD3D_OK;
+}
+
+// f16 3-D tensor map: dims (d0 inner, d1, d2), strides in ELEMENTS for d1 and d2, box (64, b1, b2)
+int make_map(vd3d_depth* e, CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
+             uint64_t s2, uint32_t b1, uint32_t b2) {
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1 * 2, s2 * 2};
+  cuuint32_t box[3] = {64, b1, b2};
+  cuuint32_t es[3] = {1, 1, 1};
+  if ((strides[0] % 16) || (strides[1] % 16) || ((uintptr_t)ptr % 16))
+    return dfail(e, VD3D_ERR_ARG, "tensor map: pointer / strides must be 16-byte aligned");
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(64,%u,%u)",
+             (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)strides[0], (unsigned long long)strides[1], b1, b2);
+    return dfail(e, VD3D_ERR_CUDA, b);
+  }
+  return VD3D_OK;
+}
+
+GemmArgs base_args(int M, int N, int K, int epi) {
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.epi = epi;
+  g.ldc = N;
+  return g;
+}
+
+int pick_bn(int N) { return N >= 128 ? 128 : (N >= 64 ? 64 : 32); }
+
+// plain GEMM: A [M, K] (lda), B [N, K] (ldb)
+int gemm(vd3d_depth* e, const __half* A, int lda, const __half* B, int ldb, GemmArgs g, int bn = 0) {
+  if (!bn) bn = pick_bn(g.N);
+  CUtensorMap ma, mb;
+  int r;
+  if ((r = make_map(e, &ma, A, g.K, g.M, 1, lda, (uint64_t)lda * g.M, 128, 1))) return r;
+  if ((r = make_map(e, &mb, B, g.K, g.N, 1, ldb, (uint64_t)ldb * g.N, bn, 1))) return r;
+  cudaError_t ce = launch_gemm(bn, ma, mb, g, (g.M + 127) / 128, 1, e->stream);
+  if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(ce));
+  e->launches++;
+  return VD3D_OK;
+}
+
+// batched GEMM over blockIdx.z: A [batch][M, K] (lda, sa), B [batch][N, K] (ldb, sb)
+int gemm_batched(vd3d_depth* e, const __half* A, int lda, uint64_t sa, const __half* B, int ldb, uint64_t sb,
+                 int batch, GemmArgs g, int bn) {
+  CUtensorMap ma, mb;
+  int r;
+  if ((r = make_map(e, &ma, A, g.K, g.M, batch, lda, sa, 128, 1))) return r;
+  if ((r = make_map(e, &mb, B, g.K, g.N, batch, ldb, sb, bn, 1))) return r;
+  cudaError_t ce = launch_gemm(bn, ma, mb, g, (g.M + 127) / 128, batch, e->stream);
+  if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(ce));
+  e->launches++;
+  return VD3D_OK;
+}
+
+void pick_tile(int W, int H, int& tw, int& th) {
+  const int cand[4][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}};
+  long best = -1;
+  for (auto& c : cand) {
+    long cover = (long)((W + c[0] - 1) / c[0]) * c[0] * (long)((H + c[1] - 1) / c[1]) * c[1];
+    if (best < 0 || cover < best) {
+      best = cover;
+      tw = c[0];
+      th = c[1];
+    }
+  }
+}
+
+// conv over an NHWC f16 map [H, W, cin] (3x3 pad 1 when k3, else 1x1); weights [N, taps*cin]
+int conv(vd3d_depth* e, const __half* in, int H, int W, int cin, const __half* wt, bool k3, GemmArgs g, int bn = 0) {
+  if (cin % 64) return dfail(e, VD3D_ERR_ARG, "conv: cin must be a multiple of 64");
+  if (!bn) bn = pick_bn(g.N);
+  int tw, th;
+  pick_tile(W, H, tw, th);
+  g.conv = k3 ? 1 : 2;
+  g.cin = cin;
+  g.imgW = W;
+  g.imgH = H;
+  g.tw = tw;
+  g.th = th;
+  g.M = H * W;
+  g.K = (k3 ? 9 : 1) * cin;
+  CUtensorMap ma, mb;
+  int r;
+  if ((r = make_map(e, &ma, in, cin, W, H, cin, (uint64_t)cin * W, tw, th))) return r;
+  if ((r = make_map(e, &mb, wt, g.K, g.N, 1, g.K, (uint64_t)g.K * g.N, bn, 1))) return r;
+  int m_tiles = ((W + tw - 1) / tw) * ((H + th - 1) / th);
+  cudaError_t ce = launch_gemm(bn, ma, mb, g, m_tiles, 1, e->stream);
+  if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("conv launch: ") + cudaGetErrorString(ce));
+  e->launches++;
+  return VD3D_OK;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" {
+
+int vd3d_depth_create(const vd3d_depth_config* cfg, void* stream, vd3d_depth** out) {
+  if (!cfg || !out) return VD3D_ERR_ARG;
+  *out = nullptr;
+  if (!load_encode()) return VD3D_ERR_CUDA;
+  if (cfg->hidden % 64 || cfg->hidden > 1024 || cfg->hidden / cfg->heads != 64 || cfg->fusion % 64 ||
+      cfg->image_h % 14 || cfg->image_w % 14)
+    return VD3D_ERR_ARG;
+  vd3d_depth* e = new vd3d_depth();
+  e->cfg = *cfg;
+  e->stream = (cudaStream_t)stream;
+  e->ph = cfg->image_h / 14;
+  e->pw = cfg->image_w / 14;
+  e->ntok = e->ph * e->pw + 1;
+  e->npad = round_up(e->ntok, 128);
+  if (e->ntok > 3072) {
+    delete e;
+    return VD3D_ERR_UNSUPPORTED;
+  }
+  *out = e;
+  return VD3D_OK;
+}
+
+void vd3d_depth_destroy(vd3d_depth* e) {
+  if (!e) return;
+  cudaStreamSynchronize(e->stream);
+  for (auto& kv : e->w)
+    if (kv.second.p) cudaFree(kv.second.p);
+  for (auto& kv : e->buf)
+    if (kv.second.p) cudaFree(kv.second.p);
+  delete e;
+}
+
+const char* vd3d_depth_last_error(vd3d_depth* e) { return e ? e->err.c_str() : "null depth engine"; }
+uint64_t vd3d_depth_launch_count(vd3d_depth* e) { return e ? e->launches : 0; }
+
+int vd3d_depth_set_tensor(vd3d_depth* e, const char* name, const void* host_data, size_t bytes) {
+  if (!e || !name || !host_data || !bytes) return VD3D_ERR_ARG;
+  DTensor& t = e->w[name];
+  if (t.p) cudaFree(t.p);
+  t.p = nullptr;
+  DCK(cudaMalloc(&t.p, (bytes + 255) / 256 * 256));
+  t.bytes = bytes;
+  DCK(cudaMemcpy(t.p, host_data, bytes, cudaMemcpyHostToDevice));
+  return VD3D_OK;
+}
+
+int vd3d_depth_get_buffer(vd3d_depth* e, const char* name, void* host_out, size_t bytes) {
+  if (!e || !name || !host_out) return VD3D_ERR_ARG;
+  auto it = e->buf.find(name);
+  if (it == e->buf.end()) return dfail(e, VD3D_ERR_ARG, std::string("no such buffer: ") + name);
+  if (bytes > it->second.bytes) return dfail(e, VD3D_ERR_ARG, "buffer smaller than requested");
+  DCK(cudaStreamSynchronize(e->stream));
+  DCK(cudaMemcpy(host_out, it->second.p, bytes, cudaMemcpyDeviceToHost));
+  return VD3D_OK;
+}
+
+// unit-test hook: C[M,N] f32 = A[M,K] f16 x B[N,K]^T f16 through the tcgen05 kernel
+int vd3d_gemm_f16(vd3d_depth* e, const void* A, const void* B, int M, int N, int K, float* C_host, int bn) {
+  if (!e || !A || !B || !C_host || (K % 8)) return VD3D_ERR_ARG;
+  void *da, *db, *dc;
+  int r;
+  if ((r = get_buf(e, "t.a", (size_t)M * K * 2, &da))) return r;
+  if ((r = get_buf(e, "t.b", (size_t)N * K * 2, &db))) return r;
+  if ((r = get_buf(e, "t.c", (size_t)M * N * 4, &dc, true))) return r;
+  DCK(cudaMemcpyAsync(da, A, (size_t)M * K * 2, cudaMemcpyHostToDevice, e->stream));
+  DCK(cudaMemcpyAsync(db, B, (size_t)N * K * 2, cudaMemcpyHostToDevice, e->stream));
+  GemmArgs g = base_args(M, N, K, EPI_F32);
+  g.out_f32 = (float*)dc;
+  if ((r = gemm(e, (const __half*)da, K, (const __half*)db, K, g, bn))) return r;
+  DCK(cudaMemcpyAsync(C_host, dc, (size_t)M * N * 4, cudaMemcpyDeviceToHost, e->stream));
+  DCK(cudaStreamSynchronize(e->stream));
+  return VD3D_OK;
+}
+
+// unit-test hook: 3x3 (or 1x1) conv on an NHWC f16 map through the implicit-GEMM path
+int vd3d_conv_f16(vd3d_depth* e, const void* in_nhwc, int H, int W, int cin, const void* wt, int cout, int k3,
+                  const float* bias, int relu, float* out_host) {
+  if (!e || !in_nhwc || !wt || !out_host) return VD3D_ERR_ARG;
+  int taps = k3 ? 9 : 1;
+  void *di, *dw, *dob, *dbias = nullptr;
+  int r;
+  if ((r = get_buf(e, "t.ci", (size_t)H * W * cin * 2, &di))) return r;
+  if ((r = get_buf(e, "t.cw", (size_t)cout * taps * cin * 2, &dw))) return r;
+  if ((r = get_buf(e, "t.co", (size_t)H * W * cout * 2, &dob, true))) return r;
+  DCK(cudaMemcpyAsync(di, in_nhwc, (size_t)H * W * cin * 2, cudaMemcpyHostToDevice, e->stream));
+  DCK(cudaMemcpyAsync(dw, wt, (size_t)cout * taps * cin * 2, cudaMemcpyHostToDevice, e->stream));
+  if (bias) {
+    if ((r = get_buf(e, "t.cb", (size_t)cout * 4, &dbias))) return r;
+    DCK(cudaMemcpyAsync(dbias, bias, (size_t)cout * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  GemmArgs g = base_args(H * W, cout, taps * cin, EPI_F16);
+  g.out_f16 = (__half*)dob;
+  g.bias = (const float*)dbias;
+  g.act = relu ? 2 : 0;
+  if ((r = conv(e, (const __half*)di, H, W, cin, (const __half*)dw, k3 != 0, g))) return r;
+  std::vector<__half> tmp((size_t)H * W * cout);
+  DCK(cudaMemcpyAsync(tmp.data(), dob, tmp.size() * 2, cudaMemcpyDeviceToHost, e->stream));
+  DCK(cudaStreamSynchronize(e->stream));
+  for (size_t i = 0; i < tmp.size(); ++i) out_host[i] = __half2float(tmp[i]);
+  return VD3D_OK;
+}
+
+// pixel_values: f32 [3, image_h, image_w] (already resized + normalised); depth_out f32 [image_h, image_w]
+int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_out, int mem) {
+  if (!e || !pixel_values || !depth_out) return VD3D_ERR_ARG;
+  const vd3d_depth_config& c = e->cfg;
+  cudaStream_t s = e->stream;
+  const int D = c.hidden, L = c.layers, Hh = c.heads, F = c.fusion;
+  const int ph = e->ph, pw = e->pw, NT = e->ntok, NP = e->npad, NPATCH = ph * pw;
+  const int IH = c.image_h, IW = c.image_w;
+  const int KPE = 592;
+  int r;
+  char nm[96];
+  // ---- buffers ----
+  void *px_d, *x, *xn, *q, *k, *vt, *S, *P, *attn, *hb, *ape, *depth_d;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = get_buf(e, "px", (size_t)3 * IH * IW * 4, &px_d))) return r;
+    DCK(cudaMemcpyAsync(px_d, pixel_values, (size_t)3 * IH * IW * 4, cudaMemcpyHostToDevice, s));
+  } else {
+    px_d = (void*)pixel_values;
+  }
+  if ((r = get_buf(e, "x", (size_t)NP * D * 4, &x))) return r;
+  if ((r = get_buf(e, "xn", (size_t)NP * D * 2, &xn))) return r;
+  if ((r = get_buf(e, "q", (size_t)Hh * NP * 64 * 2, &q))) return r;
+  if ((r = get_buf(e, "k", (size_t)Hh * NP * 64 * 2, &k))) return r;
+  if ((r = get_buf(e, "vt", (size_t)Hh * 64 * NP * 2, &vt))) return r;
+  if ((r = get_buf(e, "S", (size_t)Hh * NP * NP * 4, &S))) return r;
+  if ((r = get_buf(e, "P", (size_t)Hh * NP * NP * 2, &P))) return r;
+  if ((r = get_buf(e, "attn", (size_t)NP * D * 2, &attn))) return r;
+  if ((r = get_buf(e, "h", (size_t)NP * 4 * D * 2, &hb))) return r;
+  if ((r = get_buf(e, "ape", (size_t)NPATCH * KPE * 2, &ape))) return r;
+  if ((r = get_buf(e, "depth", (size_t)IH * IW * 4, &depth_d))) return r;
+
+  // ---- patch embedding + CLS + position embeddings ----
+  const __half* pe_w;
+  const float *pe_b, *cls, *pos;
+  if ((r = W(e, "pe.w", &pe_w, (size_t)D * KPE)) || (r = W(e, "pe.b", &pe_b, D)) || (r = W(e, "cls", &cls, D)) ||
+      (r = W(e, "pos", &pos, (size_t)NT * D)))
+    return r;
+  launch_patch_im2col((const float*)px_d, IH, IW, ph, pw, (__half*)ape, KPE, s);
+  {
+    GemmArgs g = base_args(NPATCH, D, KPE, EPI_PATCH);
+    g.out_f32 = (float*)x;
+    g.bias = pe_b;
+    g.pos = pos;
+    g.ldc = D;
+    if ((r = gemm(e, (const __half*)ape, KPE, pe_w, KPE, g))) return r;
+  }
+  launch_set_cls((float*)x, cls, pos, D, s);
+  e->launches += 2;
+
+  // ---- transformer blocks ----
+  int tap_idx = 0;
+  for (int l = 0; l < L; ++l) {
+    const float *g1, *b1, *g2, *b2, *bqkv, *bo, *ls1, *bf1, *bf2, *ls2;
+    const __half *wqkv, *wo, *wf1, *wf2;
+    auto nmf = [&](const char* suffix) {
+      snprintf(nm, sizeof nm, "l%d.%s", l, suffix);
+      return std::string(nm);
+    };
+    if ((r = W(e, nmf("ln1.g"), &g1, D)) || (r = W(e, nmf("ln1.b"), &b1, D)) || (r = W(e, nmf("ln2.g"), &g2, D)) ||
+        (r = W(e, nmf("ln2.b"), &b2, D)) || (r = W(e, nmf("qkv.w"), &wqkv, (size_t)3 * D * D)) ||
+        (r = W(e, nmf("qkv.b"), &bqkv, 3 * D)) || (r = W(e, nmf("proj.w"), &wo, (size_t)D * D)) ||
+        (r = W(e, nmf("proj.b"), &bo, D)) || (r = W(e, nmf("ls1"), &ls1, D)) ||
+        (r = W(e, nmf("fc1.w"), &wf1, (size_t)4 * D * D)) || (r = W(e, nmf("fc1.b"), &bf1, 4 * D)) ||
+        (r = W(e, nmf("fc2.w"), &wf2, (size_t)4 * D * D)) || (r = W(e, nmf("fc2.b"), &bf2, D)) ||
+        (r = W(e, nmf("ls2"), &ls2, D)))
+      return r;
+    launch_layernorm((const float*)x, NT, D, g1, b1, (__half*)xn, 0, s);
+    {
+      GemmArgs g = base_args(NT, 3 * D, D, EPI_QKV);
+      g.bias = bqkv;
+      g.q = (__half*)q;
+      g.k = (__half*)k;
+      g.vt = (__half*)vt;
+      g.heads = Hh;
+      g.npad = NP;
+      g.dmodel = D;
+      g.qscale = 0.125f;  // 1/sqrt(64), exact in f16
+      if ((r = gemm(e, (const __half*)xn, D, wqkv, D, g, 128))) return r;
+    }
+    {  // scores = (q / sqrt(d)) k^T, per head
+      GemmArgs g = base_args(NT, NT, 64, EPI_F32);
+      g.out_f32 = (float*)S;
+      g.ldc = NP;
+      g.out_batch_stride = (long long)NP * NP;
+      if ((r = gemm_batched(e, (const __half*)q, 64, (uint64_t)NP * 64, (const __half*)k, 64, (uint64_t)NP * 64, Hh,
+                            g, 128)))
+        return r;
+    }
+    launch_softmax((const float*)S, (__half*)P, NT, Hh, NT, NP, s);
+    {  // context = P v, written head-interleaved into attn [NT, D]
+      GemmArgs g = base_args(NT, 64, NT, EPI_F16);
+      g.out_f16 = (__half*)attn;
+      g.ldc = D;
+      g.out_batch_stride = 64;
+      if ((r = gemm_batched(e, (const __half*)P, NP, (uint64_t)NP * NP, (const __half*)vt, NP, (uint64_t)64 * NP, Hh,
+                            g, 64)))
+        return r;
+    }
+    {
+      GemmArgs g = base_args(NT, D, D, EPI_RESID_LS);
+      g.out_f32 = (float*)x;
+      g.bias = bo;
+      g.ls = ls1;
+      g.ldc = D;
+      if ((r = gemm(e, (const __half*)attn, D, wo, D, g))) return r;
+    }
+    launch_layernorm((const float*)x, NT, D, g2, b2, (__half*)xn, 0, s);
+    {
+      GemmArgs g = base_args(NT, 4 * D, D, EPI_F16);
+      g.out_f16 = (__half*)hb;
+      g.bias = bf1;
+      g.act = 1;
+      g.ldc = 4 * D;
+      if ((r = gemm(e, (const __half*)xn, D, wf1, D, g))) return r;
+    }
+    {
+      GemmArgs g = base_args(NT, D, 4 * D, EPI_RESID_LS);
+      g.out_f32 = (float*)x;
+      g.bias = bf2;
+      g.ls = ls2;
+      g.ldc = D;
+      if ((r = gemm(e, (const __half*)hb, 4 * D, wf2, 4 * D, g))) return r;
+    }
+    e->launches += 3;
+    if (tap_idx < 4 && c.taps[tap_idx] == l + 1) {
+      // backbone output: final LayerNorm applied (apply_layernorm=True), CLS dropped by the neck
+      const float *ng, *nb;
+      if ((r = W(e, "norm.g", &ng, D)) || (r = W(e, "norm.b", &nb, D))) return r;
+      void* tp;
+      snprintf(nm, sizeof nm, "tap%d", tap_idx);
+      if ((r = get_buf(e, nm, (size_t)round_up(NPATCH, 128) * D * 2, &tp))) return r;
+      launch_layernorm((const float*)x, NPATCH, D, ng, nb, (__half*)tp, 1, s);
+      e->launches++;
+      ++tap_idx;
+    }
+  }
+  if (tap_idx != 4) return dfail(e, VD3D_ERR_ARG, "taps must be increasing layer indices <= layers");
+
+  // ---- neck: reassemble + 3x3 conv to the fusion width ----
+  int fh[4], fw[4];
+  void* feat[4];
+  for (int i = 0; i < 4; ++i) {
+    const int C = c.neck[i], CP = round_up(C, 64);
+    const __half *pw_, *cw;
+    const float* pb;
+    snprintf(nm, sizeof nm, "r%d.proj.w", i);
+    if ((r = W(e, nm, &pw_, (size_t)CP * D))) return r;
+    snprintf(nm, sizeof nm, "r%d.proj.b", i);
+    if ((r = W(e, nm, &pb, CP))) return r;
+    void *tp = e->buf[std::string("tap") + char('0' + i)].p, *rp, *rs = nullptr;
+    snprintf(nm, sizeof nm, "r%d.p", i);
+    if ((r = get_buf(e, nm, (size_t)round_up(NPATCH, 128) * CP * 2, &rp))) return r;
+    {
+      GemmArgs g = base_args(NPATCH, CP, D, EPI_F16);
+      g.out_f16 = (__half*)rp;
+      g.bias = pb;
+      g.ldc = CP;
+      if ((r = gemm(e, (const __half*)tp, D, pw_, D, g))) return r;
+    }
+    if (i < 2) {  // ConvTranspose2d(kernel=stride=4 / 2)
+      const int kk = (i == 0) ? 4 : 2;
+      const __half* uw;
+      const float* ub;
+      snprintf(nm, sizeof nm, "r%d.up.w", i);
+      if ((r = W(e, nm, &uw, (size_t)kk * kk * CP * CP))) return r;
+      snprintf(nm, sizeof nm, "r%d.up.b", i);
+      if ((r = W(e, nm, &ub, (size_t)kk * kk * CP))) return r;
+      fh[i] = ph * kk;
+      fw[i] = pw * kk;
+      snprintf(nm, sizeof nm, "r%d.s", i);
+      if ((r = get_buf(e, nm, (size_t)fh[i] * fw[i] * CP * 2, &rs))) return r;
+      GemmArgs g = base_args(NPATCH, kk * kk * CP, CP, EPI_CONVT);
+      g.out_f16 = (__half*)rs;
+      g.bias = ub;
+      g.ct_k = kk;
+      g.ct_cout = CP;
+      g.ct_w = pw;
+      if ((r = gemm(e, (const __half*)rp, CP, uw, CP, g))) return r;
+    } else if (i == 2) {
+      fh[i] = ph;
+      fw[i] = pw;
+      rs = rp;
+    } else {  // Conv2d(3x3, stride 2, pad 1)
+      const __half* dw;
+      const float* db;
+      if ((r = W(e, "r3.down.w", &dw, (size_t)CP * 9 * CP)) || (r = W(e, "r3.down.b", &db, CP))) return r;
+      fh[i] = (ph - 1) / 2 + 1;
+      fw[i] = (pw - 1) / 2 + 1;
+      void* col;
+      if ((r = get_buf(e, "r3.col", (size_t)round_up(fh[i] * fw[i], 128) * 9 * CP * 2, &col))) return r;
+      launch_im2col_s2((const __half*)rp, ph, pw, CP, CP, (__half*)col, fh[i], fw[i], s);
+      e->launches++;
+      if ((r = get_buf(e, "r3.s", (size_t)round_up(fh[i] * fw[i], 128) * CP * 2, &rs))) return r;
+      GemmArgs g = base_args(fh[i] * fw[i], CP, 9 * CP, EPI_F16);
+      g.out_f16 = (__half*)rs;
+      g.bias = db;
+      g.ldc = CP;
+      if ((r = gemm(e, (const __half*)col, 9 * CP, dw, 9 * CP, g))) return r;
+    }
+    snprintf(nm, sizeof nm, "n%d.conv.w", i);
+    if ((r = W(e, nm, &cw, (size_t)F * 9 * CP))) return r;
+    snprintf(nm, sizeof nm, "f%d", i);
+    if ((r = get_buf(e, nm, (size_t)fh[i] * fw[i] * F * 2, &feat[i]))) return r;
+    GemmArgs g = base_args(0, F, 0, EPI_F16);
+    g.out_f16 = (__half*)feat[i];
+    g.ldc = F;
+    if ((r = conv(e, (const __half*)rs, fh[i], fw[i], CP, cw, true, g))) return r;
+  }
+
+  // ---- fusion stage (coarsest first) ----
+  void* fused = nullptr;
+  int ch = 0, cw_ = 0;
+  for (int j = 0; j < 4; ++j) {
+    const int fi = 3 - j;
+    const int Hc = fh[fi], Wc = fw[fi];
+    const size_t n = (size_t)Hc * Wc * F;
+    void *t_relu, *t_mid, *hraw, *hrelu, *yraw, *up, *prj;
+    if ((r = get_buf(e, "fu.relu", n * 2, &t_relu)) || (r = get_buf(e, "fu.mid", n * 2, &t_mid)) ||
+        (r = get_buf(e, "fu.h", n * 2, &hraw)) || (r = get_buf(e, "fu.hrelu", n * 2, &hrelu)) ||
+        (r = get_buf(e, "fu.y", n * 2, &yraw)))
+      return r;
+    auto cv = [&](const char* unit, const char* which, const __half** wv, const float** bv) -> int {
+      snprintf(nm, sizeof nm, "f%d.%s.%s.w", j, unit, which);
+      int rr = W(e, nm, wv, (size_t)F * 9 * F);
+      if (rr) return rr;
+      snprintf(nm, sizeof nm, "f%d.%s.%s.b", j, unit, which);
+      return W(e, nm, bv, F);
+    };
+    const __half *w1, *w2;
+    const float *bb1, *bb2;
+    const __half* hin_raw;
+    if (j == 0) {
+      hin_raw = (const __half*)feat[fi];
+      launch_relu_f16(hin_raw, (__half*)hrelu, n, s);
+      e->launches++;
+    } else {
+      // h = fused + residual_layer1(feat)
+      if ((r = cv("rl1", "c1", &w1, &bb1)) || (r = cv("rl1", "c2", &w2, &bb2))) return r;
+      launch_relu_f16((const __half*)feat[fi], (__half*)t_relu, n, s);
+      e->launches++;
+      GemmArgs g1 = base_args(0, F, 0, EPI_F16);
+      g1.out_f16 = (__half*)t_mid;
+      g1.bias = bb1;
+      g1.act = 2;
+      g1.ldc = F;
+      if ((r = conv(e, (const __half*)t_relu, Hc, Wc, F, w1, true, g1))) return r;
+      // y = conv2(mid) + b2 + feat ; h = y + fused  (two residual adds: second via res on a 1x1-free pass)
+      GemmArgs g2 = base_args(0, F, 0, EPI_F16);
+      g2.out_f16 = (__half*)yraw;
+      g2.bias = bb2;
+      g2.res_f16 = (const __half*)feat[fi];
+      g2.ldc = F;
+      if ((r = conv(e, (const __half*)t_mid, Hc, Wc, F, w2, true, g2))) return r;
+      // h = fused + y ; relu(h) feeds residual_layer2's first conv
+      launch_add_relu_f16((const __half*)fused, (const __half*)yraw, (__half*)hraw, (__half*)hrelu, n, s);
+      e->launches++;
+      hin_raw = (const __half*)hraw;
+    }
+    // residual_layer2
+    if ((r = cv("rl2", "c1", &w1, &bb1)) || (r = cv("rl2", "c2", &w2, &bb2))) return r;
+    {
+      GemmArgs g1 = base_args(0, F, 0, EPI_F16);
+      g1.out_f16 = (__half*)t_mid;
+      g1.bias = bb1;
+      g1.act = 2;
+      g1.ldc = F;
+      if ((r = conv(e, (const __half*)hrelu, Hc, Wc, F, w1, true, g1))) return r;
+      GemmArgs g2 = base_args(0, F, 0, EPI_F16);
+      g2.out_f16 = (__half*)yraw;
+      g2.bias = bb2;
+      g2.res_f16 = hin_raw;
+      g2.ldc = F;
+      if ((r = conv(e, (const __half*)t_mid, Hc, Wc, F, w2, true, g2))) return r;
+    }
+    // upsample (to the next feature's size, or x2 at the end), then 1x1 projection
+    int OH = (j < 3) ? fh[fi - 1] : Hc * 2, OW = (j < 3) ? fw[fi - 1] : Wc * 2;
+    snprintf(nm, sizeof nm, "fu.up%d", j);
+    if ((r = get_buf(e, nm, (size_t)OH * OW * F * 2, &up))) return r;
+    launch_upsample_ac((const __half*)yraw, Hc, Wc, F, (__half*)up, OH, OW, s);
+    e->launches++;
+    const __half* pwt;
+    const float* pbs;
+    snprintf(nm, sizeof nm, "f%d.proj.w", j);
+    if ((r = W(e, nm, &pwt, (size_t)F * F))) return r;
+    snprintf(nm, sizeof nm, "f%d.proj.b", j);
+    if ((r = W(e, nm, &pbs, F))) return r;
+    snprintf(nm, sizeof nm, "fused%d", j);
+    if ((r = get_buf(e, nm, (size_t)round_up(OH * OW, 128) * F * 2, &prj))) return r;
+    GemmArgs g = base_args(OH * OW, F, F, EPI_F16);
+    g.out_f16 = (__half*)prj;
+    g.bias = pbs;
+    g.ldc = F;
+    if ((r = gemm(e, (const __half*)up, F, pwt, F, g))) return r;
+    fused = prj;
+    ch = OH;
+    cw_ = OW;
+  }
+
+  // ---- head ----
+  {
+    const int F2 = round_up(F / 2, 64);
+    const __half *w1, *w2;
+    const float *b1h, *b2h, *w3, *b3;
+    if ((r = W(e, "h.c1.w", &w1, (size_t)F2 * 9 * F)) || (r = W(e, "h.c1.b", &b1h, F2)) ||
+        (r = W(e, "h.c2.w", &w2, (size_t)32 * 9 * F2)) || (r = W(e, "h.c2.b", &b2h, 32)) ||
+        (r = W(e, "h.c3.w", &w3, 32)) || (r = W(e, "h.c3.b", &b3, 1)))
+      return r;
+    void *h1, *h1u;
+    if ((r = get_buf(e, "h1", (size_t)ch * cw_ * F2 * 2, &h1)) || (r = get_buf(e, "h1u", (size_t)IH * IW * F2 * 2, &h1u)))
+      return r;
+    GemmArgs g1 = base_args(0, F2, 0, EPI_F16);
+    g1.out_f16 = (__half*)h1;
+    g1.bias = b1h;
+    g1.ldc = F2;
+    if ((r = conv(e, (const __half*)fused, ch, cw_, F, w1, true, g1))) return r;
+    launch_upsample_ac((const __half*)h1, ch, cw_, F2, (__half*)h1u, IH, IW, s);
+    e->launches++;
+    GemmArgs g2 = base_args(0, 32, 0, EPI_HEAD);
+    g2.out_f32 = (float*)depth_d;
+    g2.bias = b2h;
+    g2.w3 = w3;
+    g2.b3p = b3;
+    if ((r = conv(e, (const __half*)h1u, IH, IW, F2, w2, true, g2, 32))) return r;
+  }
+  DCK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) {
+    DCK(cudaMemcpyAsync(depth_out, depth_d, (size_t)IH * IW * 4, cudaMemcpyDeviceToHost, s));
+    DCK(cudaStreamSynchronize(s));
+  } else if (depth_out != (float*)depth_d) {
+    DCK(cudaMemcpyAsync(depth_out, depth_d, (size_t)IH * IW * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  return VD3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,22 @@
+// depth_launch.h -- launch prototypes of depth_kernels.cu
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vd3d {
+struct GemmArgs;
+void launch_layernorm(const float* x, int rows, int D, const float* g, const float* b, __half* out, int row_off,
+                      cudaStream_t s);
+void launch_softmax(const float* S, __half* P, int rows, int heads, int ncols, int ld, cudaStream_t s);
+void launch_patch_im2col(const float* px, int IH, int IW, int ph, int pw, __half* A, int kpad, cudaStream_t s);
+void launch_set_cls(float* x, const float* cls, const float* pos, int D, cudaStream_t s);
+void launch_im2col_s2(const __half* in, int H, int W, int C, int ldc, __half* out, int OH, int OW, cudaStream_t s);
+void launch_upsample_ac(const __half* in, int H, int W, int C, __half* out, int OH, int OW, cudaStream_t s);
+void launch_add_relu_f16(const __half* a, const __half* b, __half* sum, __half* sum_relu, size_t n, cudaStream_t s);
+void launch_relu_f16(const __half* in, __half* out, size_t n, cudaStream_t s);
+// bn in {32, 64, 128}; grid = (ceil(N/bn), m_tiles, batch)
+cudaError_t launch_gemm(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int m_tiles,
+                        int batch, cudaStream_t s);
+}  // namespace vd3d

@@ -1,0 +1,423 @@
+// umma_gemm.cuh -- hand-written sm_100a GEMM on the 5th-gen tensor cores.
+//
+//   D[M,N] (fp32 in TMEM) = A[M,K] (f16, K-major) x B[N,K]^T (f16, K-major)
+//
+// * operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) into a STAGES-deep
+//   shared-memory ring guarded by mbarriers;
+// * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
+//   accumulating in tensor memory; tcgen05.commit releases ring slots / signals the epilogue;
+// * four epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per
+//   warp) and apply the fused epilogue (bias, GELU, LayerScale+residual, QKV head split with
+//   V transposed, pixel-shuffle for ConvTranspose, ReLU / residual for convs, DPT head).
+// * A can also be an NHWC activation read through a 3-D tensor map (C, W, H): the K loop
+//   then walks the 3x3 taps and channel blocks (implicit GEMM); out-of-image taps are
+//   zero-filled by TMA, so no im2col buffer and no padding copies exist.
+//
+// Used for the Depth-Anything-V2 forward (the dense contraction of the hot path):
+// transformers' DepthAnythingForDepthEstimation as called from core/render_depth.py:1106-1119.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vd3d {
+
+enum Epi : int {
+  EPI_F16 = 0,        // out_f16[m, n] = act(acc + bias) (+ res_f16), optional second relu copy
+  EPI_F32 = 1,        // out_f32[m, n] = acc (+bias)                       (attention scores)
+  EPI_RESID_LS = 2,   // x_f32[m, n] += ls[n] * (acc + bias[n])            (proj / fc2)
+  EPI_QKV = 3,        // split heads: q (x scale), k -> [h][m][64]; v -> vT [h][64][m]
+  EPI_PATCH = 4,      // x_f32[m+1, n] = acc + bias[n] + pos[m+1, n]       (patch embedding)
+  EPI_CONVT = 5,      // ConvTranspose2d(k=s): pixel-shuffle scatter into NHWC f16
+  EPI_HEAD = 6,       // depth[m] = relu(sum_n relu(acc+bias)[n] * w3[n] + b3)
+};
+
+struct GemmArgs {
+  int M, N, K;            // logical sizes (K = total reduction length)
+  int epi;
+  int act;                // 0 none, 1 GELU(erf), 2 ReLU
+  // conv mode (implicit GEMM over a (C, W, H) activation map)
+  int conv;               // 0 = plain GEMM, 1 = 3x3 pad 1, 2 = 1x1 over the same map
+  int cin;                // channels per tap (multiple of 64)
+  int imgW, imgH;         // output == input spatial size (stride 1)
+  int tw, th;             // pixel tile: tw * th == 128
+  // outputs / epilogue operands
+  __half* out_f16;
+  __half* out2_f16;       // optional relu(out) copy (pre-activation consumers)
+  const __half* res_f16;  // optional residual added before the activation
+  float* out_f32;
+  const float* bias;      // [N] or null
+  const float* ls;        // LayerScale lambda [N]
+  const float* pos;       // position embeddings [(M+1), N]
+  int ldc;                // leading dimension of out (elements)
+  long long out_batch_stride;  // per blockIdx.z
+  // EPI_QKV
+  __half* q;
+  __half* k;
+  __half* vt;
+  int heads, npad, dmodel;
+  float qscale;
+  // EPI_CONVT
+  int ct_k, ct_cout, ct_w;  // kernel(=stride), Cout, input width (tokens per row)
+  // EPI_HEAD
+  const float* w3;
+  const float* b3p;
+};
+
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
+}
+
+// K-major, 128B-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(=1, unused for swizzled K-major)<<16 | SBO(1024B>>4)<<32 | version 1<<46 | SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=f16, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) /*c_format f32*/ | (0u << 7) /*a f16*/ | (0u << 10) /*b f16*/ | (0u << 15) | (0u << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 fp32 columns -> 32 registers per thread (thread = lane = accumulator row)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+}  // namespace umma
+
+constexpr int kGemmThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int kBK = 64;            // 64 f16 = 128 B = one swizzle row
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = 128 * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kTotal = STAGES * kStage + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads)
+k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  using S = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * S::kStage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x, m_blk = blockIdx.y, z = blockIdx.z;
+  const int nkb = (g.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmA);
+    umma::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      umma::mbar_init(umma::smem_u32(&full[s]), 1);
+      umma::mbar_init(umma::smem_u32(&empty[s]), 1);
+    }
+    umma::mbar_init(umma::smem_u32(tmem_full), 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) umma::tmem_alloc(umma::smem_u32(tmem_slot), BN);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pixel tile origin for conv mode
+  int px0 = 0, py0 = 0;
+  if (g.conv) {
+    int tiles_x = (g.imgW + g.tw - 1) / g.tw;
+    py0 = (m_blk / tiles_x) * g.th;
+    px0 = (m_blk % tiles_x) * g.tw;
+  }
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        umma::mbar_wait(umma::smem_u32(&empty[s]), ph ^ 1);
+        const uint32_t fb = umma::smem_u32(&full[s]);
+        umma::mbar_expect_tx(fb, S::kStage);
+        const uint32_t sa = umma::smem_u32(smem + s * S::kStage);
+        const uint32_t sb = sa + S::kABytes;
+        if (g.conv == 0) {
+          umma::tma_load_3d(sa, &tmA, fb, kb * kBK, m_blk * 128, z);
+        } else {
+          const int cblocks = g.cin / kBK;
+          const int tap = kb / cblocks, cb = kb % cblocks;
+          int dx = 0, dy = 0;
+          if (g.conv == 1) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          umma::tma_load_3d(sa, &tmA, fb, cb * kBK, px0 + dx, py0 + dy);
+        }
+        umma::tma_load_3d(sb, &tmB, fb, kb * kBK, n_blk * BN, z);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma::make_idesc(BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        umma::mbar_wait(umma::smem_u32(&full[s]), ph);
+        umma::tc_fence_after();
+        const uint32_t sa = umma::smem_u32(smem + s * S::kStage);
+        const uint32_t sb = sa + S::kABytes;
+        const uint64_t da = umma::make_desc(sa);
+        const uint64_t db = umma::make_desc(sb);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
+          umma::mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        }
+        umma::umma_commit(umma::smem_u32(&empty[s]));  // frees this ring slot when the MMAs retire
+      }
+      umma::umma_commit(umma::smem_u32(tmem_full));  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    umma::mbar_wait(umma::smem_u32(tmem_full), 0);
+    umma::tc_fence_after();
+    const int r = q * 32 + lane;  // accumulator row inside the tile
+    int m;                        // logical output row
+    bool row_ok;
+    if (g.conv) {
+      int ly = r / g.tw, lx = r % g.tw;
+      int y = py0 + ly, x = px0 + lx;
+      row_ok = (y < g.imgH) && (x < g.imgW);
+      m = y * g.imgW + x;
+    } else {
+      m = m_blk * 128 + r;
+      row_ok = m < g.M;
+    }
+    float head_acc = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      umma::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      const int n0 = n_blk * BN + c0;
+      if (!row_ok || n0 >= g.N) continue;
+      float a[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]);
+        if (g.bias && (n0 + j) < g.N) t += g.bias[n0 + j];
+        a[j] = t;
+      }
+      const int nvalid = min(32, g.N - n0);
+      switch (g.epi) {
+        case EPI_F16: {
+          size_t o = (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
+          if (g.res_f16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) a[j] += __half2float(g.res_f16[o + j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (g.act == 1) a[j] = umma::gelu_erf(a[j]);
+            if (g.act == 2) a[j] = fmaxf(a[j], 0.f);
+          }
+          if (nvalid == 32 && ((o & 7) == 0)) {
+            uint4* dst = (uint4*)(g.out_f16 + o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __half2 h0 = __floats2half2_rn(a[8 * j + 0], a[8 * j + 1]);
+              __half2 h1 = __floats2half2_rn(a[8 * j + 2], a[8 * j + 3]);
+              __half2 h2 = __floats2half2_rn(a[8 * j + 4], a[8 * j + 5]);
+              __half2 h3 = __floats2half2_rn(a[8 * j + 6], a[8 * j + 7]);
+              uint4 u;
+              u.x = *(uint32_t*)&h0;
+              u.y = *(uint32_t*)&h1;
+              u.z = *(uint32_t*)&h2;
+              u.w = *(uint32_t*)&h3;
+              dst[j] = u;
+            }
+            if (g.out2_f16) {
+              uint4* d2 = (uint4*)(g.out2_f16 + o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __half2 h0 = __floats2half2_rn(fmaxf(a[8 * j + 0], 0.f), fmaxf(a[8 * j + 1], 0.f));
+                __half2 h1 = __floats2half2_rn(fmaxf(a[8 * j + 2], 0.f), fmaxf(a[8 * j + 3], 0.f));
+                __half2 h2 = __floats2half2_rn(fmaxf(a[8 * j + 4], 0.f), fmaxf(a[8 * j + 5], 0.f));
+                __half2 h3 = __floats2half2_rn(fmaxf(a[8 * j + 6], 0.f), fmaxf(a[8 * j + 7], 0.f));
+                uint4 u;
+                u.x = *(uint32_t*)&h0;
+                u.y = *(uint32_t*)&h1;
+                u.z = *(uint32_t*)&h2;
+                u.w = *(uint32_t*)&h3;
+                d2[j] = u;
+              }
+            }
+          } else {
+            for (int j = 0; j < nvalid; ++j) {
+              g.out_f16[o + j] = __float2half_rn(a[j]);
+              if (g.out2_f16) g.out2_f16[o + j] = __float2half_rn(fmaxf(a[j], 0.f));
+            }
+          }
+        } break;
+        case EPI_F32: {
+          float* dst = g.out_f32 + (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
+          if (nvalid == 32 && ((((size_t)m * g.ldc + n0) & 3) == 0) && ((g.out_batch_stride & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+          } else {
+            for (int j = 0; j < nvalid; ++j) dst[j] = a[j];
+          }
+        } break;
+        case EPI_RESID_LS: {
+          float* dst = g.out_f32 + (size_t)m * g.ldc + n0;
+          for (int j = 0; j < nvalid; ++j) dst[j] = dst[j] + g.ls[n0 + j] * a[j];
+        } break;
+        case EPI_QKV: {
+          // n0 is a multiple of 32 and head_dim is 64: the 32 columns lie in one (which, head)
+          const int which = n0 / g.dmodel;
+          const int rem = n0 - which * g.dmodel;
+          const int h = rem >> 6, d0 = rem & 63;
+          if (which < 2) {
+            __half* dst = (which == 0 ? g.q : g.k) + ((size_t)h * g.npad + m) * 64 + d0;
+            const float sc = which == 0 ? g.qscale : 1.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __half2 h0 = __floats2half2_rn(a[8 * j + 0] * sc, a[8 * j + 1] * sc);
+              __half2 h1 = __floats2half2_rn(a[8 * j + 2] * sc, a[8 * j + 3] * sc);
+              __half2 h2 = __floats2half2_rn(a[8 * j + 4] * sc, a[8 * j + 5] * sc);
+              __half2 h3 = __floats2half2_rn(a[8 * j + 6] * sc, a[8 * j + 7] * sc);
+              uint4 u;
+              u.x = *(uint32_t*)&h0;
+              u.y = *(uint32_t*)&h1;
+              u.z = *(uint32_t*)&h2;
+              u.w = *(uint32_t*)&h3;
+              ((uint4*)dst)[j] = u;
+            }
+          } else {
+            __half* dst = g.vt + ((size_t)h * 64 + d0) * g.npad + m;  // transposed: lanes -> consecutive m
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[(size_t)j * g.npad] = __float2half_rn(a[j]);
+          }
+        } break;
+        case EPI_PATCH: {
+          float* dst = g.out_f32 + (size_t)(m + 1) * g.ldc + n0;
+          const float* pe = g.pos + (size_t)(m + 1) * g.ldc + n0;
+          for (int j = 0; j < nvalid; ++j) dst[j] = a[j] + pe[j];
+        } break;
+        case EPI_CONVT: {
+          // n = (dy*k + dx)*Cout + co ; m = y*ct_w + x ; out NHWC [(H*k), (W*k), Cout]
+          const int tap = n0 / g.ct_cout, co = n0 % g.ct_cout;
+          const int dy = tap / g.ct_k, dx = tap % g.ct_k;
+          const int y = m / g.ct_w, x = m % g.ct_w;
+          size_t o = ((size_t)(y * g.ct_k + dy) * (g.ct_w * g.ct_k) + (x * g.ct_k + dx)) * g.ct_cout + co;
+          for (int j = 0; j < nvalid; ++j) g.out_f16[o + j] = __float2half_rn(a[j]);
+        } break;
+        case EPI_HEAD: {
+          for (int j = 0; j < nvalid; ++j) head_acc += fmaxf(a[j], 0.f) * g.w3[n0 + j];
+        } break;
+      }
+    }
+    if (g.epi == EPI_HEAD && row_ok && n_blk == 0) g.out_f32[m] = fmaxf(head_acc + g.b3p[0], 0.f);
+  }
+
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem_base, BN);
+}
+
+}  // namespace vd3d

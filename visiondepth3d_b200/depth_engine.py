@@ -1,0 +1,117 @@
+"""ctypes wrapper of the libvd3d depth engine (include/vd3d.h, "depth forward")."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .depth_weights import CONFIGS, prepare
+
+
+class DepthConfig(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32), ("taps", C.c_int32 * 4),
+                ("neck", C.c_int32 * 4), ("fusion", C.c_int32), ("image_h", C.c_int32), ("image_w", C.c_int32)]
+
+
+def _bind(lib):
+    if getattr(lib, "_depth_bound", False):
+        return
+    vp, i = C.c_void_p, C.c_int
+    lib.vd3d_depth_create.argtypes = [C.POINTER(DepthConfig), vp, C.POINTER(vp)]
+    lib.vd3d_depth_create.restype = i
+    lib.vd3d_depth_destroy.argtypes = [vp]
+    lib.vd3d_depth_destroy.restype = None
+    lib.vd3d_depth_last_error.argtypes = [vp]
+    lib.vd3d_depth_last_error.restype = C.c_char_p
+    lib.vd3d_depth_launch_count.argtypes = [vp]
+    lib.vd3d_depth_launch_count.restype = C.c_uint64
+    lib.vd3d_depth_set_tensor.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+    lib.vd3d_depth_set_tensor.restype = i
+    lib.vd3d_depth_forward.argtypes = [vp, vp, vp, i]
+    lib.vd3d_depth_forward.restype = i
+    lib.vd3d_depth_get_buffer.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+    lib.vd3d_depth_get_buffer.restype = i
+    lib.vd3d_gemm_f16.argtypes = [vp, vp, vp, i, i, i, vp, i]
+    lib.vd3d_gemm_f16.restype = i
+    lib.vd3d_conv_f16.argtypes = [vp, vp, i, i, i, vp, i, i, vp, i, vp]
+    lib.vd3d_conv_f16.restype = i
+    lib._depth_bound = True
+
+
+class DepthEngine:
+    """Depth-Anything-V2 forward on tcgen05 tensor cores.  `cfg` is a key of CONFIGS or a dict."""
+
+    def __init__(self, cfg="vits", image_h=518, image_w=924, ctx=None, device=0):
+        self.lib = _lib.load()
+        _bind(self.lib)
+        self.ctx = ctx or _lib.default_context(device)
+        self.cfg = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
+        self.image_h, self.image_w = int(image_h), int(image_w)
+        c = self.cfg
+        dc = DepthConfig(c["hidden"], c["layers"], c["heads"], (C.c_int32 * 4)(*c["taps"]),
+                         (C.c_int32 * 4)(*c["neck"]), c["fusion"], self.image_h, self.image_w)
+        h = C.c_void_p()
+        rc = self.lib.vd3d_depth_create(C.byref(dc), self.lib.vd3d_stream(self.ctx.h), C.byref(h))
+        if rc != 0:
+            raise _lib.Vd3dError(f"vd3d_depth_create failed ({rc})")
+        self.h = h
+
+    def check(self, rc):
+        if rc != 0:
+            raise _lib.Vd3dError(f"libvd3d depth error {rc}: {self.lib.vd3d_depth_last_error(self.h).decode()}")
+
+    def load_state_dict(self, sd):
+        for name, arr in prepare(sd, self.cfg, self.image_h, self.image_w).items():
+            arr = np.ascontiguousarray(arr)
+            self.check(self.lib.vd3d_depth_set_tensor(self.h, name.encode(), arr.ctypes.data, arr.nbytes))
+
+    def forward(self, pixel_values):
+        """pixel_values: f32 [3, image_h, image_w] numpy (host) or CUDA torch tensor -> depth f32 [H, W]."""
+        try:
+            import torch
+        except Exception:  # pragma: no cover
+            torch = None
+        if torch is not None and isinstance(pixel_values, torch.Tensor) and pixel_values.is_cuda:
+            pv = pixel_values.contiguous().float()
+            out = torch.empty((self.image_h, self.image_w), dtype=torch.float32, device=pv.device)
+            torch.cuda.current_stream().synchronize()
+            self.check(self.lib.vd3d_depth_forward(self.h, pv.data_ptr(), out.data_ptr(), _lib.MEM_DEVICE))
+            self.ctx.check(self.lib.vd3d_sync(self.ctx.h))
+            return out
+        pv = np.ascontiguousarray(np.asarray(pixel_values, dtype=np.float32))
+        out = np.empty((self.image_h, self.image_w), dtype=np.float32)
+        self.check(self.lib.vd3d_depth_forward(self.h, pv.ctypes.data, out.ctypes.data, _lib.MEM_HOST))
+        return out
+
+    def get_buffer(self, name, shape, dtype):
+        out = np.empty(shape, dtype=dtype)
+        self.check(self.lib.vd3d_depth_get_buffer(self.h, name.encode(), out.ctypes.data, out.nbytes))
+        return out
+
+    def gemm(self, A, B, bn=0):
+        A = np.ascontiguousarray(A, dtype=np.float16)
+        B = np.ascontiguousarray(B, dtype=np.float16)
+        M, K = A.shape
+        N = B.shape[0]
+        Cc = np.empty((M, N), dtype=np.float32)
+        self.check(self.lib.vd3d_gemm_f16(self.h, A.ctypes.data, B.ctypes.data, M, N, K, Cc.ctypes.data, bn))
+        return Cc
+
+    def conv(self, x_nhwc, w, bias=None, k3=True, relu=False):
+        x = np.ascontiguousarray(x_nhwc, dtype=np.float16)
+        w = np.ascontiguousarray(w, dtype=np.float16)
+        H, W_, cin = x.shape
+        cout = w.shape[0]
+        out = np.empty((H, W_, cout), dtype=np.float32)
+        b = np.ascontiguousarray(bias, dtype=np.float32) if bias is not None else None
+        self.check(self.lib.vd3d_conv_f16(self.h, x.ctypes.data, H, W_, cin, w.ctypes.data, cout, int(k3),
+                                          b.ctypes.data if b is not None else None, int(relu), out.ctypes.data))
+        return out
+
+    @property
+    def launches(self):
+        return int(self.lib.vd3d_depth_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vd3d_depth_destroy(self.h)
+            self.h = None
