@@ -82,6 +82,9 @@ SYMBOLS = [
     "vd3d_pixel_shift", "vd3d_plan_sizes", "vd3d_render_frame", "vd3d_render_clip",
     "vd3d_sharpen", "vd3d_dof_grade", "vd3d_struct_size",
     "vd3d_profile", "vd3d_profile_collect",
+    # depth forward (bound in depth_engine.py)
+    "vd3d_depth_create", "vd3d_depth_destroy", "vd3d_depth_last_error", "vd3d_depth_launch_count",
+    "vd3d_depth_set_tensor", "vd3d_depth_forward", "vd3d_depth_get_buffer", "vd3d_gemm_f16", "vd3d_conv_f16",
 ]
 
 _lib = None
