@@ -28,6 +28,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# depth forward FLOPs per frame at 518x924 (linears + convs + 4*N^2*d*L attention)
+DEPTH_GFLOP = {"vits": 253.8, "vitb": 775.3, "vitl": 2583.1}
+
 WORKLOADS = {
     # BASELINE.json configs[1]
     "1080p": dict(name="1080p synthetic clip, Depth-Anything-V2-Base, Half-SBS", w=1920, h=1080,
@@ -119,18 +122,45 @@ def oracle_params(wl):
                           preserve_original_aspect=wl["preserve"], zero_parallax_strength=COMMON["zps"])
 
 
-def cpu_port_fps(wl, seconds_budget=20.0, max_frames=4):
-    """Time the oracle port (numpy, one thread) on a bounded sample of the same workload."""
+_CPU_MODEL = {}
+
+
+def cpu_port_fps(wl, seconds_budget=20.0, max_frames=3):
+    """Time the CPU port of the reference path on a bounded sample of the same workload:
+    depth = oracle/depth.py (torch fp32, all host threads; DPT resize via torch bicubic antialias),
+    stereo = oracle/dibr.py (numpy, one thread).  Returns (fps, frames, threads)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import depth as OD
     from oracle import dibr as O
+    from visiondepth3d_b200.depth_weights import CONFIGS, hf_config
     from visiondepth3d_b200.synth import synth_frame
+    torch.set_num_threads(os.cpu_count())
+    if wl["model"] not in _CPU_MODEL:
+        from transformers import DepthAnythingForDepthEstimation
+        torch.manual_seed(0)
+        _CPU_MODEL[wl["model"]] = DepthAnythingForDepthEstimation(hf_config(wl["model"])).eval().state_dict()
+    sd, cfg = _CPU_MODEL[wl["model"]], CONFIGS[wl["model"]]
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+
+    def one(i, gs, cs, rp):
+        fr, _ = synth_frame(i, wl["w"], wl["h"], "noise")
+        with torch.no_grad():
+            t = torch.from_numpy(fr[..., ::-1].copy()).permute(2, 0, 1)[None].float()
+            t = F.interpolate(t, size=(518, 924), mode="bicubic", align_corners=False, antialias=True).round().clamp(0, 255)
+            pv = (t[0] / 255.0 - mean) / std
+            d = OD.forward(sd, cfg, pv)
+            d = F.interpolate(d[None, None], size=(wl["h"], wl["w"]), mode="bicubic", align_corners=False)[0, 0].numpy()
+        d8 = ((d - d.min()) / (d.max() - d.min() + np.float32(1e-6)) * 255).astype(np.uint8)
+        O.render_frame(gs, cs, fr, np.repeat(d8[..., None], 3, axis=2), rp)
+
     gs, cs = O.GlobalState(), O.ClipState()
     rp = oracle_params(wl)
-    fr, dp = synth_frame(0, wl["w"], wl["h"], "noise")
-    O.render_frame(gs, cs, fr, dp, rp)  # warm-up frame (first-frame state init)
+    one(0, gs, cs, rp)  # warm-up frame (first-frame state init)
     n, t0 = 0, time.perf_counter()
     while n < max_frames and (time.perf_counter() - t0) < seconds_budget:
-        fr, dp = synth_frame(n + 1, wl["w"], wl["h"], "noise")
-        O.render_frame(gs, cs, fr, dp, rp)
+        one(n + 1, gs, cs, rp)
         n += 1
     dt = time.perf_counter() - t0
     return n / dt, n
@@ -154,10 +184,10 @@ def run_reference(args, wl, rank, world):
         "impl": "reference", "metric": "end-to-end frames/sec (depth+stereo)", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "stage": "DIBR frame loop (depth forward not in the CPU arm yet)"},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": "port",
-                         "sample": f"{total} frames of the workload, numpy oracle port, 1 thread "
-                                   f"(host has {os.cpu_count()} cores)"},
+        "config": {"workload": wl["name"], "stage": "CPU port: DPT processor + DA-V2 forward (torch fp32) + DIBR loop (numpy)"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{total} frames of the workload; depth forward torch fp32 on {os.cpu_count()} threads, "
+                                   "DIBR numpy port on 1 thread (the reference is Python and cannot travel to the GPU box)"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
     }
@@ -191,8 +221,20 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from visiondepth3d_b200 import _lib
     from visiondepth3d_b200 import render_3d as R
+    from visiondepth3d_b200.depth_engine import DepthEngine
+    from visiondepth3d_b200.depth_weights import hf_config
     ctx = _lib.Context(local_rank)
     lib = ctx.lib
+    # depth model: the architecture BASELINE names, random-init (seed 0) -- no checkpoints offline.
+    # One NCCL broadcast of the weights at init (rank 0 builds them), no per-frame collective.
+    from transformers import DepthAnythingForDepthEstimation
+    torch.manual_seed(0)
+    with torch.device("cpu"):
+        sd = DepthAnythingForDepthEstimation(hf_config(wl["model"])).eval().state_dict()
+    from visiondepth3d_b200.sharding import broadcast_state_dict
+    sd = broadcast_state_dict(sd, src=0, device=torch.device("cuda", local_rank))
+    deng = DepthEngine(wl["model"], 518, 924, ctx=ctx)
+    deng.load_state_dict(sd)
     rp = render_params(R, wl)
     pl = R.plan_sizes(wl["w"], wl["h"], rp)
     oshape = R.output_shape(rp, pl)
@@ -202,12 +244,10 @@ def main():
     # ---- device-resident inputs / outputs (pool larger than L2: 126 MB) ----
     dev = torch.device("cuda", local_rank)
     f_dev = [torch.from_numpy(f).to(dev) for f, _ in pool]
-    d_dev = [torch.from_numpy(d).to(dev) for _, d in pool]
     o_dev = [torch.empty(oshape, dtype=torch.uint8, device=dev) for _ in range(P)]
-    in_bytes = sum(t.numel() for t in f_dev) + sum(t.numel() for t in d_dev)
+    in_bytes = sum(t.numel() for t in f_dev) + sum(t.numel() for t in o_dev)
     # ---- pinned host buffers for the end-to-end arm ----
     f_host = [torch.from_numpy(f).pin_memory() for f, _ in pool]
-    d_host = [torch.from_numpy(d).pin_memory() for _, d in pool]
     o_host = [torch.empty(oshape, dtype=torch.uint8).pin_memory() for _ in range(P)]
     torch.cuda.synchronize()
 
@@ -222,10 +262,10 @@ def main():
         idx = [(i0 + k) % P for k in range(B)]
         step_idx[0] += 1
         if mem == _lib.MEM_DEVICE:
-            a, b, c = ptr_array(f_dev, idx), ptr_array(d_dev, idx), ptr_array(o_dev, idx)
+            a, c = ptr_array(f_dev, idx), ptr_array(o_dev, idx)
         else:
-            a, b, c = ptr_array(f_host, idx), ptr_array(d_host, idx), ptr_array(o_host, idx)
-        ctx.check(lib.vd3d_render_clip(ctx.h, B, a, b, 3, wl["h"], wl["w"], C.byref(rp), c, mem, None))
+            a, c = ptr_array(f_host, idx), ptr_array(o_host, idx)
+        ctx.check(lib.vd3d_render_clip_depth(ctx.h, deng.h, B, a, wl["h"], wl["w"], C.byref(rp), c, mem))
 
     def barrier():
         if world > 1:
@@ -247,7 +287,7 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     lib.vd3d_profile(ctx.h, 1)
-    l0 = ctx.launches
+    l0 = ctx.launches + deng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -255,10 +295,11 @@ def main():
     e1.record(stream)
     barrier()
     ms = reduce_max(e0.elapsed_time(e1))
-    launches = ctx.launches - l0
-    tot0, n0, tot1, n1 = C.c_double(), C.c_int(), C.c_double(), C.c_int()
+    launches = ctx.launches + deng.launches - l0
+    tot0, n0, tot1, n1, tot2, n2 = C.c_double(), C.c_int(), C.c_double(), C.c_int(), C.c_double(), C.c_int()
     lib.vd3d_profile_collect(ctx.h, 0, C.byref(tot0), C.byref(n0))
     lib.vd3d_profile_collect(ctx.h, 1, C.byref(tot1), C.byref(n1))
+    lib.vd3d_profile_collect(ctx.h, 2, C.byref(tot2), C.byref(n2))
     lib.vd3d_profile(ctx.h, 0)
     frames = args.steps * B
     value = world * frames / (ms / 1000.0)
@@ -275,7 +316,7 @@ def main():
     e2e_s = reduce_max(time.perf_counter() - t0)
     clk = clocks.stop()
     e2e_value = world * frames / e2e_s
-    h2d = B * (wl["w"] * wl["h"] * 3 * 2)
+    h2d = B * (wl["w"] * wl["h"] * 3)
     d2h = B * int(np.prod(oshape))
 
     if rank == 0:
@@ -289,11 +330,13 @@ def main():
         line = {
             "metric": "end-to-end frames/sec (depth+stereo)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 GEMM operands, fp32 accumulate; DIBR fp32", "data": "synthetic",
             "config": {
                 "workload": wl["name"], "frames_per_step": B, "frame_pool": P,
-                "l2_policy": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB pool cycled)",
-                "depth_model": None, "stage": "DIBR frame loop only (depth forward engine not built yet)",
+                "l2_policy": f"inputs+outputs larger than L2 ({in_bytes / 1e6:.0f} MB pool cycled)",
+                "depth_model": f"Depth-Anything-V2 {wl['model']} @518x924, random-init seed 0 (no checkpoints offline), "
+                               "f16 tensor-core operands / fp32 accumulate",
+                "stage": "DPT processor + depth forward + min-max u8 handoff in HBM + DIBR frame loop + pack",
                 "params": COMMON, "sharding": "contiguous chunks per rank, independent temporal state per chunk",
             },
             "clocks": clk,
@@ -305,12 +348,18 @@ def main():
             "roofline_stage": {"bound": "hbm", "what": "whole DIBR frame (ingest..pack)", "achieved": stage_gbs,
                                "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,
                                "algorithmic_bytes_per_frame": wl["dibr_bytes"], "avg_frame_ms": stage_ms},
+            "roofline_depth": {"bound": "tensor", "what": "depth stage (processor + DA-V2 forward + post)",
+                               "achieved": DEPTH_GFLOP[wl["model"]] / max(tot2.value / max(n2.value, 1), 1e-9),
+                               "peak": tf_peak, "unit": "TFLOP/s",
+                               "frac": DEPTH_GFLOP[wl["model"]] / max(tot2.value / max(n2.value, 1), 1e-9) / tf_peak,
+                               "algorithmic_gflop_per_frame": DEPTH_GFLOP[wl["model"]],
+                               "avg_frame_ms": tot2.value / max(n2.value, 1)},
         }
         if world == 1 and not args.no_cpu_baseline:
             fps, n = cpu_port_fps(wl)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                                    "sample": f"{n} frames of the workload after 1 warm-up frame, numpy oracle port "
-                                              f"(DIBR loop), 1 thread of {os.cpu_count()} host cores"}
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{n} frames of the workload after 1 warm-up frame; depth forward torch fp32 "
+                                              f"on {os.cpu_count()} threads + DIBR numpy port on 1 thread"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

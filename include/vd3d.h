@@ -22,6 +22,7 @@ extern "C" {
 #endif
 
 typedef struct vd3d_ctx vd3d_ctx;
+typedef struct vd3d_depth vd3d_depth; /* depth-forward engine, see the end of this header */
 
 typedef enum {
   VD3D_OK = 0,
@@ -172,6 +173,12 @@ int vd3d_render_clip(vd3d_ctx* ctx, int n, const uint8_t* const* frames, const u
                      int depth_channels, int src_h, int src_w, const vd3d_render_params* rp,
                      uint8_t* const* outs, int mem, vd3d_frame_info* infos);
 
+/* depth + stereo in one pipelined loop: depth of frame i is inferred on the GPU by `depth`
+ * (vd3d_depth_infer_device) and handed to the DIBR loop in HBM as a 1-channel u8 map -- the
+ * in-memory replacement of the reference's XVID depth-video round trip. */
+int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_t* const* frames, int src_h,
+                           int src_w, const vd3d_render_params* rp, uint8_t* const* outs, int mem);
+
 /* stage entry points (same kernels, exposed for stage-isolated parity tests) */
 /* apply_sharpening (717-732) on u8 BGR [h,w,3] */
 int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem);
@@ -184,7 +191,6 @@ int vd3d_dof_grade(vd3d_ctx* ctx, const uint8_t* eye_bgr, int h, int w, const fl
  * Replaces model.forward inside transformers' depth-estimation pipeline as called by
  * hf_batch_safe_pipe (core/render_depth.py:1106-1119).  GEMMs / 3x3 convs run on tcgen05
  * tensor cores (f16 operands, fp32 accumulation in TMEM) fed by TMA. */
-typedef struct vd3d_depth vd3d_depth;
 typedef struct {
   int32_t hidden, layers, heads; /* 384/12/6, 768/12/12, 1024/24/16 */
   int32_t taps[4];               /* out_indices of the backbone (1-based layer numbers) */
@@ -200,6 +206,15 @@ uint64_t vd3d_depth_launch_count(vd3d_depth* e);
 int vd3d_depth_set_tensor(vd3d_depth* e, const char* name, const void* host_data, size_t bytes);
 /* pixel_values f32 [3,image_h,image_w] -> predicted_depth f32 [image_h,image_w] */
 int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_out, int mem);
+/* the whole depth stage of the reference for one frame: DPT image processor (antialiased
+ * bicubic to image_h x image_w, /255, mean/std) -> forward -> post_process_depth_estimation
+ * (bicubic back to h x w) -> convert_depth_to_grayscale min-max u8 (core/render_depth.py:
+ * 1113-1119, 605-611).  _device: all pointers on the GPU, enqueued without synchronising
+ * (this is what vd3d_render_clip uses for the in-memory depth -> stereo handoff). */
+int vd3d_depth_infer(vd3d_depth* e, const uint8_t* frame_bgr, int h, int w, float* depth_f32, uint8_t* depth_u8,
+                     int invert);
+int vd3d_depth_infer_device(vd3d_depth* e, const uint8_t* frame_bgr_dev, int h, int w, uint8_t* depth_u8_dev,
+                            float* depth_f32_dev_or_null, int invert);
 /* copy an internal activation buffer to the host (parity triage: "x", "tap0".., "f0".., "fused3") */
 int vd3d_depth_get_buffer(vd3d_depth* e, const char* name, void* host_out, size_t bytes);
 /* unit-test hooks for the tensor-core kernels */

@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ x, 
   }
 }
 
-// softmax over keys (scores already scaled: q was multiplied by 1/sqrt(d)); one warp per row
+// softmax over keys (scores already scaled: q was multiplied by 1/sqrt(d)); one warp per row,
+// the row lives in registers (fully unrolled, predicated) so S is read once and P written once
+template <int MAXI>
 __global__ void __launch_bounds__(256) k_softmax(const float* __restrict__ S, __half* __restrict__ P, int rows_per_head,
                                                  int heads, int ncols, int ld) {
   int gr = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -51,23 +53,25 @@ __global__ void __launch_bounds__(256) k_softmax(const float* __restrict__ S, __
   int h = gr / rows_per_head, r = gr % rows_per_head;
   const float* s = S + ((size_t)h * ld + r) * ld;
   __half* p = P + ((size_t)h * ld + r) * ld;
-  float v[96];  // ncols <= 3072
-  int n = (ncols + 31) / 32;
+  float v[MAXI];
   float mx = -INFINITY;
-  for (int i = 0; i < n; ++i) {
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
     int c = lane + 32 * i;
-    v[i] = (c < ncols) ? s[c] : -INFINITY;
+    v[i] = (c < ncols) ? __ldcs(s + c) : -INFINITY;
     mx = fmaxf(mx, v[i]);
   }
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.f;
-  for (int i = 0; i < n; ++i) {
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
     v[i] = (lane + 32 * i < ncols) ? expf(v[i] - mx) : 0.f;
     sum += v[i];
   }
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   float inv = 1.0f / sum;
-  for (int i = 0; i < n; ++i) {
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
     int c = lane + 32 * i;
     if (c < ncols) p[c] = __float2half_rn(v[i] * inv);
   }
@@ -158,6 +162,144 @@ __global__ void __launch_bounds__(256) k_relu_f16(const __half* __restrict__ in,
   ((uint4*)out)[i] = a;
 }
 
+// ---------------------------------------------------------------------------
+// DPT image processor (transformers 5.5 image_processing_dpt.py): antialiased bicubic
+// resize of the uint8 frame (separable, width first, uint8 intermediate, like ATen's
+// _upsample_bicubic2d_aa on uint8), then rescale 1/255 and ImageNet mean/std.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float cubic_aa(float x) {  // a = -0.5 (PIL / ATen antialias filter)
+  const float a = -0.5f;
+  x = fabsf(x);
+  if (x < 1.0f) return ((a + 2.0f) * x - (a + 3.0f)) * x * x + 1.0f;
+  if (x < 2.0f) return (((x - 5.0f) * x + 8.0f) * x - 4.0f) * a;
+  return 0.0f;
+}
+
+// one axis of the antialiased resize on interleaved u8 [rows, in, 3] -> [rows, out, 3] (axis = x)
+// or [in, cols, 3] -> [out, cols, 3] (axis = y)
+__global__ void __launch_bounds__(256) k_resize_aa_u8(const uint8_t* __restrict__ src, int IH, int IW,
+                                                      uint8_t* __restrict__ dst, int OH, int OW, int axis_y,
+                                                      int bgr_to_rgb) {
+  int ox = blockIdx.x * 32 + (threadIdx.x & 31);
+  int oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ox >= OW || oy >= OH) return;
+  const int in_sz = axis_y ? IH : IW, out_sz = axis_y ? OH : OW, o = axis_y ? oy : ox;
+  float scale = (float)in_sz / (float)out_sz;
+  float support = (scale >= 1.0f) ? 2.0f * scale : 2.0f;
+  float invscale = (scale >= 1.0f) ? 1.0f / scale : 1.0f;
+  float center = scale * ((float)o + 0.5f);
+  int xmin = max(0, (int)(center - support + 0.5f));
+  int xmax = min(in_sz, (int)(center + support + 0.5f));
+  float wsum = 0.f, acc[3] = {0.f, 0.f, 0.f};
+  for (int j = xmin; j < xmax; ++j) {
+    float w = cubic_aa(((float)j - center + 0.5f) * invscale);
+    wsum += w;
+    const uint8_t* q = axis_y ? src + ((size_t)j * IW + ox) * 3 : src + ((size_t)oy * IW + j) * 3;
+    acc[0] += w * (float)q[0];
+    acc[1] += w * (float)q[1];
+    acc[2] += w * (float)q[2];
+  }
+  uint8_t* d = dst + ((size_t)oy * OW + ox) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = acc[c] / wsum;
+    int iv = __float2int_rn(v);
+    iv = iv < 0 ? 0 : (iv > 255 ? 255 : iv);
+    d[bgr_to_rgb ? 2 - c : c] = (uint8_t)iv;
+  }
+}
+
+// u8 RGB interleaved [H, W, 3] -> f32 CHW normalised pixel_values
+__global__ void __launch_bounds__(256) k_normalize_px(const uint8_t* __restrict__ rgb, int H, int W,
+                                                      float* __restrict__ px) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= H * W) return;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = (float)rgb[(size_t)i * 3 + c] * (1.0f / 255.0f);
+    px[(size_t)c * H * W + i] = (v - mean[c]) / stdv[c];
+  }
+}
+
+// post_process_depth_estimation: F.interpolate(bicubic, align_corners=False) (a = -0.75, clamped taps)
+__device__ __forceinline__ void cubic_coeffs(float t, float* c) {
+  const float A = -0.75f;
+  float x;
+  x = t + 1.0f;
+  c[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+  x = t;
+  c[1] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+  x = 1.0f - t;
+  c[2] = ((A + 2.0f) * x - (A + 3.0f)) * x * x + 1.0f;
+  x = 2.0f - t;
+  c[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+}
+__device__ __forceinline__ unsigned f2ord(float f) {  // order-preserving float -> uint
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+__global__ void __launch_bounds__(256) k_depth_upsample_minmax(const float* __restrict__ d, int IH, int IW,
+                                                               float* __restrict__ out, int OH, int OW,
+                                                               unsigned* __restrict__ mm) {
+  int ox = blockIdx.x * 32 + (threadIdx.x & 31);
+  int oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  float v = 0.f;
+  bool ok = ox < OW && oy < OH;
+  if (ok) {
+    if (IH == OH && IW == OW) {
+      v = d[(size_t)oy * IW + ox];
+    } else {
+      float sy = (float)IH / (float)OH, sx = (float)IW / (float)OW;
+      float fy = sy * ((float)oy + 0.5f) - 0.5f, fx = sx * ((float)ox + 0.5f) - 0.5f;
+      int iy = (int)floorf(fy), ix = (int)floorf(fx);
+      float cy[4], cx[4];
+      cubic_coeffs(fy - (float)iy, cy);
+      cubic_coeffs(fx - (float)ix, cx);
+      v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int yy = min(max(iy - 1 + j, 0), IH - 1);
+        float r = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int xx = min(max(ix - 1 + i, 0), IW - 1);
+          r += cx[i] * d[(size_t)yy * IW + xx];
+        }
+        v += cy[j] * r;
+      }
+    }
+    out[(size_t)oy * OW + ox] = v;
+  }
+  float lo = ok ? v : INFINITY, hi = ok ? v : -INFINITY;
+  for (int o = 16; o; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomicMin(&mm[0], f2ord(lo));
+    atomicMax(&mm[1], f2ord(hi));
+  }
+}
+__global__ void k_minmax_reset(unsigned* mm) {
+  mm[0] = 0xFFFFFFFFu;
+  mm[1] = 0u;
+}
+// convert_depth_to_grayscale tensor path (core/render_depth.py:605-611): (d-min)/(max-min+1e-6)*255, truncate
+__global__ void __launch_bounds__(256) k_depth_to_u8(const float* __restrict__ d, int n, const unsigned* __restrict__ mm,
+                                                     uint8_t* __restrict__ out, int invert) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
+  float v = ((d[i] - lo) / (hi - lo + 1e-6f)) * 255.0f;
+  int iv = (int)v;
+  iv = iv < 0 ? 0 : (iv > 255 ? 255 : iv);
+  out[i] = (uint8_t)(invert ? 255 - iv : iv);
+}
+
 // sum = a + b ; sum_relu = relu(sum)   (fusion: hidden_state + residual_layer1(residual))
 __global__ void __launch_bounds__(256) k_add_relu_f16(const __half* __restrict__ a, const __half* __restrict__ b,
                                                       __half* __restrict__ sum, __half* __restrict__ sum_relu,
@@ -183,6 +325,20 @@ __global__ void __launch_bounds__(256) k_add_relu_f16(const __half* __restrict__
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
+void launch_preprocess(const uint8_t* frame_bgr, int H, int W, uint8_t* tmp_u8, uint8_t* rgb_u8, float* px, int OH,
+                       int OW, cudaStream_t s) {
+  dim3 g1((OW + 31) / 32, (H + 7) / 8), g2((OW + 31) / 32, (OH + 7) / 8);
+  k_resize_aa_u8<<<g1, 256, 0, s>>>(frame_bgr, H, W, tmp_u8, H, OW, 0, 0);       // width pass
+  k_resize_aa_u8<<<g2, 256, 0, s>>>(tmp_u8, H, OW, rgb_u8, OH, OW, 1, 1);       // height pass (+BGR->RGB)
+  k_normalize_px<<<(OH * OW + 255) / 256, 256, 0, s>>>(rgb_u8, OH, OW, px);
+}
+void launch_depth_post(const float* depth, int IH, int IW, float* up, int OH, int OW, unsigned* mm, uint8_t* out_u8,
+                       int invert, cudaStream_t s) {
+  k_minmax_reset<<<1, 1, 0, s>>>(mm);
+  dim3 g((OW + 31) / 32, (OH + 7) / 8);
+  k_depth_upsample_minmax<<<g, 256, 0, s>>>(depth, IH, IW, up, OH, OW, mm);
+  if (out_u8) k_depth_to_u8<<<(OH * OW + 255) / 256, 256, 0, s>>>(up, OH * OW, mm, out_u8, invert);
+}
 void launch_add_relu_f16(const __half* a, const __half* b, __half* sum, __half* sum_relu, size_t n, cudaStream_t s) {
   size_t n8 = n / 8;
   k_add_relu_f16<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(a, b, sum, sum_relu, n8);
@@ -192,7 +348,12 @@ void launch_layernorm(const float* x, int rows, int D, const float* g, const flo
   k_layernorm<<<(rows + 7) / 8, 256, 0, s>>>(x, rows, D, g, b, out, row_off, 1e-6f);
 }
 void launch_softmax(const float* S, __half* P, int rows, int heads, int ncols, int ld, cudaStream_t s) {
-  k_softmax<<<(rows * heads + 7) / 8, 256, 0, s>>>(S, P, rows, heads, ncols, ld);
+  if (ncols <= 32 * 8)
+    k_softmax<8><<<(rows * heads + 7) / 8, 256, 0, s>>>(S, P, rows, heads, ncols, ld);
+  else if (ncols <= 32 * 80)
+    k_softmax<80><<<(rows * heads + 7) / 8, 256, 0, s>>>(S, P, rows, heads, ncols, ld);
+  else
+    k_softmax<96><<<(rows * heads + 7) / 8, 256, 0, s>>>(S, P, rows, heads, ncols, ld);
 }
 void launch_patch_im2col(const float* px, int IH, int IW, int ph, int pw, __half* A, int kpad, cudaStream_t s) {
   int total = ph * pw * 588;

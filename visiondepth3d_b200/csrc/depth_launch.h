@@ -14,6 +14,12 @@ void launch_patch_im2col(const float* px, int IH, int IW, int ph, int pw, __half
 void launch_set_cls(float* x, const float* cls, const float* pos, int D, cudaStream_t s);
 void launch_im2col_s2(const __half* in, int H, int W, int C, int ldc, __half* out, int OH, int OW, cudaStream_t s);
 void launch_upsample_ac(const __half* in, int H, int W, int C, __half* out, int OH, int OW, cudaStream_t s);
+// DPT image processor: BGR u8 [H,W,3] -> pixel_values f32 [3,OH,OW] (3 launches)
+void launch_preprocess(const uint8_t* frame_bgr, int H, int W, uint8_t* tmp_u8, uint8_t* rgb_u8, float* px, int OH,
+                       int OW, cudaStream_t s);
+// bicubic to (OH,OW) + min/max (+ u8 quantisation when out_u8 != null) (2-3 launches)
+void launch_depth_post(const float* depth, int IH, int IW, float* up, int OH, int OW, unsigned* mm, uint8_t* out_u8,
+                       int invert, cudaStream_t s);
 void launch_add_relu_f16(const __half* a, const __half* b, __half* sum, __half* sum_relu, size_t n, cudaStream_t s);
 void launch_relu_f16(const __half* in, __half* out, size_t n, cudaStream_t s);
 // bn in {32, 64, 128}; grid = (ceil(N/bn), m_tiles, batch)

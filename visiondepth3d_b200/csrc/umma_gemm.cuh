@@ -296,13 +296,24 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n0 = n_blk * BN + c0;
       if (!row_ok || n0 >= g.N) continue;
       float a[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]);
-        if (g.bias && (n0 + j) < g.N) t += g.bias[n0 + j];
-        a[j] = t;
-      }
       const int nvalid = min(32, g.N - n0);
+      if (g.bias && nvalid == 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 b4 = *(const float4*)(g.bias + n0 + 4 * j);
+          a[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+          a[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+          a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+          a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = __uint_as_float(v[j]);
+          if (g.bias && j < nvalid) t += g.bias[n0 + j];
+          a[j] = t;
+        }
+      }
       switch (g.epi) {
         case EPI_F16: {
           size_t o = (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
@@ -365,7 +376,20 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } break;
         case EPI_RESID_LS: {
           float* dst = g.out_f32 + (size_t)m * g.ldc + n0;
-          for (int j = 0; j < nvalid; ++j) dst[j] = dst[j] + g.ls[n0 + j] * a[j];
+          if (nvalid == 32 && ((((size_t)m * g.ldc + n0) & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 x4 = ((float4*)dst)[j];
+              float4 l4 = *(const float4*)(g.ls + n0 + 4 * j);
+              x4.x += l4.x * a[4 * j + 0];
+              x4.y += l4.y * a[4 * j + 1];
+              x4.z += l4.z * a[4 * j + 2];
+              x4.w += l4.w * a[4 * j + 3];
+              ((float4*)dst)[j] = x4;
+            }
+          } else {
+            for (int j = 0; j < nvalid; ++j) dst[j] = dst[j] + g.ls[n0 + j] * a[j];
+          }
         } break;
         case EPI_QKV: {
           // n0 is a multiple of 32 and head_dim is 64: the 32 columns lie in one (which, head)

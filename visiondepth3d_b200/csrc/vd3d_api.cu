@@ -1011,6 +1011,55 @@ int vd3d_render_clip(vd3d_ctx* ctx, int n, const uint8_t* const* frames, const u
   return VD3D_OK;
 }
 
+int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_t* const* frames, int src_h,
+                           int src_w, const vd3d_render_params* rp, uint8_t* const* outs, int mem) {
+  if (!ctx || !depth || !frames || !rp || !outs || n < 0) return fail(ctx, VD3D_ERR_ARG, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  vd3d_size_plan pl;
+  int r = vd3d_plan_sizes(src_w, src_h, rp, &pl);
+  if (r) return fail(ctx, r, "unsupported output format / sizes");
+  size_t fb = (size_t)src_w * src_h * 3, db = (size_t)src_w * src_h;
+  size_t ob = out_bytes(rp, pl);
+  for (int b = 0; b < 2; ++b) {
+    if ((r = ensure(ctx, ctx->in_depth[b], db))) return r;
+    if (mem == VD3D_MEM_HOST) {
+      if ((r = ensure(ctx, ctx->in_frame[b], fb))) return r;
+      if ((r = ensure(ctx, ctx->out_dev[b], ob))) return r;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    int b = i & 1;
+    const uint8_t* f_d = frames[i];
+    uint8_t* o_d = outs[i];
+    if (mem == VD3D_MEM_HOST) {
+      if (i >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
+      CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyHostToDevice, ctx->s_h2d));
+      CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+      f_d = (const uint8_t*)ctx->in_frame[b].p;
+      o_d = (uint8_t*)ctx->out_dev[b].p;
+    }
+    {
+      ProfScope ps(ctx, 2);
+      if ((r = vd3d_depth_infer_device(depth, f_d, src_h, src_w, (uint8_t*)ctx->in_depth[b].p, nullptr, 0))) {
+        ctx->err = std::string("depth engine: ") + vd3d_depth_last_error(depth);
+        return r;
+      }
+    }
+    if ((r = enqueue_frame(ctx, f_d, (const uint8_t*)ctx->in_depth[b].p, 1, src_h, src_w, rp, pl, o_d))) return r;
+    if (mem == VD3D_MEM_HOST) {
+      CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[b], 0));
+      CK(cudaMemcpyAsync(outs[i], ctx->out_dev[b].p, ob, cudaMemcpyDeviceToHost, ctx->s_d2h));
+      CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->s_d2h));
+  return VD3D_OK;
+}
+
 int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem) {
   if (!ctx || !src || !dst || h < 2 || w < 2) return fail(ctx, VD3D_ERR_ARG, "bad argument");
   CK(cudaSetDevice(ctx->device));

@@ -34,6 +34,10 @@ def _bind(lib):
     lib.vd3d_gemm_f16.restype = i
     lib.vd3d_conv_f16.argtypes = [vp, vp, i, i, i, vp, i, i, vp, i, vp]
     lib.vd3d_conv_f16.restype = i
+    lib.vd3d_depth_infer.argtypes = [vp, vp, i, i, vp, vp, i]
+    lib.vd3d_depth_infer.restype = i
+    lib.vd3d_depth_infer_device.argtypes = [vp, vp, i, i, vp, vp, i]
+    lib.vd3d_depth_infer_device.restype = i
     lib._depth_bound = True
 
 
@@ -81,6 +85,16 @@ class DepthEngine:
         out = np.empty((self.image_h, self.image_w), dtype=np.float32)
         self.check(self.lib.vd3d_depth_forward(self.h, pv.ctypes.data, out.ctypes.data, _lib.MEM_HOST))
         return out
+
+    def infer(self, frame_bgr, invert=False):
+        """BGR u8 [h,w,3] -> (predicted_depth f32 [h,w] resized to the frame, min-max u8 [h,w])."""
+        f = np.ascontiguousarray(frame_bgr, dtype=np.uint8)
+        h, w = f.shape[:2]
+        d32 = np.empty((h, w), dtype=np.float32)
+        d8 = np.empty((h, w), dtype=np.uint8)
+        self.check(self.lib.vd3d_depth_infer(self.h, f.ctypes.data, h, w, d32.ctypes.data, d8.ctypes.data,
+                                             int(bool(invert))))
+        return d32, d8
 
     def get_buffer(self, name, shape, dtype):
         out = np.empty(shape, dtype=dtype)

@@ -1,0 +1,94 @@
+"""Drop-in for the hot-path surface of the reference's core/render_depth.py: the `pipe`
+callable protocol and the depth -> uint8 normalisation, backed by the libvd3d depth engine
+(Depth-Anything-V2 on tcgen05 tensor cores).  GUI, ONNX, Marigold, DepthCrafter and the
+letterbox tracker are outside the B200 hot path.
+
+Protocol kept (core/render_depth.py:1113-1119, consumers 201-268 and 1894-1917):
+    pipe(images: list[PIL.Image], inference_size: (W, H) | None) -> list[{"predicted_depth": Tensor[h, w]}]
+with `predicted_depth` already resized (bicubic) to the PIL image size, as
+transformers' DepthEstimationPipeline.postprocess does.
+"""
+import numpy as np
+
+from .depth_engine import DepthEngine
+from .depth_weights import CONFIGS, hf_config
+
+try:
+    import torch
+    torch.set_grad_enabled(False)  # the reference does this at import (core/render_depth.py:42)
+except Exception:  # pragma: no cover
+    torch = None
+
+# module globals the reference's callers read (core/render_depth.py:34-36, 992)
+pipe = None
+pipe_type = None
+_engine = None
+
+# the three checkpoints of the hot path (core/render_depth.py:695-697)
+supported_models = {
+    "Depth Anything V2 Small": ("depth-anything/Depth-Anything-V2-Small-hf", "vits"),
+    "Depth Anything V2 Base": ("depth-anything/Depth-Anything-V2-Base-hf", "vitb"),
+    "Depth Anything V2 Large": ("depth-anything/Depth-Anything-V2-Large-hf", "vitl"),
+}
+
+
+def _processed_size(width, height, target=518, multiple=14):
+    """DPTImageProcessor: keep_aspect_ratio, ensure_multiple_of=14 (image_processing_dpt.py)."""
+    sh, sw = target / height, target / width
+    if abs(1 - sw) < abs(1 - sh):
+        sh = sw
+    else:
+        sw = sh
+    rnd = lambda v: max(multiple, int(round(v / multiple) * multiple))  # noqa: E731
+    return rnd(sh * height), rnd(sw * width)
+
+
+def load_depth_model(arch="vits", state_dict=None, width=1920, height=1080, seed=0):
+    """Build the engine for frames of (width, height).  `state_dict` uses HF
+    DepthAnythingForDepthEstimation naming (e.g. from a local safetensors checkpoint);
+    without one a random-init model (torch.manual_seed(seed)) is used -- there is no network
+    and the reference ships no weights."""
+    global pipe, pipe_type, _engine
+    if state_dict is None:
+        from transformers import DepthAnythingForDepthEstimation
+        torch.manual_seed(seed)
+        state_dict = DepthAnythingForDepthEstimation(hf_config(arch)).eval().state_dict()
+    ih, iw = _processed_size(width, height)
+    _engine = DepthEngine(arch, ih, iw)
+    _engine.load_state_dict(state_dict)
+    pipe = hf_batch_safe_pipe
+    pipe_type = "hf"
+    return pipe, {"arch": arch, "processed_size": (ih, iw), "config": CONFIGS[arch]}
+
+
+def hf_batch_safe_pipe(images, inference_size=None):
+    """core/render_depth.py:1113-1119."""
+    if _engine is None:
+        raise RuntimeError("no depth model loaded: call load_depth_model() first")
+    if not isinstance(images, (list, tuple)):
+        images = [images]
+    out = []
+    for img in images:
+        if inference_size is not None:
+            from PIL import Image
+            img = img.resize(tuple(inference_size), Image.BICUBIC)  # (1819-1821)
+        rgb = np.asarray(img.convert("RGB"), dtype=np.uint8)
+        d32, _ = _engine.infer(np.ascontiguousarray(rgb[..., ::-1]))
+        out.append({"predicted_depth": torch.from_numpy(d32) if torch is not None else d32})
+    return out
+
+
+def depth_u8_from_frame(frame_bgr, invert=False):
+    """frame -> pipe -> convert_depth_to_grayscale in one GPU pass (u8 [h, w])."""
+    if _engine is None:
+        raise RuntimeError("no depth model loaded: call load_depth_model() first")
+    return _engine.infer(frame_bgr, invert=invert)[1]
+
+
+def convert_depth_to_grayscale(depth):
+    """core/render_depth.py:585-611 (tensor path): per-frame min-max -> uint8, truncating.
+    Host helper for callers holding a CPU tensor; the frame path does this on the GPU."""
+    d = depth.detach().cpu().numpy() if hasattr(depth, "detach") else np.asarray(depth)
+    d = d.astype(np.float32)
+    lo, hi = d.min(), d.max()
+    return ((d - lo) / (hi - lo + np.float32(1e-6)) * 255).astype(np.uint8)
