@@ -125,7 +125,7 @@ def oracle_params(wl):
 _CPU_MODEL = {}
 
 
-def cpu_port_fps(wl, seconds_budget=20.0, max_frames=3):
+def cpu_port_fps(wl, seconds_budget=15.0, max_frames=2):
     """Time the CPU port of the reference path on a bounded sample of the same workload:
     depth = oracle/depth.py (torch fp32, all host threads; DPT resize via torch bicubic antialias),
     stereo = oracle/dibr.py (numpy, one thread).  Returns (fps, frames, threads)."""
@@ -135,7 +135,7 @@ def cpu_port_fps(wl, seconds_budget=20.0, max_frames=3):
     from oracle import dibr as O
     from visiondepth3d_b200.depth_weights import CONFIGS, hf_config
     from visiondepth3d_b200.synth import synth_frame
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(32, os.cpu_count()))
     if wl["model"] not in _CPU_MODEL:
         from transformers import DepthAnythingForDepthEstimation
         torch.manual_seed(0)
@@ -175,7 +175,7 @@ def run_reference(args, wl, rank, world):
     per_step = []
     total = 0
     for s in range(args.warmup + args.steps):
-        fps, n = cpu_port_fps(wl, seconds_budget=max(5.0, 60.0 / (args.warmup + args.steps)), max_frames=2)
+        fps, n = cpu_port_fps(wl, seconds_budget=1.0, max_frames=1)
         if s >= args.warmup:
             per_step.append(fps)
             total += n

@@ -376,20 +376,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } break;
         case EPI_RESID_LS: {
           float* dst = g.out_f32 + (size_t)m * g.ldc + n0;
-          if (nvalid == 32 && ((((size_t)m * g.ldc + n0) & 3) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 x4 = ((float4*)dst)[j];
-              float4 l4 = *(const float4*)(g.ls + n0 + 4 * j);
-              x4.x += l4.x * a[4 * j + 0];
-              x4.y += l4.y * a[4 * j + 1];
-              x4.z += l4.z * a[4 * j + 2];
-              x4.w += l4.w * a[4 * j + 3];
-              ((float4*)dst)[j] = x4;
-            }
-          } else {
-            for (int j = 0; j < nvalid; ++j) dst[j] = dst[j] + g.ls[n0 + j] * a[j];
-          }
+          for (int j = 0; j < nvalid; ++j) dst[j] = dst[j] + g.ls[n0 + j] * a[j];
         } break;
         case EPI_QKV: {
           // n0 is a multiple of 32 and head_dim is 64: the 32 columns lie in one (which, head)
