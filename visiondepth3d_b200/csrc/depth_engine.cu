@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -53,6 +54,7 @@ struct vd3d_depth {
   uint64_t launches = 0;
   int ph = 0, pw = 0, ntok = 0, npad = 0;
   bool planned = false;
+  bool flash = true;  // fused attention kernel (VD3D_FLASH=0 selects the 3-kernel path)
 };
 
 namespace {
@@ -215,6 +217,7 @@ int vd3d_depth_create(const vd3d_depth_config* cfg, void* stream, vd3d_depth** o
   e->pw = cfg->image_w / 14;
   e->ntok = e->ph * e->pw + 1;
   e->npad = round_up(e->ntok, 128);
+  if (const char* f = getenv("VD3D_FLASH")) e->flash = atoi(f) != 0;
   if (e->ntok > 3072) {
     delete e;
     return VD3D_ERR_UNSUPPORTED;
@@ -327,8 +330,11 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
   if ((r = get_buf(e, "q", (size_t)Hh * NP * 64 * 2, &q))) return r;
   if ((r = get_buf(e, "k", (size_t)Hh * NP * 64 * 2, &k))) return r;
   if ((r = get_buf(e, "vt", (size_t)Hh * 64 * NP * 2, &vt))) return r;
-  if ((r = get_buf(e, "S", (size_t)Hh * NP * NP * 4, &S))) return r;
-  if ((r = get_buf(e, "P", (size_t)Hh * NP * NP * 2, &P))) return r;
+  S = P = nullptr;
+  if (!e->flash) {
+    if ((r = get_buf(e, "S", (size_t)Hh * NP * NP * 4, &S))) return r;
+    if ((r = get_buf(e, "P", (size_t)Hh * NP * NP * 2, &P))) return r;
+  }
   if ((r = get_buf(e, "attn", (size_t)NP * D * 2, &attn))) return r;
   if ((r = get_buf(e, "h", (size_t)NP * 4 * D * 2, &hb))) return r;
   if ((r = get_buf(e, "ape", (size_t)NPATCH * KPE * 2, &ape))) return r;
@@ -382,24 +388,36 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
       g.qscale = 0.125f;  // 1/sqrt(64), exact in f16
       if ((r = gemm(e, (const __half*)xn, D, wqkv, D, g, 128))) return r;
     }
-    {  // scores = (q / sqrt(d)) k^T, per head
-      GemmArgs g = base_args(NT, NT, 64, EPI_F32);
-      g.out_f32 = (float*)S;
-      g.ldc = NP;
-      g.out_batch_stride = (long long)NP * NP;
-      if ((r = gemm_batched(e, (const __half*)q, 64, (uint64_t)NP * 64, (const __half*)k, 64, (uint64_t)NP * 64, Hh,
-                            g, 128)))
-        return r;
-    }
-    launch_softmax((const float*)S, (__half*)P, NT, Hh, NT, NP, s);
-    {  // context = P v, written head-interleaved into attn [NT, D]
-      GemmArgs g = base_args(NT, 64, NT, EPI_F16);
-      g.out_f16 = (__half*)attn;
-      g.ldc = D;
-      g.out_batch_stride = 64;
-      if ((r = gemm_batched(e, (const __half*)P, NP, (uint64_t)NP * NP, (const __half*)vt, NP, (uint64_t)64 * NP, Hh,
-                            g, 64)))
-        return r;
+    if (e->flash) {
+      // fused tcgen05 attention: scores stay in TMEM, probabilities in shared memory
+      CUtensorMap mq, mk, mv;
+      if ((r = make_map(e, &mq, q, 64, NT, Hh, 64, (uint64_t)NP * 64, 128, 1))) return r;
+      if ((r = make_map(e, &mk, k, 64, NT, Hh, 64, (uint64_t)NP * 64, 128, 1))) return r;
+      if ((r = make_map(e, &mv, vt, NT, 64, Hh, NP, (uint64_t)64 * NP, 64, 1))) return r;
+      cudaError_t ce = launch_attention(mq, mk, mv, NT, D, (__half*)attn, Hh, s);
+      if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(ce));
+      e->launches++;
+    } else {
+      {  // scores = (q / sqrt(d)) k^T, per head
+        GemmArgs g = base_args(NT, NT, 64, EPI_F32);
+        g.out_f32 = (float*)S;
+        g.ldc = NP;
+        g.out_batch_stride = (long long)NP * NP;
+        if ((r = gemm_batched(e, (const __half*)q, 64, (uint64_t)NP * 64, (const __half*)k, 64, (uint64_t)NP * 64, Hh,
+                              g, 128)))
+          return r;
+      }
+      launch_softmax((const float*)S, (__half*)P, NT, Hh, NT, NP, s);
+      e->launches++;
+      {  // context = P v, written head-interleaved into attn [NT, D]
+        GemmArgs g = base_args(NT, 64, NT, EPI_F16);
+        g.out_f16 = (__half*)attn;
+        g.ldc = D;
+        g.out_batch_stride = 64;
+        if ((r = gemm_batched(e, (const __half*)P, NP, (uint64_t)NP * NP, (const __half*)vt, NP, (uint64_t)64 * NP, Hh,
+                              g, 64)))
+          return r;
+      }
     }
     {
       GemmArgs g = base_args(NT, D, D, EPI_RESID_LS);
@@ -426,7 +444,7 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
       g.ldc = D;
       if ((r = gemm(e, (const __half*)hb, 4 * D, wf2, 4 * D, g))) return r;
     }
-    e->launches += 3;
+    e->launches += 2;
     if (tap_idx < 4 && c.taps[tap_idx] == l + 1) {
       // backbone output: final LayerNorm applied (apply_layernorm=True), CLS dropped by the neck
       const float *ng, *nb;

@@ -5,6 +5,7 @@
 // core/render_depth.py:1106-1119 (hf_batch_safe_pipe).
 #include "depth_launch.h"
 #include "umma_gemm.cuh"
+#include "umma_attention.cuh"
 
 namespace vd3d {
 
@@ -386,6 +387,23 @@ static cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, con
     attr_set = true;
   }
   k_umma_gemm<BN, STAGES><<<grid, kGemmThreads, smem, s>>>(a, b, g);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, int ntok, int dmodel,
+                             __half* out, int heads, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_umma_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  AttnArgs a;
+  a.ntok = ntok;
+  a.dmodel = dmodel;
+  a.out = out;
+  dim3 grid((ntok + 127) / 128, heads);
+  k_umma_attention<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,256 @@
+// umma_attention.cuh -- fused multi-head attention for the ViT blocks on tcgen05.
+//
+//   O[m, :] = softmax_n(q[m] . k[n]) v[n]      head_dim 64, q pre-scaled by 1/sqrt(64)
+//
+// One CTA per (128-query block, head).  Scores never leave the SM: S = Q K^T is accumulated in
+// tensor memory (two 128-column buffers), the softmax warps read it with tcgen05.ld, and the
+// probabilities are written (f16, 128B-swizzled K-major) into shared memory where they are the
+// A operand of the second MMA, O += P V, whose accumulator also lives in TMEM.
+// Two passes over the keys (N <= 3072 here): pass A finds the exact row maximum, pass B
+// recomputes S, exponentiates against the final maximum and accumulates P V -- no online
+// rescaling of O, at the price of issuing the (cheap, K = 64) QK^T MMAs twice.
+//
+// warp 0: TMA producer (Q once; K tiles twice; V^T tiles once)   warp 1: MMA issuer + TMEM alloc
+// warps 2-5: softmax / epilogue (thread = query row)
+//
+// Replaces Dinov2SelfAttention (transformers 5.5 models/dinov2/modeling_dinov2.py) inside the depth
+// forward called from core/render_depth.py:1106-1119.
+#pragma once
+#include "umma_gemm.cuh"
+
+namespace vd3d {
+
+struct AttnArgs {
+  int ntok;     // valid tokens (queries == keys)
+  int dmodel;   // row stride of the output (elements)
+  __half* out;  // [ntok, dmodel], head h writes columns [64h, 64h+64)
+};
+
+constexpr int kAttnThreads = 192;
+constexpr int kAttnKS = 3, kAttnVS = 2;
+constexpr int kAttnSmem = 16384 /*Q*/ + kAttnKS * 16384 + kAttnVS * 16384 + 2 * 32768 /*P*/ + 1024 + 512;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = sK + kAttnKS * 16384;
+  uint8_t* sP = sV + kAttnVS * 16384;
+  uint64_t* bars = (uint64_t*)(sP + 2 * 32768);
+  uint64_t* q_full = bars;               // 1
+  uint64_t* k_full = bars + 1;           // KS
+  uint64_t* k_empty = k_full + kAttnKS;  // KS
+  uint64_t* v_full = k_empty + kAttnKS;  // VS
+  uint64_t* v_empty = v_full + kAttnVS;  // VS
+  uint64_t* s_full = v_empty + kAttnVS;  // 2
+  uint64_t* s_empty = s_full + 2;        // 2 (4 arrivals: one per softmax warp)
+  uint64_t* p_full = s_empty + 2;        // 2 (4 arrivals)
+  uint64_t* p_empty = p_full + 2;        // 2
+  uint64_t* o_full = p_empty + 2;        // 1
+  uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qblk = blockIdx.x, h = blockIdx.y;
+  const int T = (g.ntok + 127) / 128;  // key tiles
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmQ);
+    umma::prefetch_tmap(&tmK);
+    umma::prefetch_tmap(&tmV);
+    umma::mbar_init(umma::smem_u32(q_full), 1);
+    for (int i = 0; i < kAttnKS; ++i) {
+      umma::mbar_init(umma::smem_u32(&k_full[i]), 1);
+      umma::mbar_init(umma::smem_u32(&k_empty[i]), 1);
+    }
+    for (int i = 0; i < kAttnVS; ++i) {
+      umma::mbar_init(umma::smem_u32(&v_full[i]), 1);
+      umma::mbar_init(umma::smem_u32(&v_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(umma::smem_u32(&s_full[i]), 1);
+      umma::mbar_init(umma::smem_u32(&s_empty[i]), 4);
+      umma::mbar_init(umma::smem_u32(&p_full[i]), 4);
+      umma::mbar_init(umma::smem_u32(&p_empty[i]), 1);
+    }
+    umma::mbar_init(umma::smem_u32(o_full), 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) umma::tmem_alloc(umma::smem_u32(tmem_slot), 512);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S[2] = {tmem_base, tmem_base + 128};
+  const uint32_t tmem_O = tmem_base + 256;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      umma::mbar_expect_tx(umma::smem_u32(q_full), 16384);
+      umma::tma_load_3d(umma::smem_u32(sQ), &tmQ, umma::smem_u32(q_full), 0, qblk * 128, h);
+      int kiter = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int t = 0; t < T; ++t, ++kiter) {
+          const int ks = kiter % kAttnKS;
+          umma::mbar_wait(umma::smem_u32(&k_empty[ks]), ((kiter / kAttnKS) & 1) ^ 1);
+          umma::mbar_expect_tx(umma::smem_u32(&k_full[ks]), 16384);
+          umma::tma_load_3d(umma::smem_u32(sK + ks * 16384), &tmK, umma::smem_u32(&k_full[ks]), 0, t * 128, h);
+          if (pass == 1) {
+            const int vs = t % kAttnVS;
+            umma::mbar_wait(umma::smem_u32(&v_empty[vs]), ((t / kAttnVS) & 1) ^ 1);
+            umma::mbar_expect_tx(umma::smem_u32(&v_full[vs]), 16384);
+            const uint32_t dst = umma::smem_u32(sV + vs * 16384);
+            umma::tma_load_3d(dst, &tmV, umma::smem_u32(&v_full[vs]), t * 128, 0, h);
+            umma::tma_load_3d(dst + 8192, &tmV, umma::smem_u32(&v_full[vs]), t * 128 + 64, 0, h);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma::make_idesc(128);
+      constexpr uint32_t idesc_o = umma::make_idesc(64);
+      umma::mbar_wait(umma::smem_u32(q_full), 0);
+      umma::tc_fence_after();
+      const uint64_t dq = umma::make_desc(umma::smem_u32(sQ));
+      int kiter = 0;
+      auto issue_S = [&](int gi) {  // gi: global S iteration 0 .. 2T-1
+        const int ks = kiter % kAttnKS;
+        umma::mbar_wait(umma::smem_u32(&k_full[ks]), (kiter / kAttnKS) & 1);
+        const int sb = gi & 1;
+        umma::mbar_wait(umma::smem_u32(&s_empty[sb]), ((gi >> 1) & 1) ^ 1);
+        umma::tc_fence_after();
+        const uint64_t dk = umma::make_desc(umma::smem_u32(sK + ks * 16384));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::mma_f16(tmem_S[sb], dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+        umma::umma_commit(umma::smem_u32(&k_empty[ks]));
+        umma::umma_commit(umma::smem_u32(&s_full[sb]));
+        ++kiter;
+      };
+      // pass A: scores only (row maxima)
+      for (int t = 0; t < T; ++t) issue_S(t);
+      // pass B: scores again, then O += P V (S of tile t+1 is issued before waiting for P of tile t)
+      issue_S(T);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) issue_S(T + t + 1);
+        const int pb = t & 1, vs = t % kAttnVS;
+        umma::mbar_wait(umma::smem_u32(&p_full[pb]), (t >> 1) & 1);
+        umma::mbar_wait(umma::smem_u32(&v_full[vs]), (t / kAttnVS) & 1);
+        umma::tc_fence_after();
+        const uint32_t pa = umma::smem_u32(sP + pb * 32768);
+        const uint32_t va = umma::smem_u32(sV + vs * 16384);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = umma::make_desc(pa + (kk >> 2) * 16384) + (uint64_t)(2 * (kk & 3));
+          const uint64_t db = umma::make_desc(va + (kk >> 2) * 8192) + (uint64_t)(2 * (kk & 3));
+          umma::mma_f16(tmem_O, da, db, idesc_o, (t | kk) ? 1u : 0u);
+        }
+        umma::umma_commit(umma::smem_u32(&v_empty[vs]));
+        umma::umma_commit(umma::smem_u32(&p_empty[pb]));
+      }
+      umma::umma_commit(umma::smem_u32(o_full));
+    }
+  } else {
+    // ===================== softmax / epilogue warps =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // query row inside the block == TMEM lane
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    float mx = -INFINITY;
+    // ---- pass A: exact row maximum ----
+    for (int gi = 0; gi < T; ++gi) {
+      const int sb = gi & 1;
+      umma::mbar_wait(umma::smem_u32(&s_full[sb]), (gi >> 1) & 1);
+      umma::tc_fence_after();
+      const int nvalid = min(128, g.ntok - gi * 128);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        umma::tmem_ld_32x32(tmem_S[sb] + lane_off + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(umma::smem_u32(&s_empty[sb]));
+    }
+    // ---- pass B: p = exp(s - max), P -> smem (swizzled, A operand of the PV MMA) ----
+    float sum = 0.f;
+    const float mxl = mx * 1.4426950408889634f;
+    for (int t = 0; t < T; ++t) {
+      const int gi = T + t, sb = gi & 1, pb = t & 1;
+      umma::mbar_wait(umma::smem_u32(&s_full[sb]), (gi >> 1) & 1);
+      umma::mbar_wait(umma::smem_u32(&p_empty[pb]), ((t >> 1) & 1) ^ 1);
+      umma::tc_fence_after();
+      const int nvalid = min(128, g.ntok - t * 128);
+      uint8_t* prow = sP + pb * 32768 + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        umma::tmem_ld_32x32(tmem_S[sb] + lane_off + (uint32_t)(c * 32), v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float p0 = (c * 32 + j < nvalid) ? exp2f(__uint_as_float(v[j]) * 1.4426950408889634f - mxl) : 0.f;
+          float p1 = (c * 32 + j + 1 < nvalid) ? exp2f(__uint_as_float(v[j + 1]) * 1.4426950408889634f - mxl) : 0.f;
+          sum += p0 + p1;
+          __half2 hp = __floats2half2_rn(p0, p1);
+          pk[j >> 1] = *(uint32_t*)&hp;
+        }
+        uint8_t* pblk = prow + (c >> 1) * 16384;  // 64-key block
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = (c & 1) * 4 + i;           // logical 16-byte chunk inside the 128-byte row
+          const int phys = idx ^ (r & 7);            // 128B swizzle
+          *(uint4*)(pblk + phys * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+      umma::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(umma::smem_u32(&s_empty[sb]));
+        mbar_arrive(umma::smem_u32(&p_full[pb]));
+      }
+    }
+    // ---- epilogue: O / sum -> out[m, 64h .. 64h+63] ----
+    umma::mbar_wait(umma::smem_u32(o_full), 0);
+    umma::tc_fence_after();
+    const int m = qblk * 128 + r;
+    const float inv = 1.0f / sum;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      umma::tmem_ld_32x32(tmem_O + lane_off + (uint32_t)(c * 32), v);
+      if (m < g.ntok) {
+        uint4* dst = (uint4*)(g.out + (size_t)m * g.dmodel + h * 64 + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          uint4 u;
+          u.x = *(uint32_t*)&h0;
+          u.y = *(uint32_t*)&h1;
+          u.z = *(uint32_t*)&h2;
+          u.w = *(uint32_t*)&h3;
+          dst[i] = u;
+        }
+      }
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace vd3d
