@@ -375,8 +375,30 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         } break;
         case EPI_RESID_LS: {
+          // read-modify-write of the fp32 residual stream: issue all loads before the first store
+          // (a load/store-per-element loop serialises on possible aliasing: ~800 cycles per element)
           float* dst = g.out_f32 + (size_t)m * g.ldc + n0;
-          for (int j = 0; j < nvalid; ++j) dst[j] = dst[j] + g.ls[n0 + j] * a[j];
+          if (nvalid == 32 && ((((size_t)m * g.ldc + n0) & 3) == 0)) {
+            float4 x4[8], l4[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              x4[j] = __ldcg((const float4*)dst + j);
+              l4[j] = __ldg((const float4*)(g.ls + n0) + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              x4[j].x += l4[j].x * a[4 * j + 0];
+              x4[j].y += l4[j].y * a[4 * j + 1];
+              x4[j].z += l4[j].z * a[4 * j + 2];
+              x4[j].w += l4[j].w * a[4 * j + 3];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = x4[j];
+          } else {
+            float xv[32];
+            for (int j = 0; j < nvalid; ++j) xv[j] = dst[j];
+            for (int j = 0; j < nvalid; ++j) dst[j] = xv[j] + g.ls[n0 + j] * a[j];
+          }
         } break;
         case EPI_QKV: {
           // n0 is a multiple of 32 and head_dim is 64: the 32 columns lie in one (which, head)
@@ -408,7 +430,12 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         case EPI_PATCH: {
           float* dst = g.out_f32 + (size_t)(m + 1) * g.ldc + n0;
           const float* pe = g.pos + (size_t)(m + 1) * g.ldc + n0;
-          for (int j = 0; j < nvalid; ++j) dst[j] = a[j] + pe[j];
+          float pv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[j] = (j < nvalid) ? __ldg(pe + j) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) dst[j] = a[j] + pv[j];
         } break;
         case EPI_CONVT: {
           // n = (dy*k + dx)*Cout + co ; m = y*ct_w + x ; out NHWC [(H*k), (W*k), Cout]
