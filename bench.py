@@ -42,6 +42,8 @@ WORKLOADS = {
                fmt="Full-SBS", preserve=True, model="vitl", pool=6, frames_per_step=6,
                dibr_bytes=18 * 3840 * 2160),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_compose launch (profiles/r01_ncu_full_summary.md)
+NCU_COMPOSE_TRAFFIC = {"4k": 156386048, "1080p": None}
 COMMON = dict(fg=4.5, mg=-1.5, bg=-6.0, sharp=0.2, feather=10.0, ksize=9, tracking=True, floating=True,
               zps=0.01, dof=0.0)
 
@@ -286,7 +288,6 @@ def main():
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    lib.vd3d_profile(ctx.h, 1)
     l0 = ctx.launches + deng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -296,11 +297,6 @@ def main():
     barrier()
     ms = reduce_max(e0.elapsed_time(e1))
     launches = ctx.launches + deng.launches - l0
-    tot0, n0, tot1, n1, tot2, n2 = C.c_double(), C.c_int(), C.c_double(), C.c_int(), C.c_double(), C.c_int()
-    lib.vd3d_profile_collect(ctx.h, 0, C.byref(tot0), C.byref(n0))
-    lib.vd3d_profile_collect(ctx.h, 1, C.byref(tot1), C.byref(n1))
-    lib.vd3d_profile_collect(ctx.h, 2, C.byref(tot2), C.byref(n2))
-    lib.vd3d_profile(ctx.h, 0)
     frames = args.steps * B
     value = world * frames / (ms / 1000.0)
 
@@ -319,6 +315,16 @@ def main():
     h2d = B * (wl["w"] * wl["h"] * 3)
     d2h = B * int(np.prod(oshape))
 
+    # ================= per-stage device timing (CUDA events around the stages; eager launches) ======
+    lib.vd3d_profile(ctx.h, 1)
+    for _ in range(max(2, min(args.steps, 4))):
+        step(_lib.MEM_DEVICE)
+    tot0, n0, tot1, n1, tot2, n2 = C.c_double(), C.c_int(), C.c_double(), C.c_int(), C.c_double(), C.c_int()
+    lib.vd3d_profile_collect(ctx.h, 0, C.byref(tot0), C.byref(n0))
+    lib.vd3d_profile_collect(ctx.h, 1, C.byref(tot1), C.byref(n1))
+    lib.vd3d_profile_collect(ctx.h, 2, C.byref(tot2), C.byref(n2))
+    lib.vd3d_profile(ctx.h, 0)
+
     if rank == 0:
         hbm_peak, tf_peak, which = peaks()
         px = wl["w"] * wl["h"] if wl["preserve"] else pl.resized_width * pl.resized_height
@@ -327,6 +333,8 @@ def main():
         stage_ms = tot0.value / max(n0.value, 1)
         comp_gbs = comp_bytes / (comp_ms * 1e-3) / 1e9 if comp_ms > 0 else 0.0
         stage_gbs = wl["dibr_bytes"] / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else 0.0
+        depth_ms = tot2.value / max(n2.value, 1)
+        depth_tf = DEPTH_GFLOP[wl["model"]] / max(depth_ms, 1e-9)
         line = {
             "metric": "end-to-end frames/sec (depth+stereo)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -337,23 +345,25 @@ def main():
                 "depth_model": f"Depth-Anything-V2 {wl['model']} @518x924, random-init seed 0 (no checkpoints offline), "
                                "f16 tensor-core operands / fp32 accumulate",
                 "stage": "DPT processor + depth forward + min-max u8 handoff in HBM + DIBR frame loop + pack",
+                "launch_mode": "CUDA graph replay of the ~200-kernel frame sequence (vd3d_set_graphs)",
                 "params": COMMON, "sharding": "contiguous chunks per rank, independent temporal state per chunk",
             },
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_compose", "achieved": comp_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": comp_gbs / hbm_peak, "traffic": None, "peak_source": which,
-                         "algorithmic_bytes_per_launch": comp_bytes, "avg_launch_ms": comp_ms},
-            "roofline_stage": {"bound": "hbm", "what": "whole DIBR frame (ingest..pack)", "achieved": stage_gbs,
-                               "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,
-                               "algorithmic_bytes_per_frame": wl["dibr_bytes"], "avg_frame_ms": stage_ms},
-            "roofline_depth": {"bound": "tensor", "what": "depth stage (processor + DA-V2 forward + post)",
-                               "achieved": DEPTH_GFLOP[wl["model"]] / max(tot2.value / max(n2.value, 1), 1e-9),
-                               "peak": tf_peak, "unit": "TFLOP/s",
-                               "frac": DEPTH_GFLOP[wl["model"]] / max(tot2.value / max(n2.value, 1), 1e-9) / tf_peak,
-                               "algorithmic_gflop_per_frame": DEPTH_GFLOP[wl["model"]],
-                               "avg_frame_ms": tot2.value / max(n2.value, 1)},
+            # dominant share of the step: the depth stage (tcgen05 GEMMs + fused attention), tensor bound
+            "roofline": {"bound": "tensor", "kernel": "depth stage: k_umma_gemm<*> + k_umma_attention (+ small fused kernels)",
+                         "achieved": depth_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": depth_tf / tf_peak,
+                         "traffic": None, "peak_source": which + " (cuBLAS bf16 sustained)",
+                         "algorithmic_gflop_per_frame": DEPTH_GFLOP[wl["model"]], "avg_frame_ms": depth_ms,
+                         "share_of_step": depth_ms / max(depth_ms + stage_ms, 1e-9)},
+            "roofline_dibr_compose": {"bound": "hbm", "kernel": "k_compose4", "achieved": comp_gbs, "peak": hbm_peak,
+                                      "unit": "GB/s", "frac": comp_gbs / hbm_peak,
+                                      "traffic": NCU_COMPOSE_TRAFFIC.get(args.workload), "peak_source": which,
+                                      "algorithmic_bytes_per_launch": comp_bytes, "avg_launch_ms": comp_ms},
+            "roofline_dibr_stage": {"bound": "hbm", "what": "whole DIBR frame (ingest..pack)", "achieved": stage_gbs,
+                                    "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,
+                                    "algorithmic_bytes_per_frame": wl["dibr_bytes"], "avg_frame_ms": stage_ms},
         }
         if world == 1 and not args.no_cpu_baseline:
             fps, n = cpu_port_fps(wl)

@@ -202,6 +202,7 @@ int vd3d_depth_create(const vd3d_depth_config* cfg, void* cuda_stream, vd3d_dept
 void vd3d_depth_destroy(vd3d_depth* e);
 const char* vd3d_depth_last_error(vd3d_depth* e);
 uint64_t vd3d_depth_launch_count(vd3d_depth* e);
+void vd3d_depth_add_launches(vd3d_depth* e, uint64_t n); /* bookkeeping for CUDA-graph replays */
 /* upload one prepared weight tensor (names / layouts: visiondepth3d_b200/depth_weights.py) */
 int vd3d_depth_set_tensor(vd3d_depth* e, const char* name, const void* host_data, size_t bytes);
 /* pixel_values f32 [3,image_h,image_w] -> predicted_depth f32 [image_h,image_w] */

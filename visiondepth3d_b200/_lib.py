@@ -85,7 +85,7 @@ SYMBOLS = [
     # depth forward (bound in depth_engine.py)
     "vd3d_depth_create", "vd3d_depth_destroy", "vd3d_depth_last_error", "vd3d_depth_launch_count",
     "vd3d_depth_set_tensor", "vd3d_depth_forward", "vd3d_depth_get_buffer", "vd3d_gemm_f16", "vd3d_conv_f16",
-    "vd3d_depth_infer", "vd3d_depth_infer_device", "vd3d_render_clip_depth",
+    "vd3d_depth_infer", "vd3d_depth_infer_device", "vd3d_render_clip_depth", "vd3d_depth_add_launches",
 ]
 
 _lib = None

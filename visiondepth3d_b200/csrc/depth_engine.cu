@@ -238,6 +238,9 @@ void vd3d_depth_destroy(vd3d_depth* e) {
 
 const char* vd3d_depth_last_error(vd3d_depth* e) { return e ? e->err.c_str() : "null depth engine"; }
 uint64_t vd3d_depth_launch_count(vd3d_depth* e) { return e ? e->launches : 0; }
+void vd3d_depth_add_launches(vd3d_depth* e, uint64_t n) {
+  if (e) e->launches += n;  // graph replays account for the launches they contain
+}
 
 int vd3d_depth_set_tensor(vd3d_depth* e, const char* name, const void* host_data, size_t bytes) {
   if (!e || !name || !host_data || !bytes) return VD3D_ERR_ARG;

@@ -814,13 +814,15 @@ __global__ void __launch_bounds__(256) k_warp_edges(const float* __restrict__ d,
 // (core/render_3d.py:697-698, 355-374, 289-291, 1373-1386)
 // SRC_U8: sample the BGR u8 frame directly (identity-resize path) else f32 RGB planes
 // ---------------------------------------------------------------------------
+// lut[i] == (float)i / 255.0f (built per block): the IEEE division costs ~10 instructions and a
+// pixel needs 27 of them; the table gives the identical bits with one shared-memory load.
 template <bool SRC_U8>
-__device__ __forceinline__ void fetch_rgb(const ComposeArgs& a, int y, int x, float* rgb) {
+__device__ __forceinline__ void fetch_rgb(const ComposeArgs& a, const float* lut, int y, int x, float* rgb) {
   if (SRC_U8) {
     const uint8_t* q = a.src_u8 + ((size_t)(a.cy0 + y) * a.src_pitch + a.cx0 + x) * 3;
-    rgb[0] = (float)q[2] / 255.0f;
-    rgb[1] = (float)q[1] / 255.0f;
-    rgb[2] = (float)q[0] / 255.0f;
+    rgb[0] = lut[q[2]];
+    rgb[1] = lut[q[1]];
+    rgb[2] = lut[q[0]];
   } else {
     size_t plane = (size_t)a.H * a.W;
     size_t o = (size_t)y * a.W + x;
@@ -833,6 +835,9 @@ __device__ __forceinline__ void fetch_rgb(const ComposeArgs& a, int y, int x, fl
 template <bool SRC_U8>
 __global__ void __launch_bounds__(256) k_compose(ComposeArgs a) {
   extern __shared__ float2 tile[];  // (32+k-1) x (8+k-1)
+  __shared__ float lut[256];
+  lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+  if (!a.feather) __syncthreads();
   const int k = a.feather ? a.k : 1;
   const int p = k / 2;
   const int tw = 32 + k - 1, th = 8 + k - 1;
@@ -871,17 +876,17 @@ __global__ void __launch_bounds__(256) k_compose(ComposeArgs a) {
     br = ar / kk;
   }
   float o[3];
-  fetch_rgb<SRC_U8>(a, y, x, o);
+  fetch_rgb<SRC_U8>(a, lut, y, x, o);
   float l00[3], l01[3], l10[3], l11[3];
   uint8_t outl[3], outr[3];
 #pragma unroll
   for (int eye = 0; eye < 2; ++eye) {
     const Tap& t = eye ? tr : tl;
     float b = eye ? br : bl;
-    fetch_rgb<SRC_U8>(a, t.y0, t.x0, l00);
-    fetch_rgb<SRC_U8>(a, t.y0, t.x1, l01);
-    fetch_rgb<SRC_U8>(a, t.y1, t.x0, l10);
-    fetch_rgb<SRC_U8>(a, t.y1, t.x1, l11);
+    fetch_rgb<SRC_U8>(a, lut, t.y0, t.x0, l00);
+    fetch_rgb<SRC_U8>(a, lut, t.y0, t.x1, l01);
+    fetch_rgb<SRC_U8>(a, lut, t.y1, t.x0, l10);
+    fetch_rgb<SRC_U8>(a, lut, t.y1, t.x1, l11);
     float c[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
@@ -892,7 +897,7 @@ __global__ void __launch_bounds__(256) k_compose(ComposeArgs a) {
     uint8_t* dst = eye ? outr : outl;
     uint8_t r8 = trunc_u8(c[0]), g8 = trunc_u8(c[1]), b8 = trunc_u8(c[2]);
     if (a.grade) {  // frame_to_tensor -> apply_color_grade -> tensor_to_frame
-      float r = (float)r8 / 255.0f, g = (float)g8 / 255.0f, bb = (float)b8 / 255.0f;
+      float r = lut[r8], g = lut[g8], bb = lut[b8];
       grade_px(r, g, bb, a.sat, a.con, a.bri);
       r8 = trunc_u8(r);
       g8 = trunc_u8(g);
@@ -909,6 +914,112 @@ __global__ void __launch_bounds__(256) k_compose(ComposeArgs a) {
   a.right[oo] = outr[0];
   a.right[oo + 1] = outr[1];
   a.right[oo + 2] = outr[2];
+}
+
+// Register-tiled variant for the common odd pool sizes: 4 horizontally adjacent outputs per
+// thread share one row segment of the mask tile (6 LDS.128 per row for K = 9 instead of 36 LDS.64),
+// K is a compile-time constant (fully unrolled), and each output still accumulates its K x K taps
+// in the reference's row-major order, so results are bit-identical to k_compose.
+template <bool SRC_U8, int K>
+__global__ void __launch_bounds__(256) k_compose4(ComposeArgs a) {
+  extern __shared__ float2 tile[];
+  __shared__ float lut[256];
+  lut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+  constexpr int P = K / 2;
+  constexpr int TW = 128 + K - 1 + ((128 + K - 1) & 1);  // even row pitch (float2) for 16-byte loads
+  constexpr int TH = 8 + K - 1;
+  constexpr int NV = 4 + K - 1 + ((4 + K - 1) & 1);
+  const int bx = blockIdx.x * 128, by = blockIdx.y * 8;
+  const int H = a.H, W = a.W;
+  for (int i = threadIdx.x; i < TW * TH; i += 256) {
+    int ty = i / TW, tx = i % TW;
+    int gy = by - P + ty, gx = bx - P + tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = a.e2[(size_t)gy * W + gx];
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int x0 = bx + lx * 4, y = by + ly;
+  if (x0 >= W || y >= H) return;
+  float al[4] = {0.f, 0.f, 0.f, 0.f}, ar[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dy = 0; dy < K; ++dy) {
+    const float4* row = (const float4*)(tile + (ly + dy) * TW + lx * 4);
+    float2 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) {
+      float4 f = row[j];
+      v[2 * j] = make_float2(f.x, f.y);
+      v[2 * j + 1] = make_float2(f.z, f.w);
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        al[o] = al[o] + v[o + dx].x;
+        ar[o] = ar[o] + v[o + dx].y;
+      }
+  }
+  const float kk = (float)(K * K);
+  const float yv = a.ys[y];
+  uint8_t ol[12], orr[12];
+  int nvalid = min(4, W - x0);
+  for (int i = 0; i < nvalid; ++i) {
+    const int x = x0 + i;
+    float sv = a.shift[(size_t)y * W + x];
+    float xv = a.xs[x];
+    Tap tl = make_tap(xv + sv, yv, H, W);
+    Tap tr = make_tap(xv - sv, yv, H, W);
+    float bl = al[i] / kk, br = ar[i] / kk;
+    float o[3];
+    fetch_rgb<SRC_U8>(a, lut, y, x, o);
+    float l00[3], l01[3], l10[3], l11[3];
+#pragma unroll
+    for (int eye = 0; eye < 2; ++eye) {
+      const Tap& t = eye ? tr : tl;
+      float b = eye ? br : bl;
+      fetch_rgb<SRC_U8>(a, lut, t.y0, t.x0, l00);
+      fetch_rgb<SRC_U8>(a, lut, t.y0, t.x1, l01);
+      fetch_rgb<SRC_U8>(a, lut, t.y1, t.x0, l10);
+      fetch_rgb<SRC_U8>(a, lut, t.y1, t.x1, l11);
+      float c[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float s = tap_apply(t, l00[ch], l01[ch], l10[ch], l11[ch]);
+        c[ch] = clamp01((s * (1.0f - b)) + (o[ch] * b));
+      }
+      uint8_t r8 = trunc_u8(c[0]), g8 = trunc_u8(c[1]), b8 = trunc_u8(c[2]);
+      if (a.grade) {
+        float r = lut[r8], g = lut[g8], bb = lut[b8];
+        grade_px(r, g, bb, a.sat, a.con, a.bri);
+        r8 = trunc_u8(r);
+        g8 = trunc_u8(g);
+        b8 = trunc_u8(bb);
+      }
+      uint8_t* dst = eye ? orr : ol;
+      dst[3 * i] = b8;
+      dst[3 * i + 1] = g8;
+      dst[3 * i + 2] = r8;
+    }
+  }
+  size_t oo = ((size_t)y * W + x0) * 3;
+  if (nvalid == 4 && (oo & 3) == 0) {
+    uint32_t* pl = (uint32_t*)(a.left + oo);
+    uint32_t* pr = (uint32_t*)(a.right + oo);
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      pl[w] = (uint32_t)ol[4 * w] | ((uint32_t)ol[4 * w + 1] << 8) | ((uint32_t)ol[4 * w + 2] << 16) |
+              ((uint32_t)ol[4 * w + 3] << 24);
+      pr[w] = (uint32_t)orr[4 * w] | ((uint32_t)orr[4 * w + 1] << 8) | ((uint32_t)orr[4 * w + 2] << 16) |
+              ((uint32_t)orr[4 * w + 3] << 24);
+    }
+  } else {
+    for (int i = 0; i < nvalid * 3; ++i) {
+      a.left[oo + i] = ol[i];
+      a.right[oo + i] = orr[i];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1143,7 +1254,26 @@ cudaError_t init_kernel_attributes() {
   e = cudaFuncSetAttribute(k_dof, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   return e;
 }
+template <int K>
+static void launch_compose4(const ComposeArgs& a, cudaStream_t s) {
+  constexpr int TW = 128 + K - 1 + ((128 + K - 1) & 1);
+  int smem = TW * (8 + K - 1) * (int)sizeof(float2);
+  dim3 g((a.W + 127) / 128, (a.H + 7) / 8);
+  if (a.src_u8)
+    k_compose4<true, K><<<g, 256, smem, s>>>(a);
+  else
+    k_compose4<false, K><<<g, 256, smem, s>>>(a);
+}
 void launch_compose(const ComposeArgs& a, cudaStream_t s) {
+  if (a.feather) {
+    switch (a.k) {
+      case 3: return launch_compose4<3>(a, s);
+      case 5: return launch_compose4<5>(a, s);
+      case 7: return launch_compose4<7>(a, s);
+      case 9: return launch_compose4<9>(a, s);
+      default: break;
+    }
+  }
   int smem = a.feather ? compose_smem_bytes(a.k) : 0;
   if (a.src_u8)
     k_compose<true><<<grid2d(a.W, a.H), 256, smem, s>>>(a);

@@ -11,7 +11,7 @@
 // rescaling of O, at the price of issuing the (cheap, K = 64) QK^T MMAs twice.
 //
 // warp 0: TMA producer (Q once; K tiles twice; V^T tiles once)   warp 1: MMA issuer + TMEM alloc
-// warps 2-5: softmax / epilogue (thread = query row)
+// warps 2-9: softmax / epilogue (two threads per query row, 64 keys of every 128-key tile each)
 //
 // Replaces Dinov2SelfAttention (transformers 5.5 models/dinov2/modeling_dinov2.py) inside the depth
 // forward called from core/render_depth.py:1106-1119.
@@ -26,9 +26,9 @@ struct AttnArgs {
   __half* out;  // [ntok, dmodel], head h writes columns [64h, 64h+64)
 };
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 per TMEM lane quarter)
 constexpr int kAttnKS = 3, kAttnVS = 2;
-constexpr int kAttnSmem = 16384 /*Q*/ + kAttnKS * 16384 + kAttnVS * 16384 + 2 * 32768 /*P*/ + 1024 + 512;
+constexpr int kAttnSmem = 16384 /*Q*/ + kAttnKS * 16384 + kAttnVS * 16384 + 2 * 32768 /*P*/ + 1024 + 512 + 2048;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -55,6 +55,7 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* p_empty = p_full + 2;        // 2
   uint64_t* o_full = p_empty + 2;        // 1
   uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
+  float* xch = (float*)(bars + 64);  // [2][128] row max / row sum exchange between the two half-row threads
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, h = blockIdx.y;
@@ -75,8 +76,8 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       umma::mbar_init(umma::smem_u32(&s_full[i]), 1);
-      umma::mbar_init(umma::smem_u32(&s_empty[i]), 4);
-      umma::mbar_init(umma::smem_u32(&p_full[i]), 4);
+      umma::mbar_init(umma::smem_u32(&s_empty[i]), 8);
+      umma::mbar_init(umma::smem_u32(&p_full[i]), 8);
       umma::mbar_init(umma::smem_u32(&p_empty[i]), 1);
     }
     umma::mbar_init(umma::smem_u32(o_full), 1);
@@ -160,20 +161,22 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else {
     // ===================== softmax / epilogue warps =====================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // query row inside the block == TMEM lane
+    const int q = warp & 3;             // TMEM lane quarter (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;   // which 64 keys of every 128-key tile
+    const int r = q * 32 + lane;        // query row inside the block == TMEM lane
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t col_off = (uint32_t)(half * 64);
     float mx = -INFINITY;
     // ---- pass A: exact row maximum ----
     for (int gi = 0; gi < T; ++gi) {
       const int sb = gi & 1;
       umma::mbar_wait(umma::smem_u32(&s_full[sb]), (gi >> 1) & 1);
       umma::tc_fence_after();
-      const int nvalid = min(128, g.ntok - gi * 128);
+      const int nvalid = min(128, g.ntok - gi * 128) - half * 64;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        umma::tmem_ld_32x32(tmem_S[sb] + lane_off + (uint32_t)(c * 32), v);
+        umma::tmem_ld_32x32(tmem_S[sb] + lane_off + col_off + (uint32_t)(c * 32), v);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (c * 32 + j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
@@ -182,6 +185,10 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(umma::smem_u32(&s_empty[sb]));
     }
+    xch[half * 128 + r] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(xch[r], xch[128 + r]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     // ---- pass B: p = exp(s - max), P -> smem (swizzled, A operand of the PV MMA) ----
     float sum = 0.f;
     const float mxl = mx * 1.4426950408889634f;
@@ -190,12 +197,12 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       umma::mbar_wait(umma::smem_u32(&s_full[sb]), (gi >> 1) & 1);
       umma::mbar_wait(umma::smem_u32(&p_empty[pb]), ((t >> 1) & 1) ^ 1);
       umma::tc_fence_after();
-      const int nvalid = min(128, g.ntok - t * 128);
-      uint8_t* prow = sP + pb * 32768 + (r >> 3) * 1024 + (r & 7) * 128;
+      const int nvalid = min(128, g.ntok - t * 128) - half * 64;
+      uint8_t* pblk = sP + pb * 32768 + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;  // this row, this 64-key block
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        umma::tmem_ld_32x32(tmem_S[sb] + lane_off + (uint32_t)(c * 32), v);
+        umma::tmem_ld_32x32(tmem_S[sb] + lane_off + col_off + (uint32_t)(c * 32), v);
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -205,11 +212,10 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           __half2 hp = __floats2half2_rn(p0, p1);
           pk[j >> 1] = *(uint32_t*)&hp;
         }
-        uint8_t* pblk = prow + (c >> 1) * 16384;  // 64-key block
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int idx = (c & 1) * 4 + i;           // logical 16-byte chunk inside the 128-byte row
-          const int phys = idx ^ (r & 7);            // 128B swizzle
+          const int idx = c * 4 + i;       // logical 16-byte chunk inside the 128-byte row
+          const int phys = idx ^ (r & 7);  // 128B swizzle
           *(uint4*)(pblk + phys * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
       }
@@ -221,17 +227,19 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_arrive(umma::smem_u32(&p_full[pb]));
       }
     }
-    // ---- epilogue: O / sum -> out[m, 64h .. 64h+63] ----
+    xch[half * 128 + r] = sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    sum = xch[r] + xch[128 + r];
+    // ---- epilogue: O / sum -> out[m, 64h + 32*half .. +31] ----
     umma::mbar_wait(umma::smem_u32(o_full), 0);
     umma::tc_fence_after();
     const int m = qblk * 128 + r;
     const float inv = 1.0f / sum;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      umma::tmem_ld_32x32(tmem_O + lane_off + (uint32_t)(c * 32), v);
+      umma::tmem_ld_32x32(tmem_O + lane_off + (uint32_t)(half * 32), v);
       if (m < g.ntok) {
-        uint4* dst = (uint4*)(g.out + (size_t)m * g.dmodel + h * 64 + c * 32);
+        uint4* dst = (uint4*)(g.out + (size_t)m * g.dmodel + h * 64 + half * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);

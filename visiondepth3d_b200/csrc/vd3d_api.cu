@@ -66,10 +66,22 @@ struct vd3d_ctx {
   int prof = 0;
   std::vector<cudaEvent_t> prof_ev[4];  // stage -> [start, stop, start, stop, ...]
   std::vector<cudaEvent_t> prof_pool;
+  // CUDA graphs of the per-frame kernel sequence, keyed by (staging slot, depth ping-pong parity)
+  struct FrameGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t n_ctx = 0, n_depth = 0;
+  } fg[2][2];
+  vd3d_render_params fg_rp;
+  int fg_h = 0, fg_w = 0, fg_dch = 0, fg_warm = 0;
+  void* fg_depth = nullptr;
   // dof kernel cache
   double dof_sigma_cached = -1.0;
   int dof_nlevels = 0, dof_ksize[8] = {0}, dof_koff[8] = {0}, dof_halo = 0;
 };
+
+extern "C" {
+static void drop_graphs(vd3d_ctx* ctx);
+}
 
 namespace {
 
@@ -499,6 +511,7 @@ void vd3d_destroy(vd3d_ctx* ctx) {
                  &ctx->dof_kern};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
+  drop_graphs(ctx);
   cudaFree(ctx->st);
   cudaFree(ctx->fs);
   cudaFree(ctx->jobwords);
@@ -589,6 +602,7 @@ int vd3d_profile_collect(vd3d_ctx* ctx, int stage, double* total_ms, int* count)
 int vd3d_set_graphs(vd3d_ctx* ctx, int enable) {
   if (!ctx) return VD3D_ERR_ARG;
   ctx->use_graphs = enable;
+  if (!enable) drop_graphs(ctx);
   return VD3D_OK;
 }
 
@@ -927,6 +941,87 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
   return VD3D_OK;
 }
 
+extern "C" uint64_t vd3d_depth_launch_count(vd3d_depth* e);
+extern "C" void vd3d_depth_add_launches(vd3d_depth* e, uint64_t n);
+
+static void drop_graphs(vd3d_ctx* ctx) {
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (ctx->fg[i][j].exec) {
+        cudaGraphExecDestroy(ctx->fg[i][j].exec);
+        ctx->fg[i][j].exec = nullptr;
+      }
+  ctx->fg_warm = 0;
+}
+
+// One frame on the staging buffers of slot b: [depth inference ->] render_sbs_3d loop body.
+// After two eager frames of an unchanged configuration the launch sequence (~200 kernels) is captured
+// once per (slot, parity) into a CUDA graph and replayed; all scalars it depends on live on the device.
+static int run_frame_slot(vd3d_ctx* ctx, vd3d_depth* depth, int b, int depth_channels, int src_h, int src_w,
+                          const vd3d_render_params* rp, const vd3d_size_plan& pl) {
+  const uint8_t* f_d = (const uint8_t*)ctx->in_frame[b].p;
+  uint8_t* d_d = (uint8_t*)ctx->in_depth[b].p;
+  uint8_t* o_d = (uint8_t*)ctx->out_dev[b].p;
+  auto eager = [&]() -> int {
+    int r;
+    if (depth) {
+      ProfScope ps(ctx, 2);
+      if ((r = vd3d_depth_infer_device(depth, f_d, src_h, src_w, d_d, nullptr, 0))) {
+        ctx->err = std::string("depth engine: ") + vd3d_depth_last_error(depth);
+        return r;
+      }
+    }
+    return enqueue_frame(ctx, f_d, d_d, depth ? 1 : depth_channels, src_h, src_w, rp, pl, o_d);
+  };
+  bool same = ctx->fg_h == src_h && ctx->fg_w == src_w && ctx->fg_dch == depth_channels && ctx->fg_depth == depth &&
+              memcmp(&ctx->fg_rp, rp, sizeof *rp) == 0;
+  if (!same) {
+    drop_graphs(ctx);
+    ctx->fg_h = src_h;
+    ctx->fg_w = src_w;
+    ctx->fg_dch = depth_channels;
+    ctx->fg_depth = depth;
+    ctx->fg_rp = *rp;
+  }
+  if (!ctx->use_graphs || ctx->prof || ctx->fg_warm < 2) {
+    ctx->fg_warm++;
+    return eager();
+  }
+  const int par = ctx->frame_parity;
+  vd3d_ctx::FrameGraph& g = ctx->fg[b][par];
+  if (!g.exec) {
+    uint64_t l0 = ctx->launches, d0 = depth ? vd3d_depth_launch_count(depth) : 0;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->use_graphs = 0;
+      return eager();
+    }
+    int r = eager();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    ctx->frame_parity = par;  // capture does not execute
+    uint64_t nl = ctx->launches - l0, nd = depth ? vd3d_depth_launch_count(depth) - d0 : 0;
+    ctx->launches = l0;
+    if (depth) vd3d_depth_add_launches(depth, (uint64_t)0 - nd);
+    if (r != VD3D_OK || ce != cudaSuccess || !graph ||
+        cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      g.exec = nullptr;
+      ctx->use_graphs = 0;  // fall back to eager launches for the rest of this ctx
+      return eager();
+    }
+    cudaGraphDestroy(graph);
+    g.n_ctx = nl;
+    g.n_depth = nd;
+  }
+  CK(cudaGraphLaunch(g.exec, ctx->stream));
+  ctx->launches += g.n_ctx;
+  if (depth) vd3d_depth_add_launches(depth, g.n_depth);
+  ctx->frame_parity ^= 1;
+  return VD3D_OK;
+}
+
 static size_t out_bytes(const vd3d_render_params* rp, const vd3d_size_plan& pl) {
   if (rp->output_format == VD3D_FMT_ANAGLYPH || rp->output_format == VD3D_FMT_INTERLACED)
     return (size_t)pl.per_eye_w * pl.per_eye_h * 3;
@@ -972,38 +1067,33 @@ int vd3d_render_clip(vd3d_ctx* ctx, int n, const uint8_t* const* frames, const u
   if (r) return fail(ctx, r, "unsupported output format / sizes");
   size_t fb = (size_t)src_w * src_h * 3, db = (size_t)src_w * src_h * depth_channels;
   size_t ob = out_bytes(rp, pl);
-  if (mem == VD3D_MEM_DEVICE) {
-    for (int i = 0; i < n; ++i) {
-      if ((r = enqueue_frame(ctx, frames[i], depths[i], depth_channels, src_h, src_w, rp, pl, outs[i]))) return r;
-      if (infos && (r = fetch_info(ctx, &infos[i]))) return r;
-    }
-    CK(cudaStreamSynchronize(ctx->stream));
-    return VD3D_OK;
-  }
   for (int b = 0; b < 2; ++b) {
     if ((r = ensure(ctx, ctx->in_frame[b], fb))) return r;
     if ((r = ensure(ctx, ctx->in_depth[b], db))) return r;
     if ((r = ensure(ctx, ctx->out_dev[b], ob))) return r;
   }
-  // software pipeline over three streams: H2D(i+1) | kernels(i) | D2H(i-1)
   for (int i = 0; i < n; ++i) {
     int b = i & 1;
-    // the staging buffers of slot b are free once frame i-2 finished computing / copying out
-    if (i >= 2) {
-      CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
+    if (mem == VD3D_MEM_DEVICE) {
+      // fixed staging addresses keep the frame graph replayable; D2D copies are ~1 % of a frame
+      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+      CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyDeviceToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->in_depth[b].p, depths[i], db, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      // software pipeline over three streams: H2D(i+1) | kernels(i) | D2H(i-1)
+      if (i >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
+      CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyHostToDevice, ctx->s_h2d));
+      CK(cudaMemcpyAsync(ctx->in_depth[b].p, depths[i], db, cudaMemcpyHostToDevice, ctx->s_h2d));
+      CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
     }
-    CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyHostToDevice, ctx->s_h2d));
-    CK(cudaMemcpyAsync(ctx->in_depth[b].p, depths[i], db, cudaMemcpyHostToDevice, ctx->s_h2d));
-    CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
-    if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
-    if ((r = enqueue_frame(ctx, (const uint8_t*)ctx->in_frame[b].p, (const uint8_t*)ctx->in_depth[b].p,
-                           depth_channels, src_h, src_w, rp, pl, (uint8_t*)ctx->out_dev[b].p)))
-      return r;
+    if ((r = run_frame_slot(ctx, nullptr, b, depth_channels, src_h, src_w, rp, pl))) return r;
     if (infos && (r = fetch_info(ctx, &infos[i]))) return r;
     CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[b], 0));
-    CK(cudaMemcpyAsync(outs[i], ctx->out_dev[b].p, ob, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CK(cudaMemcpyAsync(outs[i], ctx->out_dev[b].p, ob,
+                       mem == VD3D_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->s_d2h));
     CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
   }
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1021,39 +1111,28 @@ int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_
   size_t fb = (size_t)src_w * src_h * 3, db = (size_t)src_w * src_h;
   size_t ob = out_bytes(rp, pl);
   for (int b = 0; b < 2; ++b) {
+    if ((r = ensure(ctx, ctx->in_frame[b], fb))) return r;
     if ((r = ensure(ctx, ctx->in_depth[b], db))) return r;
-    if (mem == VD3D_MEM_HOST) {
-      if ((r = ensure(ctx, ctx->in_frame[b], fb))) return r;
-      if ((r = ensure(ctx, ctx->out_dev[b], ob))) return r;
-    }
+    if ((r = ensure(ctx, ctx->out_dev[b], ob))) return r;
   }
   for (int i = 0; i < n; ++i) {
     int b = i & 1;
-    const uint8_t* f_d = frames[i];
-    uint8_t* o_d = outs[i];
-    if (mem == VD3D_MEM_HOST) {
+    if (mem == VD3D_MEM_DEVICE) {
+      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+      CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
       if (i >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
       CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyHostToDevice, ctx->s_h2d));
       CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
       if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
-      f_d = (const uint8_t*)ctx->in_frame[b].p;
-      o_d = (uint8_t*)ctx->out_dev[b].p;
     }
-    {
-      ProfScope ps(ctx, 2);
-      if ((r = vd3d_depth_infer_device(depth, f_d, src_h, src_w, (uint8_t*)ctx->in_depth[b].p, nullptr, 0))) {
-        ctx->err = std::string("depth engine: ") + vd3d_depth_last_error(depth);
-        return r;
-      }
-    }
-    if ((r = enqueue_frame(ctx, f_d, (const uint8_t*)ctx->in_depth[b].p, 1, src_h, src_w, rp, pl, o_d))) return r;
-    if (mem == VD3D_MEM_HOST) {
-      CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
-      CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[b], 0));
-      CK(cudaMemcpyAsync(outs[i], ctx->out_dev[b].p, ob, cudaMemcpyDeviceToHost, ctx->s_d2h));
-      CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
-    }
+    if ((r = run_frame_slot(ctx, depth, b, 1, src_h, src_w, rp, pl))) return r;
+    CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[b], 0));
+    CK(cudaMemcpyAsync(outs[i], ctx->out_dev[b].p, ob,
+                       mem == VD3D_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
   }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaStreamSynchronize(ctx->s_d2h));
