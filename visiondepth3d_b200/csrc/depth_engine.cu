@@ -135,7 +135,7 @@ int pick_bn(int N) { return N >= 128 ? 128 : (N >= 64 ? 64 : 32); }
 
 // plain GEMM: A [M, K] (lda), B [N, K] (ldb)
 int gemm(vd3d_depth* e, const __half* A, int lda, const __half* B, int ldb, GemmArgs g, int bn = 0) {
-  if (!bn) bn = pick_bn(g.N);
+  if (!bn) bn = pick_bn(g.N);  // (64-wide tiles for sub-wave grids were measured slower: L2->smem fill bound)
   CUtensorMap ma, mb;
   int r;
   if ((r = make_map(e, &ma, A, g.K, g.M, 1, lda, (uint64_t)lda * g.M, 128, 1))) return r;

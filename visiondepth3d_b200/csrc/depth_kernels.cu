@@ -407,9 +407,22 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
   return cudaGetLastError();
 }
 
-cudaError_t launch_gemm(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int m_tiles,
+cudaError_t launch_gemm(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g_in, int m_tiles,
                         int batch, cudaStream_t s) {
-  dim3 grid((g.N + bn - 1) / bn, m_tiles, batch);
+  // persistent grid: two CTAs per SM (97 KB smem, 2 x BN TMEM columns each), each walks its tiles
+  GemmArgs g = g_in;
+  g.nt = (g.N + bn - 1) / bn;
+  g.mt = m_tiles;
+  g.nz = batch;
+  static int resident = 0;
+  if (!resident) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    resident = 2 * sms;
+  }
+  int total = g.nt * g.mt * g.nz;
+  dim3 grid(total < resident ? total : resident, 1, 1);
   switch (bn) {
     case 128: return launch_gemm_t<128, 3>(a, b, g, grid, s);
     case 64: return launch_gemm_t<64, 4>(a, b, g, grid, s);

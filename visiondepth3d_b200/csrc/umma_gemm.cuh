@@ -35,6 +35,7 @@ enum Epi : int {
 
 struct GemmArgs {
   int M, N, K;            // logical sizes (K = total reduction length)
+  int nt, mt, nz;         // tile counts along N, M and batch (filled by launch_gemm)
   int epi;
   int act;                // 0 none, 1 GELU(erf), 2 ReLU
   // conv mode (implicit GEMM over a (C, W, H) activation map)
@@ -191,12 +192,14 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* bars = (uint64_t*)(smem + STAGES * S::kStage);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+  uint64_t* tmem_full = bars + 2 * STAGES;   // [2] accumulator stage complete (MMA -> epilogue)
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2] accumulator stage drained (epilogue -> MMA)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x, m_blk = blockIdx.y, z = blockIdx.z;
+  // persistent: this CTA walks tiles blockIdx.x, +gridDim.x, ...; n fastest so co-resident CTAs share A in L2
+  const int total_tiles = g.nt * g.mt * g.nz;
   const int nkb = (g.K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
@@ -206,29 +209,41 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       umma::mbar_init(umma::smem_u32(&full[s]), 1);
       umma::mbar_init(umma::smem_u32(&empty[s]), 1);
     }
-    umma::mbar_init(umma::smem_u32(tmem_full), 1);
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(umma::smem_u32(&tmem_full[i]), 1);
+      umma::mbar_init(umma::smem_u32(&tmem_empty[i]), 4);
+    }
     umma::fence_barrier_init();
   }
-  if (warp == 1) umma::tmem_alloc(umma::smem_u32(tmem_slot), BN);
+  if (warp == 1) umma::tmem_alloc(umma::smem_u32(tmem_slot), 2 * BN);  // two accumulator stages
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // pixel tile origin for conv mode
-  int px0 = 0, py0 = 0;
-  if (g.conv) {
-    int tiles_x = (g.imgW + g.tw - 1) / g.tw;
-    py0 = (m_blk / tiles_x) * g.th;
-    px0 = (m_blk % tiles_x) * g.tw;
-  }
+  auto decode = [&](int tile, int& n_blk, int& m_blk, int& z, int& px0, int& py0) {
+    n_blk = tile % g.nt;
+    int rem = tile / g.nt;
+    m_blk = rem % g.mt;
+    z = rem / g.mt;
+    px0 = py0 = 0;
+    if (g.conv) {  // pixel tile origin for conv mode
+      int tiles_x = (g.imgW + g.tw - 1) / g.tw;
+      py0 = (m_blk / tiles_x) * g.th;
+      px0 = (m_blk % tiles_x) * g.tw;
+    }
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      int kit = 0;  // k-block counter across tiles (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n_blk, m_blk, z, px0, py0;
+      decode(tile, n_blk, m_blk, z, px0, py0);
+      for (int kb = 0; kb < nkb; ++kb, ++kit) {
+        const int s = kit % STAGES;
+        const uint32_t ph = (kit / STAGES) & 1;
         umma::mbar_wait(umma::smem_u32(&empty[s]), ph ^ 1);
         const uint32_t fb = umma::smem_u32(&full[s]);
         umma::mbar_expect_tx(fb, S::kStage);
@@ -248,14 +263,21 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         umma::tma_load_3d(sb, &tmB, fb, kb * kBK, n_blk * BN, z);
       }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma::make_idesc(BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      int kit = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;  // accumulator stage
+      umma::mbar_wait(umma::smem_u32(&tmem_empty[as]), ((it >> 1) & 1) ^ 1);
+      umma::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
+      for (int kb = 0; kb < nkb; ++kb, ++kit) {
+        const int s = kit % STAGES;
+        const uint32_t ph = (kit / STAGES) & 1;
         umma::mbar_wait(umma::smem_u32(&full[s]), ph);
         umma::tc_fence_after();
         const uint32_t sa = umma::smem_u32(smem + s * S::kStage);
@@ -265,17 +287,24 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
           // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
-          umma::mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma::mma_f16(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
         }
         umma::umma_commit(umma::smem_u32(&empty[s]));  // frees this ring slot when the MMAs retire
       }
-      umma::umma_commit(umma::smem_u32(tmem_full));  // accumulator complete
+      umma::umma_commit(umma::smem_u32(&tmem_full[as]));  // accumulator complete
+      }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    umma::mbar_wait(umma::smem_u32(tmem_full), 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    int n_blk, m_blk, z, px0, py0;
+    decode(tile, n_blk, m_blk, z, px0, py0);
+    const int as = it & 1;
+    umma::mbar_wait(umma::smem_u32(&tmem_full[as]), (it >> 1) & 1);
     umma::tc_fence_after();
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
     const int r = q * 32 + lane;  // accumulator row inside the tile
     int m;                        // logical output row
     bool row_ok;
@@ -292,7 +321,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
-      umma::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      umma::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       const int n0 = n_blk * BN + c0;
       if (!row_ok || n0 >= g.N) continue;
       float a[32];
@@ -451,11 +480,16 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
     if (g.epi == EPI_HEAD && row_ok && n_blk == 0) g.out_f32[m] = fmaxf(head_acc + g.b3p[0], 0.f);
+    // this accumulator stage may be overwritten by the MMA warp
+    umma::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(&tmem_empty[as])) : "memory");
+    }
   }
 
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem_base, BN);
+  if (warp == 1) umma::tmem_dealloc(tmem_base, 2 * BN);
 }
 
 }  // namespace vd3d
