@@ -207,7 +207,7 @@ int vd3d_depth_create(const vd3d_depth_config* cfg, void* stream, vd3d_depth** o
   if (!cfg || !out) return VD3D_ERR_ARG;
   *out = nullptr;
   if (!load_encode()) return VD3D_ERR_CUDA;
-  if (cfg->hidden % 64 || cfg->hidden > 1024 || cfg->hidden / cfg->heads != 64 || cfg->fusion % 64 ||
+  if (cfg->hidden % 128 || cfg->hidden > 1024 || cfg->hidden / cfg->heads != 64 || cfg->fusion % 64 ||
       cfg->image_h % 14 || cfg->image_w % 14)
     return VD3D_ERR_ARG;
   vd3d_depth* e = new vd3d_depth();

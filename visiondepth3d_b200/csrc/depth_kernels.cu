@@ -19,28 +19,40 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ x, 
   int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* xr = x + (size_t)(row + row_off) * D;
-  float v[32];  // D <= 1024
+  const float4* xr = (const float4*)(x + (size_t)(row + row_off) * D);
+  float4 v[8];  // D <= 1024, D % 128 == 0: lane owns float4 #(lane + 32 i)
+  const int n = D / 128;
   float s = 0.f;
-  int n = D / 32;
-  for (int i = 0; i < n; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += v[i];
-  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < n) {
+      v[i] = xr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  float mean = s / (float)D;
+  const float mean = s / (float)D;
   float q = 0.f;
-  for (int i = 0; i < n; ++i) {
-    float d = v[i] - mean;
-    q += d * d;
-  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < n) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
   for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  float rstd = rsqrtf(q / (float)D + eps);
-  __half* orow = out + (size_t)row * D;
-  for (int i = 0; i < n; ++i) {
-    int c = lane + 32 * i;
-    orow[c] = __float2half_rn((v[i] - mean) * rstd * gamma[c] + beta[c]);
-  }
+  const float rstd = rsqrtf(q / (float)D + eps);
+  uint2* orow = (uint2*)(out + (size_t)row * D);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < n) {
+      const int c4 = lane + 32 * i;
+      float4 g4 = ((const float4*)gamma)[c4], b4 = ((const float4*)beta)[c4];
+      __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g4.x + b4.x, (v[i].y - mean) * rstd * g4.y + b4.y);
+      __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * g4.z + b4.z, (v[i].w - mean) * rstd * g4.w + b4.w);
+      uint2 u;
+      u.x = *(uint32_t*)&h0;
+      u.y = *(uint32_t*)&h1;
+      orow[c4] = u;
+    }
 }
 
 // softmax over keys (scores already scaled: q was multiplied by 1/sqrt(d)); one warp per row,

@@ -27,14 +27,17 @@ struct AttnArgs {
 };
 
 constexpr int kAttnThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 per TMEM lane quarter)
-constexpr int kAttnKS = 3, kAttnVS = 2;
-constexpr int kAttnSmem = 16384 /*Q*/ + kAttnKS * 16384 + kAttnVS * 16384 + 2 * 32768 /*P*/ + 1024 + 512 + 2048;
+// Two CTAs per SM (96 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs
+// and 240 CTAs (20 query blocks x 12 heads) fit in a single wave of 296 slots.
+constexpr int kAttnKS = 2, kAttnVS = 1, kAttnSB = 1, kAttnPB = 1;
+constexpr int kAttnTmemCols = 256;  // S: kAttnSB x 128, O: 64
+constexpr int kAttnSmem = 16384 /*Q*/ + kAttnKS * 16384 + kAttnVS * 16384 + kAttnPB * 32768 /*P*/ + 1024 + 512 + 2048;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -43,7 +46,7 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* sK = smem + 16384;
   uint8_t* sV = sK + kAttnKS * 16384;
   uint8_t* sP = sV + kAttnVS * 16384;
-  uint64_t* bars = (uint64_t*)(sP + 2 * 32768);
+  uint64_t* bars = (uint64_t*)(sP + kAttnPB * 32768);
   uint64_t* q_full = bars;               // 1
   uint64_t* k_full = bars + 1;           // KS
   uint64_t* k_empty = k_full + kAttnKS;  // KS
@@ -74,7 +77,7 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       umma::mbar_init(umma::smem_u32(&v_full[i]), 1);
       umma::mbar_init(umma::smem_u32(&v_empty[i]), 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2; ++i) {  // (slots beyond kAttnSB / kAttnPB are simply unused)
       umma::mbar_init(umma::smem_u32(&s_full[i]), 1);
       umma::mbar_init(umma::smem_u32(&s_empty[i]), 8);
       umma::mbar_init(umma::smem_u32(&p_full[i]), 8);
@@ -83,13 +86,13 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     umma::mbar_init(umma::smem_u32(o_full), 1);
     umma::fence_barrier_init();
   }
-  if (warp == 1) umma::tmem_alloc(umma::smem_u32(tmem_slot), 512);
+  if (warp == 1) umma::tmem_alloc(umma::smem_u32(tmem_slot), kAttnTmemCols);
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tmem_O = tmem_base + 256;
+  const uint32_t tmem_S[2] = {tmem_base, tmem_base + 128};  // [1] only used when kAttnSB == 2
+  const uint32_t tmem_O = tmem_base + kAttnSB * 128;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -126,8 +129,8 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       auto issue_S = [&](int gi) {  // gi: global S iteration 0 .. 2T-1
         const int ks = kiter % kAttnKS;
         umma::mbar_wait(umma::smem_u32(&k_full[ks]), (kiter / kAttnKS) & 1);
-        const int sb = gi & 1;
-        umma::mbar_wait(umma::smem_u32(&s_empty[sb]), ((gi >> 1) & 1) ^ 1);
+        const int sb = gi % kAttnSB;
+        umma::mbar_wait(umma::smem_u32(&s_empty[sb]), ((gi / kAttnSB) & 1) ^ 1);
         umma::tc_fence_after();
         const uint64_t dk = umma::make_desc(umma::smem_u32(sK + ks * 16384));
 #pragma unroll
@@ -142,8 +145,8 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       issue_S(T);
       for (int t = 0; t < T; ++t) {
         if (t + 1 < T) issue_S(T + t + 1);
-        const int pb = t & 1, vs = t % kAttnVS;
-        umma::mbar_wait(umma::smem_u32(&p_full[pb]), (t >> 1) & 1);
+        const int pb = t % kAttnPB, vs = t % kAttnVS;
+        umma::mbar_wait(umma::smem_u32(&p_full[pb]), (t / kAttnPB) & 1);
         umma::mbar_wait(umma::smem_u32(&v_full[vs]), (t / kAttnVS) & 1);
         umma::tc_fence_after();
         const uint32_t pa = umma::smem_u32(sP + pb * 32768);
@@ -169,8 +172,8 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float mx = -INFINITY;
     // ---- pass A: exact row maximum ----
     for (int gi = 0; gi < T; ++gi) {
-      const int sb = gi & 1;
-      umma::mbar_wait(umma::smem_u32(&s_full[sb]), (gi >> 1) & 1);
+      const int sb = gi % kAttnSB;
+      umma::mbar_wait(umma::smem_u32(&s_full[sb]), (gi / kAttnSB) & 1);
       umma::tc_fence_after();
       const int nvalid = min(128, g.ntok - gi * 128) - half * 64;
 #pragma unroll 1
@@ -193,9 +196,9 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     float sum = 0.f;
     const float mxl = mx * 1.4426950408889634f;
     for (int t = 0; t < T; ++t) {
-      const int gi = T + t, sb = gi & 1, pb = t & 1;
-      umma::mbar_wait(umma::smem_u32(&s_full[sb]), (gi >> 1) & 1);
-      umma::mbar_wait(umma::smem_u32(&p_empty[pb]), ((t >> 1) & 1) ^ 1);
+      const int gi = T + t, sb = gi % kAttnSB, pb = t % kAttnPB;
+      umma::mbar_wait(umma::smem_u32(&s_full[sb]), (gi / kAttnSB) & 1);
+      umma::mbar_wait(umma::smem_u32(&p_empty[pb]), ((t / kAttnPB) & 1) ^ 1);
       umma::tc_fence_after();
       const int nvalid = min(128, g.ntok - t * 128) - half * 64;
       uint8_t* pblk = sP + pb * 32768 + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;  // this row, this 64-key block
@@ -258,7 +261,7 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 1) umma::tmem_dealloc(tmem_base, 512);
+  if (warp == 1) umma::tmem_dealloc(tmem_base, kAttnTmemCols);
 }
 
 }  // namespace vd3d
