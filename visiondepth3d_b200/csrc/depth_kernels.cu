@@ -436,7 +436,10 @@ cudaError_t launch_gemm(int bn, const CUtensorMap& a, const CUtensorMap& b, cons
   int total = g.nt * g.mt * g.nz;
   dim3 grid(total < resident ? total : resident, 1, 1);
   switch (bn) {
-    case 128: return launch_gemm_t<128, 3>(a, b, g, grid, s);
+    case 128:
+      // <= one CTA per SM: a deeper operand ring (6 x 32 KB) keeps twice the TMA bytes in flight
+      if (total <= resident / 2) return launch_gemm_t<128, 6>(a, b, g, grid, s);
+      return launch_gemm_t<128, 3>(a, b, g, grid, s);
     case 64: return launch_gemm_t<64, 4>(a, b, g, grid, s);
     case 32: return launch_gemm_t<32, 4>(a, b, g, grid, s);
     default: return cudaErrorInvalidValue;

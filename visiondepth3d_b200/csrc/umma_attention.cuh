@@ -176,13 +176,24 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       umma::mbar_wait(umma::smem_u32(&s_full[sb]), (gi / kAttnSB) & 1);
       umma::tc_fence_after();
       const int nvalid = min(128, g.ntok - gi * 128) - half * 64;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        umma::tmem_ld_32x32(tmem_S[sb] + lane_off + col_off + (uint32_t)(c * 32), v);
+      {
+        uint32_t v[64];
+        umma::tmem_ld_32x64(tmem_S[sb] + lane_off + col_off, v);
+        if (nvalid >= 64) {  // full tile: no masking
+          float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int j = 0; j < 64; j += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[j]));
+            m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+            m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
       }
       umma::tc_fence_before();
       __syncwarp();
@@ -202,24 +213,37 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       umma::tc_fence_after();
       const int nvalid = min(128, g.ntok - t * 128) - half * 64;
       uint8_t* pblk = sP + pb * 32768 + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;  // this row, this 64-key block
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        umma::tmem_ld_32x32(tmem_S[sb] + lane_off + col_off + (uint32_t)(c * 32), v);
-        uint32_t pk[16];
+      {
+        uint32_t v[64];
+        umma::tmem_ld_32x64(tmem_S[sb] + lane_off + col_off, v);
+        uint32_t pk[32];
+        const float L2E = 1.4426950408889634f;
+        if (nvalid >= 64) {  // full tile: one FFMA + MUFU.EX2 + FADD per score
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float p0 = (c * 32 + j < nvalid) ? exp2f(__uint_as_float(v[j]) * 1.4426950408889634f - mxl) : 0.f;
-          float p1 = (c * 32 + j + 1 < nvalid) ? exp2f(__uint_as_float(v[j + 1]) * 1.4426950408889634f - mxl) : 0.f;
-          sum += p0 + p1;
-          __half2 hp = __floats2half2_rn(p0, p1);
-          pk[j >> 1] = *(uint32_t*)&hp;
+          for (int j = 0; j < 64; j += 2) {
+            float p0 = umma::ex2_fast(fmaf(__uint_as_float(v[j]), L2E, -mxl));
+            float p1 = umma::ex2_fast(fmaf(__uint_as_float(v[j + 1]), L2E, -mxl));
+            s0 += p0;
+            s1 += p1;
+            __half2 hp = __floats2half2_rn(p0, p1);
+            pk[j >> 1] = *(uint32_t*)&hp;
+          }
+          sum += s0 + s1;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; j += 2) {
+            float p0 = (j < nvalid) ? umma::ex2_fast(fmaf(__uint_as_float(v[j]), L2E, -mxl)) : 0.f;
+            float p1 = (j + 1 < nvalid) ? umma::ex2_fast(fmaf(__uint_as_float(v[j + 1]), L2E, -mxl)) : 0.f;
+            sum += p0 + p1;
+            __half2 hp = __floats2half2_rn(p0, p1);
+            pk[j >> 1] = *(uint32_t*)&hp;
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = c * 4 + i;       // logical 16-byte chunk inside the 128-byte row
-          const int phys = idx ^ (r & 7);  // 128B swizzle
-          *(uint4*)(pblk + phys * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        for (int idx = 0; idx < 8; ++idx) {    // logical 16-byte chunk inside the 128-byte row
+          const int phys = idx ^ (r & 7);      // 128B swizzle
+          *(uint4*)(pblk + phys * 16) = make_uint4(pk[4 * idx], pk[4 * idx + 1], pk[4 * idx + 2], pk[4 * idx + 3]);
         }
       }
       umma::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
