@@ -287,14 +287,26 @@ __global__ void __launch_bounds__(256) k_depth_upsample_minmax(const float* __re
     }
     out[(size_t)oy * OW + ox] = v;
   }
+  __shared__ float slo[8], shi[8];
   float lo = ok ? v : INFINITY, hi = ok ? v : -INFINITY;
   for (int o = 16; o; o >>= 1) {
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if ((threadIdx.x & 31) == 0 && lo <= hi) {
-    atomicMin(&mm[0], f2ord(lo));
-    atomicMax(&mm[1], f2ord(hi));
+  if ((threadIdx.x & 31) == 0) {
+    slo[threadIdx.x >> 5] = lo;
+    shi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // one pair of atomics per block (was per warp: 130 K serialised atomics at 1080p)
+    for (int i = 1; i < 8; ++i) {
+      lo = fminf(lo, slo[i]);
+      hi = fmaxf(hi, shi[i]);
+    }
+    if (lo <= hi) {
+      atomicMin(&mm[0], f2ord(lo));
+      atomicMax(&mm[1], f2ord(hi));
+    }
   }
 }
 __global__ void k_minmax_reset(unsigned* mm) {

@@ -373,9 +373,25 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         case EPI_F16: {
           size_t o = (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
           if (g.res_f16) {
+            if (nvalid == 32 && ((o & 7) == 0)) {
+              uint4 rv[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) a[j] += __half2float(g.res_f16[o + j]);
+              for (int j = 0; j < 4; ++j) rv[j] = __ldg((const uint4*)(g.res_f16 + o) + j);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __half2* hh = (const __half2*)&rv[j];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  float2 f = __half22float2(hh[t]);
+                  a[8 * j + 2 * t] += f.x;
+                  a[8 * j + 2 * t + 1] += f.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) a[j] += __half2float(g.res_f16[o + j]);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -498,7 +514,24 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int dy = tap / g.ct_k, dx = tap % g.ct_k;
           const int y = m / g.ct_w, x = m % g.ct_w;
           size_t o = ((size_t)(y * g.ct_k + dy) * (g.ct_w * g.ct_k) + (x * g.ct_k + dx)) * g.ct_cout + co;
-          for (int j = 0; j < nvalid; ++j) g.out_f16[o + j] = __float2half_rn(a[j]);
+          if (nvalid == 32 && ((o & 7) == 0)) {
+            uint4* dst = (uint4*)(g.out_f16 + o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __half2 h0 = __floats2half2_rn(a[8 * j + 0], a[8 * j + 1]);
+              __half2 h1 = __floats2half2_rn(a[8 * j + 2], a[8 * j + 3]);
+              __half2 h2 = __floats2half2_rn(a[8 * j + 4], a[8 * j + 5]);
+              __half2 h3 = __floats2half2_rn(a[8 * j + 6], a[8 * j + 7]);
+              uint4 u;
+              u.x = *(uint32_t*)&h0;
+              u.y = *(uint32_t*)&h1;
+              u.z = *(uint32_t*)&h2;
+              u.w = *(uint32_t*)&h3;
+              dst[j] = u;
+            }
+          } else {
+            for (int j = 0; j < nvalid; ++j) g.out_f16[o + j] = __float2half_rn(a[j]);
+          }
         } break;
         case EPI_HEAD: {
           for (int j = 0; j < nvalid; ++j) head_acc += fmaxf(a[j], 0.f) * g.w3[n0 + j];
