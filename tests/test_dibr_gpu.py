@@ -240,3 +240,13 @@ def test_full_size_properties(R, cfg):
     # property: determinism / idempotent state reset
     R.reset_temporal_state()
     assert np.array_equal(R.render_frame(fr, dp, rp), out)
+
+
+def test_format_3d_output_on_gpu(R):
+    rng = np.random.default_rng(11)
+    l = rng.integers(0, 256, (45, 67, 3), dtype=np.uint8)
+    r = rng.integers(0, 256, (45, 67, 3), dtype=np.uint8)
+    assert np.array_equal(R.format_3d_output(l, r, "Full-SBS"), np.hstack((l, r)))
+    assert np.array_equal(R.format_3d_output(l, r, "Half-SBS"), np.hstack((l, r)))
+    assert np.array_equal(R.generate_anaglyph_3d(l, r), O.anaglyph(l, r))
+    assert np.array_equal(R.format_3d_output(l, r, "Passive Interlaced"), O.format_output(l, r, "Passive Interlaced"))

@@ -1179,6 +1179,48 @@ int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor,
   return VD3D_OK;
 }
 
+// format_3d_output / generate_anaglyph_3d (core/render_3d.py:837-883) on two same-size u8 BGR eyes
+int vd3d_pack(vd3d_ctx* ctx, const uint8_t* left, const uint8_t* right, int h, int w, int fmt, uint8_t* dst, int mem) {
+  if (!ctx || !left || !right || !dst || h < 1 || w < 1) return fail(ctx, VD3D_ERR_ARG, "bad argument");
+  if (fmt < VD3D_FMT_HALF_SBS || fmt > VD3D_FMT_INTERLACED) return fail(ctx, VD3D_ERR_UNSUPPORTED, "format");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t bytes = (size_t)h * w * 3;
+  bool sbs = (fmt == VD3D_FMT_HALF_SBS || fmt == VD3D_FMT_FULL_SBS);
+  size_t obytes = sbs ? bytes * 2 : bytes;
+  const void *l_d, *r_d;
+  int r;
+  if ((r = copy_in(ctx, ctx->eyeL, left, bytes, mem, s, &l_d))) return r;
+  if ((r = copy_in(ctx, ctx->eyeR, right, bytes, mem, s, &r_d))) return r;
+  uint8_t* o_d = dst;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->out_dev[0], obytes))) return r;
+    o_d = (uint8_t*)ctx->out_dev[0].p;
+  }
+  PostArgs pa;
+  memset(&pa, 0, sizeof pa);
+  pa.left = (const uint8_t*)l_d;
+  pa.right = (const uint8_t*)r_d;
+  pa.H = h;
+  pa.W = w;
+  pa.fmt = fmt;
+  pa.per_eye_w = w;
+  pa.per_eye_h = h;
+  pa.fit_w = w;
+  pa.fit_h = h;
+  pa.sx = pa.sy = 1;
+  pa.inv_area = 1.f;
+  pa.out = o_d;
+  pa.out_w = sbs ? 2 * w : w;
+  pa.out_h = h;
+  launch_post(pa, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(dst, o_d, obytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+
 int vd3d_dof_grade(vd3d_ctx* ctx, const uint8_t* eye_bgr, int h, int w, const float* depth01, int dh, int dw,
                    double focal, double max_sigma, double sat, double con, double bri, uint8_t* dst, int mem) {
   if (!ctx || !eye_bgr || !dst || h < 2 || w < 2) return fail(ctx, VD3D_ERR_ARG, "bad argument");

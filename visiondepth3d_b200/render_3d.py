@@ -190,33 +190,31 @@ def pad_to_aspect_ratio(image, target_width, target_height, bg_color=(0, 0, 0)):
     return out
 
 
+def _pack(left, right, fmt):
+    """format_3d_output on the GPU (vd3d_pack): SBS hstack, Dubois anaglyph, row interlace."""
+    ctx = _ctx()
+    l = np.ascontiguousarray(left, dtype=np.uint8)
+    r = np.ascontiguousarray(right, dtype=np.uint8)
+    assert l.shape == r.shape and l.ndim == 3 and l.shape[2] == 3, "Shape mismatch"
+    h, w = l.shape[:2]
+    code = _lib.FMT[fmt]
+    out = np.empty((h, 2 * w, 3) if code in (0, 1) else (h, w, 3), dtype=np.uint8)
+    ctx.check(ctx.lib.vd3d_pack(ctx.h, l.ctypes.data, r.ctypes.data, h, w, code, out.ctypes.data, _lib.MEM_HOST))
+    return out
+
+
 def generate_anaglyph_3d(left_frame, right_frame):
-    """core/render_3d.py:862-883 via the pack kernel (identity fit, no sharpen)."""
+    """core/render_3d.py:862-883 (Dubois matrix on channel indices 0,1,2 as written there)."""
     return _pack(left_frame, right_frame, "Red-Cyan Anaglyph")
 
 
 def format_3d_output(left, right, fmt):
     """core/render_3d.py:837-860."""
-    if fmt in ("Red-Cyan Anaglyph",):
-        return generate_anaglyph_3d(left, right)
-    if fmt == "Passive Interlaced":
-        out = np.zeros_like(left)
-        out[::2] = left[::2]
-        out[1::2] = right[1::2]
-        return out
     if fmt == "VR":
         raise NotImplementedError("VR (1440x1600 INTER_LINEAR) is outside the B200 hot path")
-    return np.hstack((left, right))
-
-
-def _pack(left, right, fmt):
-    l = np.asarray(left).astype(np.float32) / np.float32(255.0)
-    r = np.asarray(right).astype(np.float32) / np.float32(255.0)
-    red = (np.float32(0.4561) * l[..., 0] + np.float32(0.5005) * l[..., 1]) + np.float32(0.1762) * l[..., 2]
-    grn = (np.float32(0.3764) * r[..., 0] + np.float32(0.7616) * r[..., 1]) - np.float32(0.1876) * r[..., 2]
-    blu = (np.float32(-0.0401) * r[..., 0] - np.float32(0.1126) * r[..., 1]) + np.float32(1.2723) * r[..., 2]
-    out = np.stack([np.clip(red, 0, 1), np.clip(grn, 0, 1), np.clip(blu, 0, 1)], -1).astype(np.float32)
-    return (out * np.float32(255)).astype(np.uint8)
+    if fmt not in ("Half-SBS", "Full-SBS", "Red-Cyan Anaglyph", "Passive Interlaced"):
+        fmt = "Half-SBS"  # the reference falls back to hstack (860)
+    return _pack(left, right, fmt)
 
 
 # ---------------------------------------------------------------------------
