@@ -179,6 +179,9 @@ int vd3d_render_clip(vd3d_ctx* ctx, int n, const uint8_t* const* frames, const u
 int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_t* const* frames, int src_h,
                            int src_w, const vd3d_render_params* rp, uint8_t* const* outs, int mem);
 
+/* drop the per-ctx clones / graphs built for `depth`; call before vd3d_depth_destroy(depth) */
+int vd3d_release_depth(vd3d_ctx* ctx, vd3d_depth* depth);
+
 /* stage entry points (same kernels, exposed for stage-isolated parity tests) */
 /* apply_sharpening (717-732) on u8 BGR [h,w,3] */
 int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem);
@@ -203,6 +206,8 @@ typedef struct {
 } vd3d_depth_config;
 int vd3d_depth_create(const vd3d_depth_config* cfg, void* cuda_stream, vd3d_depth** out);
 void vd3d_depth_destroy(vd3d_depth* e);
+/* another instance on `cuda_stream` sharing e's weights (own activations); destroy it before e */
+int vd3d_depth_clone(vd3d_depth* e, void* cuda_stream, vd3d_depth** out);
 const char* vd3d_depth_last_error(vd3d_depth* e);
 uint64_t vd3d_depth_launch_count(vd3d_depth* e);
 void vd3d_depth_add_launches(vd3d_depth* e, uint64_t n); /* bookkeeping for CUDA-graph replays */

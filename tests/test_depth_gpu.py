@@ -127,3 +127,35 @@ def test_infer_matches_hf_pipeline_stages():
         du = np.abs(d8.astype(int) - _depth_u8(ref).astype(int))
         assert du.max() <= 4 and (du > 1).mean() <= 5e-3, (du.max(), (du > 0).mean())
     e.close()
+
+
+def test_clip_depth_pipeline_equals_stagewise():
+    """vd3d_render_clip_depth (two depth streams + graphs + in-HBM u8 handoff) must equal
+    depth inference followed by vd3d_render_frame with that u8 depth, frame by frame."""
+    import ctypes as C
+    from visiondepth3d_b200 import _lib
+    from visiondepth3d_b200 import render_3d as R
+    from visiondepth3d_b200.depth_engine import DepthEngine
+    from visiondepth3d_b200.synth import synth_frame
+    sd = _model("vits")
+    w, h = 640, 360
+    e = DepthEngine("vits", 364, 644)  # DPT size for a 16:9 frame of height 360: round(360*518/360 ...) -> any /14 size works
+    e.load_state_dict(sd)
+    rp = R.make_render_params(w, h, 4.5, -1.5, -6.0, 0.2, "Half-SBS", 16 / 9, 0.0, 10.0, 9, True, True,
+                              zero_parallax_strength=0.01)
+    frames = [synth_frame(i, w, h, "smooth")[0] for i in range(7)]
+    ctx = e.ctx
+    ctx.reset()
+    ref = []
+    for f in frames:
+        _, d8 = e.infer(f)
+        ref.append(R.render_frame(f, d8, rp, ctx=ctx))
+    ctx.reset()
+    n = len(frames)
+    outs = [np.empty_like(ref[0]) for _ in range(n)]
+    fp = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    ctx.check(ctx.lib.vd3d_render_clip_depth(ctx.h, e.h, n, fp, h, w, C.byref(rp), op, _lib.MEM_HOST))
+    for i, (a, b) in enumerate(zip(ref, outs)):
+        assert np.array_equal(a, b), i
+    e.close()

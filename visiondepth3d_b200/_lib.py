@@ -85,7 +85,7 @@ SYMBOLS = [
     # depth forward (bound in depth_engine.py)
     "vd3d_depth_create", "vd3d_depth_destroy", "vd3d_depth_last_error", "vd3d_depth_launch_count",
     "vd3d_depth_set_tensor", "vd3d_depth_forward", "vd3d_depth_get_buffer", "vd3d_gemm_f16", "vd3d_conv_f16",
-    "vd3d_depth_infer", "vd3d_depth_infer_device", "vd3d_render_clip_depth", "vd3d_depth_add_launches",
+    "vd3d_depth_infer", "vd3d_depth_infer_device", "vd3d_render_clip_depth", "vd3d_depth_add_launches", "vd3d_depth_clone", "vd3d_release_depth",
 ]
 
 _lib = None
@@ -147,6 +147,8 @@ def load():
     lib.vd3d_render_clip_depth.restype = i
     lib.vd3d_pack.argtypes = [vp, u8p, u8p, i, i, i, u8p, i]
     lib.vd3d_pack.restype = i
+    lib.vd3d_release_depth.argtypes = [vp, vp]
+    lib.vd3d_release_depth.restype = i
     lib.vd3d_sharpen.argtypes = [vp, u8p, i, i, C.c_double, u8p, i]
     lib.vd3d_sharpen.restype = i
     lib.vd3d_dof_grade.argtypes = [vp, u8p, i, i, fp, i, i, C.c_double, C.c_double, C.c_double, C.c_double,

@@ -55,6 +55,7 @@ struct vd3d_depth {
   int ph = 0, pw = 0, ntok = 0, npad = 0;
   bool planned = false;
   bool flash = true;  // fused attention kernel (VD3D_FLASH=0 selects the 3-kernel path)
+  bool owns_weights = true;  // clones share the weight tensors of their parent
 };
 
 namespace {
@@ -226,11 +227,29 @@ int vd3d_depth_create(const vd3d_depth_config* cfg, void* stream, vd3d_depth** o
   return VD3D_OK;
 }
 
+// A second engine instance on another stream that shares the parent's weights (own activation
+// buffers): lets two frames' depth forwards overlap on the GPU (vd3d_render_clip_depth).
+int vd3d_depth_clone(vd3d_depth* src, void* stream, vd3d_depth** out) {
+  if (!src || !out) return VD3D_ERR_ARG;
+  vd3d_depth* e = new vd3d_depth();
+  e->cfg = src->cfg;
+  e->stream = (cudaStream_t)stream;
+  e->w = src->w;
+  e->owns_weights = false;
+  e->ph = src->ph;
+  e->pw = src->pw;
+  e->ntok = src->ntok;
+  e->npad = src->npad;
+  e->flash = src->flash;
+  *out = e;
+  return VD3D_OK;
+}
+
 void vd3d_depth_destroy(vd3d_depth* e) {
   if (!e) return;
   cudaStreamSynchronize(e->stream);
   for (auto& kv : e->w)
-    if (kv.second.p) cudaFree(kv.second.p);
+    if (e->owns_weights && kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : e->buf)
     if (kv.second.p) cudaFree(kv.second.p);
   delete e;

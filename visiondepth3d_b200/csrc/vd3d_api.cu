@@ -74,6 +74,17 @@ struct vd3d_ctx {
   vd3d_render_params fg_rp;
   int fg_h = 0, fg_w = 0, fg_dch = 0, fg_warm = 0;
   void* fg_depth = nullptr;
+  // depth stage of the depth+stereo clip: two engine clones (shared weights) on two streams so the
+  // depth forwards of consecutive frames overlap each other and the DIBR kernels of the previous frame
+  vd3d_depth* dclone[2] = {nullptr, nullptr};
+  vd3d_depth* dclone_parent = nullptr;
+  cudaStream_t s_depth[2] = {nullptr, nullptr};
+  cudaEvent_t ev_depth[2] = {nullptr, nullptr};
+  struct DepthGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t n = 0;
+  } dg[2];
+  int dg_warm = 0, dg_h = 0, dg_w = 0;
   // dof kernel cache
   double dof_sigma_cached = -1.0;
   int dof_nlevels = 0, dof_ksize[8] = {0}, dof_koff[8] = {0}, dof_halo = 0;
@@ -81,6 +92,9 @@ struct vd3d_ctx {
 
 extern "C" {
 static void drop_graphs(vd3d_ctx* ctx);
+static void drop_depth_graphs(vd3d_ctx* ctx);
+int vd3d_depth_clone(vd3d_depth* e, void* cuda_stream, vd3d_depth** out);
+void vd3d_depth_destroy(vd3d_depth* e);
 }
 
 namespace {
@@ -512,6 +526,12 @@ void vd3d_destroy(vd3d_ctx* ctx) {
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   drop_graphs(ctx);
+  drop_depth_graphs(ctx);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
+    if (ctx->s_depth[i]) cudaStreamDestroy(ctx->s_depth[i]);
+    if (ctx->ev_depth[i]) cudaEventDestroy(ctx->ev_depth[i]);
+  }
   cudaFree(ctx->st);
   cudaFree(ctx->fs);
   cudaFree(ctx->jobwords);
@@ -944,6 +964,79 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
 extern "C" uint64_t vd3d_depth_launch_count(vd3d_depth* e);
 extern "C" void vd3d_depth_add_launches(vd3d_depth* e, uint64_t n);
 
+static void drop_depth_graphs(vd3d_ctx* ctx) {
+  for (int i = 0; i < 2; ++i)
+    if (ctx->dg[i].exec) {
+      cudaGraphExecDestroy(ctx->dg[i].exec);
+      ctx->dg[i].exec = nullptr;
+    }
+  ctx->dg_warm = 0;
+}
+
+static int ensure_depth_clones(vd3d_ctx* ctx, vd3d_depth* parent) {
+  if (ctx->dclone_parent == parent && ctx->dclone[0]) return VD3D_OK;
+  drop_depth_graphs(ctx);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
+    ctx->dclone[i] = nullptr;
+    if (!ctx->s_depth[i]) CK(cudaStreamCreateWithFlags(&ctx->s_depth[i], cudaStreamNonBlocking));
+    if (!ctx->ev_depth[i]) CK(cudaEventCreateWithFlags(&ctx->ev_depth[i], cudaEventDisableTiming));
+    if (vd3d_depth_clone(parent, ctx->s_depth[i], &ctx->dclone[i]) != VD3D_OK)
+      return fail(ctx, VD3D_ERR_ARG, "vd3d_depth_clone failed");
+  }
+  ctx->dclone_parent = parent;
+  return VD3D_OK;
+}
+
+// depth inference of staging slot b on its own stream (graph-replayed after two eager frames)
+static int run_depth_slot(vd3d_ctx* ctx, vd3d_depth* parent, int b, int src_h, int src_w) {
+  vd3d_depth* e = ctx->dclone[b];
+  const uint8_t* f_d = (const uint8_t*)ctx->in_frame[b].p;
+  uint8_t* d_d = (uint8_t*)ctx->in_depth[b].p;
+  if (ctx->dg_h != src_h || ctx->dg_w != src_w) {
+    drop_depth_graphs(ctx);
+    ctx->dg_h = src_h;
+    ctx->dg_w = src_w;
+  }
+  auto eager = [&]() -> int {
+    uint64_t l0 = vd3d_depth_launch_count(e);
+    int r = vd3d_depth_infer_device(e, f_d, src_h, src_w, d_d, nullptr, 0);
+    if (r) ctx->err = std::string("depth engine: ") + vd3d_depth_last_error(e);
+    vd3d_depth_add_launches(parent, vd3d_depth_launch_count(e) - l0);
+    return r;
+  };
+  if (!ctx->use_graphs || ctx->dg_warm < 2) {
+    ctx->dg_warm++;
+    return eager();
+  }
+  vd3d_ctx::DepthGraph& g = ctx->dg[b];
+  if (!g.exec) {
+    uint64_t l0 = vd3d_depth_launch_count(e), p0 = vd3d_depth_launch_count(parent);
+    if (cudaStreamBeginCapture(ctx->s_depth[b], cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->use_graphs = 0;
+      return eager();
+    }
+    int r = vd3d_depth_infer_device(e, f_d, src_h, src_w, d_d, nullptr, 0);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(ctx->s_depth[b], &graph);
+    uint64_t n = vd3d_depth_launch_count(e) - l0;
+    (void)p0;
+    if (r != VD3D_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      g.exec = nullptr;
+      ctx->use_graphs = 0;
+      return eager();
+    }
+    cudaGraphDestroy(graph);
+    g.n = n;
+  }
+  CK(cudaGraphLaunch(g.exec, ctx->s_depth[b]));
+  vd3d_depth_add_launches(parent, g.n);
+  return VD3D_OK;
+}
+
 static void drop_graphs(vd3d_ctx* ctx) {
   for (int i = 0; i < 2; ++i)
     for (int j = 0; j < 2; ++j)
@@ -1115,19 +1208,30 @@ int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_
     if ((r = ensure(ctx, ctx->in_depth[b], db))) return r;
     if ((r = ensure(ctx, ctx->out_dev[b], ob))) return r;
   }
+  const bool serial = ctx->prof != 0;  // stage timing wants one stream; otherwise depth runs on its own streams
+  if (!serial && (r = ensure_depth_clones(ctx, depth))) return r;
   for (int i = 0; i < n; ++i) {
     int b = i & 1;
-    if (mem == VD3D_MEM_DEVICE) {
-      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
-      CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyDeviceToDevice, ctx->stream));
-    } else {
-      if (i >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
-      CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyHostToDevice, ctx->s_h2d));
-      CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+    // ---- stage the frame into slot b (free once DIBR of frame i-2 has finished) ----
+    if (i >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
+    CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb,
+                       mem == VD3D_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+    if (serial) {
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
       if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+      if ((r = run_frame_slot(ctx, depth, b, 1, src_h, src_w, rp, pl))) return r;
+    } else {
+      // ---- depth of frame i on stream b: overlaps depth(i-1) and DIBR(i-1) ----
+      CK(cudaStreamWaitEvent(ctx->s_depth[b], ctx->ev_h2d[b], 0));
+      if (i >= 2) CK(cudaStreamWaitEvent(ctx->s_depth[b], ctx->ev_done[b], 0));  // in_depth[b] consumed
+      if ((r = run_depth_slot(ctx, depth, b, src_h, src_w))) return r;
+      CK(cudaEventRecord(ctx->ev_depth[b], ctx->s_depth[b]));
+      // ---- DIBR loop body on the main stream (sequential temporal state) ----
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_depth[b], 0));
+      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));        // out_dev[b] drained
+      if ((r = run_frame_slot(ctx, nullptr, b, 1, src_h, src_w, rp, pl))) return r;
     }
-    if ((r = run_frame_slot(ctx, depth, b, 1, src_h, src_w, rp, pl))) return r;
     CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
     CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[b], 0));
     CK(cudaMemcpyAsync(outs[i], ctx->out_dev[b].p, ob,
@@ -1136,6 +1240,28 @@ int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_
   }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaStreamSynchronize(ctx->s_d2h));
+  if (!serial) {
+    CK(cudaStreamSynchronize(ctx->s_depth[0]));
+    CK(cudaStreamSynchronize(ctx->s_depth[1]));
+  }
+  return VD3D_OK;
+}
+
+// forget the engine clones made for `depth` (call before destroying that engine)
+int vd3d_release_depth(vd3d_ctx* ctx, vd3d_depth* depth) {
+  if (!ctx) return VD3D_ERR_ARG;
+  if (ctx->dclone_parent == depth || !depth) {
+    cudaStreamSynchronize(ctx->stream);
+    drop_depth_graphs(ctx);
+    drop_graphs(ctx);
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->s_depth[i]) cudaStreamSynchronize(ctx->s_depth[i]);
+      if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
+      ctx->dclone[i] = nullptr;
+    }
+    ctx->dclone_parent = nullptr;
+    ctx->fg_depth = nullptr;
+  }
   return VD3D_OK;
 }
 

@@ -127,5 +127,13 @@ class DepthEngine:
 
     def close(self):
         if getattr(self, "h", None):
+            if getattr(self.ctx, "h", None):
+                self.lib.vd3d_release_depth(self.ctx.h, self.h)
             self.lib.vd3d_depth_destroy(self.h)
             self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
