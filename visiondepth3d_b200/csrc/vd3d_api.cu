@@ -31,6 +31,7 @@ struct JobMem {  // device memory of one selection job
   SelTarget* tg;
 };
 
+constexpr int kSlots = 3;  // frames in flight (staging buffers, depth streams)
 constexpr int kJobs = 5;  // pct, subj(norm), quantile(d0), subj(d0), subj(shaped)
 constexpr size_t kJobWords = 4096 + 4 * 4096 + 4 * 64 + 64 + 64;  // + count (padded)
 
@@ -57,11 +58,11 @@ struct vd3d_ctx {
   int xs_n = 0, ys_n = 0;
   // planes
   Buf tdf, dn0, dn1, rgb_s, frameB, d, shift, e2, eyeL, eyeR, eyeL2, eyeR2;
-  Buf in_frame[2], in_depth[2], out_dev[2], in_rgbf, in_depthf;
+  Buf in_frame[kSlots], in_depth[kSlots], out_dev[kSlots], in_rgbf, in_depthf;
   Buf dof_kern;
   int tdf_w = 0, tdf_h = 0;
   int frame_parity = 0;
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[kSlots] = {}, ev_done[kSlots] = {}, ev_d2h[kSlots] = {};
   // optional per-stage device timing (bench.py roofline): event pairs on ctx->stream
   int prof = 0;
   std::vector<cudaEvent_t> prof_ev[4];  // stage -> [start, stop, start, stop, ...]
@@ -70,20 +71,20 @@ struct vd3d_ctx {
   struct FrameGraph {
     cudaGraphExec_t exec = nullptr;
     uint64_t n_ctx = 0, n_depth = 0;
-  } fg[2][2];
+  } fg[kSlots][2];
   vd3d_render_params fg_rp;
   int fg_h = 0, fg_w = 0, fg_dch = 0, fg_warm = 0;
   void* fg_depth = nullptr;
   // depth stage of the depth+stereo clip: two engine clones (shared weights) on two streams so the
   // depth forwards of consecutive frames overlap each other and the DIBR kernels of the previous frame
-  vd3d_depth* dclone[2] = {nullptr, nullptr};
+  vd3d_depth* dclone[kSlots] = {};
   vd3d_depth* dclone_parent = nullptr;
-  cudaStream_t s_depth[2] = {nullptr, nullptr};
-  cudaEvent_t ev_depth[2] = {nullptr, nullptr};
+  cudaStream_t s_depth[kSlots] = {};
+  cudaEvent_t ev_depth[kSlots] = {};
   struct DepthGraph {
     cudaGraphExec_t exec = nullptr;
     uint64_t n = 0;
-  } dg[2];
+  } dg[kSlots];
   int dg_warm = 0, dg_h = 0, dg_w = 0;
   // dof kernel cache
   double dof_sigma_cached = -1.0;
@@ -484,7 +485,7 @@ int vd3d_create(int device, vd3d_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kSlots; ++i) {
     cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming);
@@ -520,14 +521,17 @@ void vd3d_destroy(vd3d_ctx* ctx) {
   cudaDeviceSynchronize();
   Buf* bufs[] = {&ctx->xs,    &ctx->ys,    &ctx->tdf,   &ctx->dn0,   &ctx->dn1,      &ctx->rgb_s,
                  &ctx->frameB, &ctx->d,     &ctx->shift, &ctx->e2,    &ctx->eyeL,     &ctx->eyeR,
-                 &ctx->eyeL2, &ctx->eyeR2, &ctx->in_frame[0], &ctx->in_frame[1], &ctx->in_depth[0],
-                 &ctx->in_depth[1], &ctx->out_dev[0], &ctx->out_dev[1], &ctx->in_rgbf, &ctx->in_depthf,
-                 &ctx->dof_kern};
+                 &ctx->eyeL2, &ctx->eyeR2, &ctx->in_rgbf, &ctx->in_depthf, &ctx->dof_kern};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
+  for (int i = 0; i < kSlots; ++i) {
+    if (ctx->in_frame[i].p) cudaFree(ctx->in_frame[i].p);
+    if (ctx->in_depth[i].p) cudaFree(ctx->in_depth[i].p);
+    if (ctx->out_dev[i].p) cudaFree(ctx->out_dev[i].p);
+  }
   drop_graphs(ctx);
   drop_depth_graphs(ctx);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kSlots; ++i) {
     if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
     if (ctx->s_depth[i]) cudaStreamDestroy(ctx->s_depth[i]);
     if (ctx->ev_depth[i]) cudaEventDestroy(ctx->ev_depth[i]);
@@ -538,7 +542,7 @@ void vd3d_destroy(vd3d_ctx* ctx) {
   cudaFree(ctx->tgs);
   cudaFreeHost(ctx->fs_pinned);
   cudaFreeHost(ctx->st_pinned);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kSlots; ++i) {
     cudaEventDestroy(ctx->ev_h2d[i]);
     cudaEventDestroy(ctx->ev_done[i]);
     cudaEventDestroy(ctx->ev_d2h[i]);
@@ -965,7 +969,7 @@ extern "C" uint64_t vd3d_depth_launch_count(vd3d_depth* e);
 extern "C" void vd3d_depth_add_launches(vd3d_depth* e, uint64_t n);
 
 static void drop_depth_graphs(vd3d_ctx* ctx) {
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < kSlots; ++i)
     if (ctx->dg[i].exec) {
       cudaGraphExecDestroy(ctx->dg[i].exec);
       ctx->dg[i].exec = nullptr;
@@ -976,7 +980,7 @@ static void drop_depth_graphs(vd3d_ctx* ctx) {
 static int ensure_depth_clones(vd3d_ctx* ctx, vd3d_depth* parent) {
   if (ctx->dclone_parent == parent && ctx->dclone[0]) return VD3D_OK;
   drop_depth_graphs(ctx);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kSlots; ++i) {
     if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
     ctx->dclone[i] = nullptr;
     if (!ctx->s_depth[i]) CK(cudaStreamCreateWithFlags(&ctx->s_depth[i], cudaStreamNonBlocking));
@@ -1005,7 +1009,7 @@ static int run_depth_slot(vd3d_ctx* ctx, vd3d_depth* parent, int b, int src_h, i
     vd3d_depth_add_launches(parent, vd3d_depth_launch_count(e) - l0);
     return r;
   };
-  if (!ctx->use_graphs || ctx->dg_warm < 2) {
+  if (!ctx->use_graphs || ctx->dg_warm < kSlots) {
     ctx->dg_warm++;
     return eager();
   }
@@ -1038,7 +1042,7 @@ static int run_depth_slot(vd3d_ctx* ctx, vd3d_depth* parent, int b, int src_h, i
 }
 
 static void drop_graphs(vd3d_ctx* ctx) {
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < kSlots; ++i)
     for (int j = 0; j < 2; ++j)
       if (ctx->fg[i][j].exec) {
         cudaGraphExecDestroy(ctx->fg[i][j].exec);
@@ -1076,7 +1080,7 @@ static int run_frame_slot(vd3d_ctx* ctx, vd3d_depth* depth, int b, int depth_cha
     ctx->fg_depth = depth;
     ctx->fg_rp = *rp;
   }
-  if (!ctx->use_graphs || ctx->prof || ctx->fg_warm < 2) {
+  if (!ctx->use_graphs || ctx->prof || ctx->fg_warm < kSlots) {
     ctx->fg_warm++;
     return eager();
   }
@@ -1160,26 +1164,26 @@ int vd3d_render_clip(vd3d_ctx* ctx, int n, const uint8_t* const* frames, const u
   if (r) return fail(ctx, r, "unsupported output format / sizes");
   size_t fb = (size_t)src_w * src_h * 3, db = (size_t)src_w * src_h * depth_channels;
   size_t ob = out_bytes(rp, pl);
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < kSlots; ++b) {
     if ((r = ensure(ctx, ctx->in_frame[b], fb))) return r;
     if ((r = ensure(ctx, ctx->in_depth[b], db))) return r;
     if ((r = ensure(ctx, ctx->out_dev[b], ob))) return r;
   }
   for (int i = 0; i < n; ++i) {
-    int b = i & 1;
+    int b = i % kSlots;
     if (mem == VD3D_MEM_DEVICE) {
       // fixed staging addresses keep the frame graph replayable; D2D copies are ~1 % of a frame
-      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+      if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
       CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyDeviceToDevice, ctx->stream));
       CK(cudaMemcpyAsync(ctx->in_depth[b].p, depths[i], db, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
       // software pipeline over three streams: H2D(i+1) | kernels(i) | D2H(i-1)
-      if (i >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
+      if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
       CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb, cudaMemcpyHostToDevice, ctx->s_h2d));
       CK(cudaMemcpyAsync(ctx->in_depth[b].p, depths[i], db, cudaMemcpyHostToDevice, ctx->s_h2d));
       CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
-      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+      if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
     }
     if ((r = run_frame_slot(ctx, nullptr, b, depth_channels, src_h, src_w, rp, pl))) return r;
     if (infos && (r = fetch_info(ctx, &infos[i]))) return r;
@@ -1203,7 +1207,7 @@ int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_
   if (r) return fail(ctx, r, "unsupported output format / sizes");
   size_t fb = (size_t)src_w * src_h * 3, db = (size_t)src_w * src_h;
   size_t ob = out_bytes(rp, pl);
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < kSlots; ++b) {
     if ((r = ensure(ctx, ctx->in_frame[b], fb))) return r;
     if ((r = ensure(ctx, ctx->in_depth[b], db))) return r;
     if ((r = ensure(ctx, ctx->out_dev[b], ob))) return r;
@@ -1211,25 +1215,25 @@ int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_
   const bool serial = ctx->prof != 0;  // stage timing wants one stream; otherwise depth runs on its own streams
   if (!serial && (r = ensure_depth_clones(ctx, depth))) return r;
   for (int i = 0; i < n; ++i) {
-    int b = i & 1;
+    int b = i % kSlots;
     // ---- stage the frame into slot b (free once DIBR of frame i-2 has finished) ----
-    if (i >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
+    if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
     CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb,
                        mem == VD3D_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
     if (serial) {
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
-      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+      if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
       if ((r = run_frame_slot(ctx, depth, b, 1, src_h, src_w, rp, pl))) return r;
     } else {
       // ---- depth of frame i on stream b: overlaps depth(i-1) and DIBR(i-1) ----
       CK(cudaStreamWaitEvent(ctx->s_depth[b], ctx->ev_h2d[b], 0));
-      if (i >= 2) CK(cudaStreamWaitEvent(ctx->s_depth[b], ctx->ev_done[b], 0));  // in_depth[b] consumed
+      if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->s_depth[b], ctx->ev_done[b], 0));  // in_depth[b] consumed
       if ((r = run_depth_slot(ctx, depth, b, src_h, src_w))) return r;
       CK(cudaEventRecord(ctx->ev_depth[b], ctx->s_depth[b]));
       // ---- DIBR loop body on the main stream (sequential temporal state) ----
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_depth[b], 0));
-      if (i >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));        // out_dev[b] drained
+      if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));        // out_dev[b] drained
       if ((r = run_frame_slot(ctx, nullptr, b, 1, src_h, src_w, rp, pl))) return r;
     }
     CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
@@ -1254,7 +1258,7 @@ int vd3d_release_depth(vd3d_ctx* ctx, vd3d_depth* depth) {
     cudaStreamSynchronize(ctx->stream);
     drop_depth_graphs(ctx);
     drop_graphs(ctx);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
       if (ctx->s_depth[i]) cudaStreamSynchronize(ctx->s_depth[i]);
       if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
       ctx->dclone[i] = nullptr;
