@@ -179,6 +179,18 @@ int vd3d_render_clip(vd3d_ctx* ctx, int n, const uint8_t* const* frames, const u
 int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_t* const* frames, int src_h,
                            int src_w, const vd3d_render_params* rp, uint8_t* const* outs, int mem);
 
+/* ---- exact frame sharding --------------------------------------------------
+ * The loop is stateful (7 EMAs / trackers + the temporal depth plane).  A rank that renders frames
+ * [a, b) exactly needs the state after frame a-1: vd3d_advance_state runs one loop iteration
+ * WITHOUT rendering (all state updates, ~1/3 of the DIBR cost), vd3d_export_state /
+ * vd3d_import_state move the state (struct + two f32 planes of target_eye size) between contexts
+ * or GPUs (NCCL send/recv of the blob). */
+int vd3d_advance_state(vd3d_ctx* ctx, const uint8_t* frame_bgr, const uint8_t* depth, int depth_channels,
+                       int src_h, int src_w, const vd3d_render_params* rp, int mem);
+size_t vd3d_state_bytes(vd3d_ctx* ctx);
+int vd3d_export_state(vd3d_ctx* ctx, void* dst, size_t capacity, int mem);
+int vd3d_import_state(vd3d_ctx* ctx, const void* src, size_t bytes, int mem);
+
 /* drop the per-ctx clones / graphs built for `depth`; call before vd3d_depth_destroy(depth) */
 int vd3d_release_depth(vd3d_ctx* ctx, vd3d_depth* depth);
 

@@ -250,3 +250,27 @@ def test_format_3d_output_on_gpu(R):
     assert np.array_equal(R.format_3d_output(l, r, "Half-SBS"), np.hstack((l, r)))
     assert np.array_equal(R.generate_anaglyph_3d(l, r), O.anaglyph(l, r))
     assert np.array_equal(R.format_3d_output(l, r, "Passive Interlaced"), O.format_output(l, r, "Passive Interlaced"))
+
+
+def test_state_handoff_makes_sharding_exact(R):
+    """chunk B rendered on another context after importing the state that a stats-only
+    pass over chunk A produced must equal sequential rendering bit for bit."""
+    from visiondepth3d_b200 import _lib
+    rp, _ = _rp(R, LOOP_CASES["loop_halfsbs_320x180.npz"]["rp"], 320, 180)
+    frames = [synth_frame(i, 320, 180, "smooth") for i in range(9)]
+    main = _lib.default_context(0)
+    main.reset()
+    seq = [R.render_frame(f, d, rp, ctx=main) for f, d in frames]
+    a, b = _lib.Context(0), _lib.Context(0)
+    a.reset()
+    for f, d in frames[:5]:
+        R.advance_state(f, d, rp, ctx=a)        # no rendering on "rank 0" for this check
+    blob = a.export_state()
+    b.import_state(blob)
+    for i in range(5, 9):
+        out = R.render_frame(frames[i][0], frames[i][1], rp, ctx=b)
+        assert np.array_equal(out, seq[i]), i
+    # and the exporter itself can continue rendering from its own state
+    assert np.array_equal(R.render_frame(frames[5][0], frames[5][1], rp, ctx=a), seq[5])
+    a.close()
+    b.close()

@@ -86,6 +86,7 @@ SYMBOLS = [
     "vd3d_depth_create", "vd3d_depth_destroy", "vd3d_depth_last_error", "vd3d_depth_launch_count",
     "vd3d_depth_set_tensor", "vd3d_depth_forward", "vd3d_depth_get_buffer", "vd3d_gemm_f16", "vd3d_conv_f16",
     "vd3d_depth_infer", "vd3d_depth_infer_device", "vd3d_render_clip_depth", "vd3d_depth_add_launches", "vd3d_depth_clone", "vd3d_release_depth",
+    "vd3d_advance_state", "vd3d_state_bytes", "vd3d_export_state", "vd3d_import_state",
 ]
 
 _lib = None
@@ -147,6 +148,14 @@ def load():
     lib.vd3d_render_clip_depth.restype = i
     lib.vd3d_pack.argtypes = [vp, u8p, u8p, i, i, i, u8p, i]
     lib.vd3d_pack.restype = i
+    lib.vd3d_advance_state.argtypes = [vp, u8p, u8p, i, i, i, C.POINTER(RenderParams), i]
+    lib.vd3d_advance_state.restype = i
+    lib.vd3d_state_bytes.argtypes = [vp]
+    lib.vd3d_state_bytes.restype = C.c_size_t
+    lib.vd3d_export_state.argtypes = [vp, vp, C.c_size_t, i]
+    lib.vd3d_export_state.restype = i
+    lib.vd3d_import_state.argtypes = [vp, vp, C.c_size_t, i]
+    lib.vd3d_import_state.restype = i
     lib.vd3d_release_depth.argtypes = [vp, vp]
     lib.vd3d_release_depth.restype = i
     lib.vd3d_sharpen.argtypes = [vp, u8p, i, i, C.c_double, u8p, i]
@@ -180,6 +189,19 @@ class Context:
 
     def reset(self, which=STATE_GLOBAL | STATE_CLIP):
         self.check(self.lib.vd3d_reset_state(self.h, which))
+
+    def export_state(self):
+        """Temporal state after the last frame as a uint8 numpy blob (SURVEY 8(e) exact sharding)."""
+        import numpy as np
+        n = int(self.lib.vd3d_state_bytes(self.h))
+        buf = np.empty(n, dtype=np.uint8)
+        self.check(self.lib.vd3d_export_state(self.h, buf.ctypes.data, n, MEM_HOST))
+        return buf
+
+    def import_state(self, blob):
+        import numpy as np
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        self.check(self.lib.vd3d_import_state(self.h, b.ctypes.data, b.nbytes, MEM_HOST))
 
     def close(self):
         if getattr(self, "h", None):

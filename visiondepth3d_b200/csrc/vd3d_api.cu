@@ -43,6 +43,7 @@ struct vd3d_ctx {
   std::string err;
   uint64_t launches = 0;
   int use_graphs = 1;
+  int stats_only = 0;  // advance temporal state only (exact multi-GPU sharding: SURVEY 8(e))
 
   DevState* st = nullptr;
   FrameScalars* fs = nullptr;
@@ -273,6 +274,11 @@ int run_core(vd3d_ctx* ctx, const CoreIn& in) {
   sa.W = W;
   sa.H = H;
   launch_fin_shape(s1, sa, ctx->st, ctx->fs, s);
+  if (ctx->stats_only) {  // every temporal state update of the frame has happened by now
+    ctx->launches += 1 + 6 + 1 + 1 + 6 + 1;
+    CK(cudaGetLastError());
+    return VD3D_OK;
+  }
   launch_shift(d, shift, H, W, ctx->fs, in.p.enable_edge_masking ? 1 : 0, (float)in.p.feather_strength, s);
   ctx->launches += 1 + 6 + 1 + 1 + 6 + 1 + 1;
   int feather = in.p.enable_feathering ? 1 : 0;
@@ -894,6 +900,10 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
   ci.right = (uint8_t*)ctx->eyeR.p;
   if ((r = run_core(ctx, ci))) return r;
 
+  if (ctx->stats_only) {
+    ctx->frame_parity ^= 1;
+    return VD3D_OK;
+  }
   const uint8_t* eye_l = (const uint8_t*)ctx->eyeL.p;
   const uint8_t* eye_r = (const uint8_t*)ctx->eyeR.p;
   if (dof) {
@@ -1248,6 +1258,97 @@ int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_
     CK(cudaStreamSynchronize(ctx->s_depth[0]));
     CK(cudaStreamSynchronize(ctx->s_depth[1]));
   }
+  return VD3D_OK;
+}
+
+// ---- exact frame sharding: advance / export / import the temporal state ----------
+// One loop iteration without rendering: updates TemporalDepthFilter, DepthPercentileEMA, ShiftSmoother,
+// FocalDepthTracker, ConvergenceEMA, FloatingBarEaser and FloatingWindowTracker exactly as
+// vd3d_render_frame would (same kernels up to the shift map), at ~1/3 of a frame's DIBR cost.
+int vd3d_advance_state(vd3d_ctx* ctx, const uint8_t* frame_bgr, const uint8_t* depth, int depth_channels, int src_h,
+                       int src_w, const vd3d_render_params* rp, int mem) {
+  if (!ctx || !frame_bgr || !depth || !rp) return fail(ctx, VD3D_ERR_ARG, "null argument");
+  if (depth_channels != 1 && depth_channels != 3) return fail(ctx, VD3D_ERR_ARG, "depth_channels must be 1 or 3");
+  CK(cudaSetDevice(ctx->device));
+  vd3d_size_plan pl;
+  int r = vd3d_plan_sizes(src_w, src_h, rp, &pl);
+  if (r) return fail(ctx, r, "unsupported output format / sizes");
+  cudaStream_t s = ctx->stream;
+  const void *f_d, *d_d;
+  size_t fb = (size_t)src_w * src_h * 3, db = (size_t)src_w * src_h * depth_channels;
+  if ((r = copy_in(ctx, ctx->in_frame[0], frame_bgr, fb, mem, s, &f_d))) return r;
+  if ((r = copy_in(ctx, ctx->in_depth[0], depth, db, mem, s, &d_d))) return r;
+  ctx->stats_only = 1;
+  r = enqueue_frame(ctx, (const uint8_t*)f_d, (const uint8_t*)d_d, depth_channels, src_h, src_w, rp, pl, nullptr);
+  ctx->stats_only = 0;
+  if (r) return r;
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+
+struct StateHeader {
+  uint32_t magic, tw, th, reserved;
+};
+size_t vd3d_state_bytes(vd3d_ctx* ctx) {
+  if (!ctx) return 0;
+  return sizeof(StateHeader) + sizeof(DevState) + 2 * sizeof(float) * (size_t)ctx->tdf_w * ctx->tdf_h;
+}
+// blob = header | DevState | tdf plane | previous normalised-depth plane   (host or device memory)
+int vd3d_export_state(vd3d_ctx* ctx, void* dst, size_t cap, int mem) {
+  if (!ctx || !dst) return VD3D_ERR_ARG;
+  size_t need = vd3d_state_bytes(ctx);
+  if (cap < need) return fail(ctx, VD3D_ERR_ARG, "state buffer too small");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  cudaMemcpyKind kd = mem == VD3D_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  cudaMemcpyKind kh = mem == VD3D_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice;
+  StateHeader h = {0x56443344u, (uint32_t)ctx->tdf_w, (uint32_t)ctx->tdf_h, 0};
+  uint8_t* p = (uint8_t*)dst;
+  CK(cudaMemcpyAsync(p, &h, sizeof h, kh, s));
+  CK(cudaStreamSynchronize(s));  // h is a stack object
+  p += sizeof h;
+  CK(cudaMemcpyAsync(p, ctx->st, sizeof(DevState), kd, s));
+  p += sizeof(DevState);
+  size_t plane = sizeof(float) * (size_t)ctx->tdf_w * ctx->tdf_h;
+  if (plane) {
+    CK(cudaMemcpyAsync(p, ctx->tdf.p, plane, kd, s));
+    p += plane;
+    const void* prev = ctx->frame_parity ? ctx->dn0.p : ctx->dn1.p;  // what the next frame reads as prev_depth
+    CK(cudaMemcpyAsync(p, prev, plane, kd, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+int vd3d_import_state(vd3d_ctx* ctx, const void* src, size_t bytes, int mem) {
+  if (!ctx || !src || bytes < sizeof(StateHeader) + sizeof(DevState)) return fail(ctx, VD3D_ERR_ARG, "bad state blob");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  cudaMemcpyKind kd = mem == VD3D_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  cudaMemcpyKind kh = mem == VD3D_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost;
+  StateHeader h;
+  CK(cudaMemcpyAsync(&h, src, sizeof h, kh, s));
+  CK(cudaStreamSynchronize(s));
+  if (h.magic != 0x56443344u) return fail(ctx, VD3D_ERR_ARG, "bad state blob magic");
+  size_t plane = sizeof(float) * (size_t)h.tw * h.th;
+  if (bytes < sizeof h + sizeof(DevState) + 2 * plane) return fail(ctx, VD3D_ERR_ARG, "state blob truncated");
+  int r;
+  if (plane) {
+    if ((r = ensure(ctx, ctx->tdf, plane)) || (r = ensure(ctx, ctx->dn0, plane)) || (r = ensure(ctx, ctx->dn1, plane)))
+      return r;
+  }
+  ctx->tdf_w = (int)h.tw;
+  ctx->tdf_h = (int)h.th;
+  const uint8_t* p = (const uint8_t*)src + sizeof h;
+  CK(cudaMemcpyAsync(ctx->st, p, sizeof(DevState), kd, s));
+  p += sizeof(DevState);
+  if (plane) {
+    CK(cudaMemcpyAsync(ctx->tdf.p, p, plane, kd, s));
+    p += plane;
+    ctx->frame_parity = 0;  // next frame writes dn0 and reads dn1 as prev_depth
+    CK(cudaMemcpyAsync(ctx->dn1.p, p, plane, kd, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  drop_graphs(ctx);
   return VD3D_OK;
 }
 

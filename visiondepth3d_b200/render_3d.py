@@ -271,6 +271,17 @@ def render_frame(frame_bgr, depth_bgr, rp, want_info=False, ctx=None):
     return (out, info) if want_info else out
 
 
+def advance_state(frame_bgr, depth_bgr, rp, ctx=None):
+    """One loop iteration without rendering (temporal state only): the building block of exact
+    multi-GPU frame sharding (visiondepth3d_b200/sharding.py)."""
+    ctx = ctx or _ctx()
+    f = np.ascontiguousarray(frame_bgr, dtype=np.uint8)
+    d = np.ascontiguousarray(depth_bgr, dtype=np.uint8)
+    dch = 1 if d.ndim == 2 else d.shape[2]
+    ctx.check(ctx.lib.vd3d_advance_state(ctx.h, f.ctypes.data, d.ctypes.data, dch, f.shape[0], f.shape[1],
+                                         C.byref(rp), _lib.MEM_HOST))
+
+
 def render_sbs_3d(
     input_path, depth_path, output_path, selected_codec, fps, output_width, output_height,
     fg_shift, mg_shift, bg_shift, sharpness_factor, output_format, selected_aspect_ratio,

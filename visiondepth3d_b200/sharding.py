@@ -28,3 +28,40 @@ def broadcast_state_dict(sd, src=0, device=None):
         sd[k] = flat[off:off + n].reshape(sd[k].shape).to(sd[k].dtype)
         off += n
     return sd
+
+
+def render_chunk_exact(ctx, frames, depths, rp, render_frame, advance_state, rank=None, world=None):
+    """Exact frame-sharded rendering of one clip.
+
+    Every rank holds the whole list of (frame, depth) pairs or at least its own chunk.  Rank r
+    (1) receives the temporal state after frame start-1 from rank r-1, (2) advances it over its own
+    chunk without rendering and forwards it to rank r+1 -- this short scalar/plane chain is the only
+    sequential part -- then (3) re-imports its start state and renders its chunk.  The result is
+    bit-identical to one GPU rendering the clip sequentially.
+    Returns (start, stop, [rendered frames of the chunk])."""
+    import numpy as np
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    start, stop = chunk_range(len(frames), rank, world)
+    if rank > 0:
+        n = torch.zeros(1, dtype=torch.int64)
+        dist.recv(n, src=rank - 1)
+        blob = torch.empty(int(n.item()), dtype=torch.uint8)
+        dist.recv(blob, src=rank - 1)
+        start_state = blob.numpy().copy()
+        ctx.import_state(start_state)
+    else:
+        ctx.reset()
+        start_state = None
+    if rank + 1 < world:
+        for i in range(start, stop):
+            advance_state(frames[i], depths[i], rp, ctx=ctx)
+        end_state = torch.from_numpy(np.ascontiguousarray(ctx.export_state()))
+        dist.send(torch.tensor([end_state.numel()], dtype=torch.int64), dst=rank + 1)
+        dist.send(end_state, dst=rank + 1)
+        if start_state is not None:
+            ctx.import_state(start_state)
+        else:
+            ctx.reset()
+    outs = [render_frame(frames[i], depths[i], rp, ctx=ctx) for i in range(start, stop)]
+    return start, stop, outs
