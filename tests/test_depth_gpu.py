@@ -63,7 +63,7 @@ def _depth_u8(d):
     return ((d - d.min()) / (d.max() - d.min() + np.float32(1e-6)) * 255).astype(np.uint8)
 
 
-@pytest.mark.parametrize("name,h,w", [("vits", 70, 98), ("vits", 518, 924), ("vitb", 518, 924)])
+@pytest.mark.parametrize("name,h,w", [("vits", 70, 98), ("vits", 518, 924), ("vitb", 518, 924), ("vitl", 518, 924)])
 def test_forward_matches_oracle(name, h, w):
     import torch
     from oracle import depth as OD
