@@ -197,6 +197,10 @@ int vd3d_release_depth(vd3d_ctx* ctx, vd3d_depth* depth);
 /* stage entry points (same kernels, exposed for stage-isolated parity tests) */
 /* apply_sharpening (717-732) on u8 BGR [h,w,3] */
 int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem);
+/* heal_missing_pixels (431-459; the reference's "gradient-blend occlusion fill", defined but not called by
+ * its render loop): f32 RGB planes [3,h,w] warped + original, optional edge mask [h,w] -> f32 [3,h,w] */
+int vd3d_heal(vd3d_ctx* ctx, const float* warped, const float* original, const float* edge_mask_or_null, int h, int w,
+              double heal_strength, float* out, int mem);
 /* format_3d_output / generate_anaglyph_3d (837-883) on two same-size u8 BGR eyes [h,w,3]:
  * SBS -> [h,2w,3]; anaglyph / interlaced -> [h,w,3] */
 int vd3d_pack(vd3d_ctx* ctx, const uint8_t* left, const uint8_t* right, int h, int w, int fmt, uint8_t* dst, int mem);

@@ -489,6 +489,24 @@ def pixel_shift(gs: GlobalState, frame_t: np.ndarray, depth_t: np.ndarray,
     return left, right, final
 
 
+def heal_missing_pixels(warped: np.ndarray, original: np.ndarray, edge_mask=None, heal_strength=0.5) -> np.ndarray:
+    """heal_missing_pixels (core/render_3d.py:431-459; defined but never called by the reference --
+    the "gradient-blend occlusion fill" of its method notes).  [3,H,W] float32 in, out."""
+    gray = ((warped[0] + warped[1]).astype(f32) + warped[2]).astype(f32)
+    gray = (gray / f32(3)).astype(f32)[None]
+    g = _grad_mag(gray, absval=False)
+    miss = (g > f32(0.05)).astype(f32)
+    miss = np.clip(avg_pool_same(miss, 5), f32(0), f32(1)).astype(f32)
+    if edge_mask is not None:
+        miss = np.maximum(miss, edge_mask.astype(f32))
+    hm = (f32(heal_strength) * miss).astype(f32)
+    healed = (((f32(1) - hm).astype(f32) * warped).astype(f32) + (hm * original).astype(f32)).astype(f32)
+    soft = avg_pool_same(healed, 3)
+    sm = (f32(0.3) * miss).astype(f32)
+    out = (((f32(1) - sm).astype(f32) * healed).astype(f32) + (sm * soft).astype(f32)).astype(f32)
+    return np.clip(out, f32(0), f32(1)).astype(f32)
+
+
 # --------------------------------------------------------------------------
 # post chain (core/render_3d.py:717-892)
 # --------------------------------------------------------------------------

@@ -274,3 +274,15 @@ def test_state_handoff_makes_sharding_exact(R):
     assert np.array_equal(R.render_frame(frames[5][0], frames[5][1], rp, ctx=a), seq[5])
     a.close()
     b.close()
+
+
+def test_heal_missing_pixels(R, golden_dir):
+    g = np.load(os.path.join(golden_dir, "heal_160x90.npz"))
+    for key, em in (("heal_none", None), ("heal_edge", g["edge"])):
+        out = R.heal_missing_pixels(g["warped"], None, g["orig"], em, 0.5)
+        assert np.abs(out - g[key]).max() <= 1e-6  # vs the reference function's own output
+        assert np.array_equal(out, O.heal_missing_pixels(g["warped"], g["orig"], em, 0.5))
+    rng = np.random.default_rng(4)
+    w = rng.random((3, 37, 53), dtype=np.float32)
+    o = rng.random((3, 37, 53), dtype=np.float32)
+    assert np.array_equal(R.heal_missing_pixels(w, None, o, None, 0.8), O.heal_missing_pixels(w, o, None, 0.8))

@@ -166,6 +166,20 @@ def main():
     rp = dict(rp, output_format="Passive Interlaced")
     g = run_loop(r3d, torch, cv2, 256, 144, 3, "smooth", rp)
     np.savez_compressed(os.path.join(OUT, "loop_interlaced_256x144.npz"), **g, **meta)
+    # G. heal_missing_pixels (dead code in the reference's loop, named by north_star): standalone op
+    rng = np.random.default_rng(21)
+    H, W = 90, 160
+    yy, xx = np.mgrid[0:H, 0:W]
+    warped = np.stack([(xx / W), (yy / H), ((xx + yy) % 32) / 32.0]).astype(np.float32)
+    warped[:, 30:60, 50:90] = rng.random((3, 30, 40), dtype=np.float32)
+    orig = np.clip(warped + 0.1 * rng.standard_normal(warped.shape).astype(np.float32), 0, 1).astype(np.float32)
+    edge = (rng.random((1, H, W), dtype=np.float32) > 0.9).astype(np.float32)
+    outs = {}
+    for name, em in (("none", None), ("edge", edge)):
+        outs["heal_" + name] = r3d.heal_missing_pixels(
+            torch.from_numpy(warped), None, torch.from_numpy(orig),
+            torch.from_numpy(em) if em is not None else None, 0.5).numpy()
+    np.savez_compressed(os.path.join(OUT, "heal_160x90.npz"), warped=warped, orig=orig, edge=edge, **outs)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1185,8 +1185,91 @@ __global__ void __launch_bounds__(256) k_post(PostArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// heal_missing_pixels (core/render_3d.py:431-459): gradient-gated blend of the warped eye toward the
+// original frame + 3x3 softening.  f32 RGB planes in/out.  One pass: gray (halo 4) -> gradient flags
+// (halo 3) -> 5x5 pooled mask (halo 1) -> healed (halo 1) -> 3x3 blur -> out.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_heal(const float* __restrict__ warped, const float* __restrict__ orig,
+                                              const float* __restrict__ edge, float* __restrict__ out, int H, int W,
+                                              float hs) {
+  __shared__ float gray[16][41];    // y in [by-4, by+12), x in [bx-4, bx+36)   (+1 pad)
+  __shared__ float flag[14][39];    // grad > 0.05 over [by-3, by+11) x [bx-3, bx+35)
+  __shared__ float mm[10][35];      // pooled mask over [by-1, by+9) x [bx-1, bx+33)
+  __shared__ float heal[3][10][35];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 8;
+  const size_t plane = (size_t)H * W;
+  for (int i = threadIdx.x; i < 16 * 40; i += 256) {
+    int ty = i / 40, tx = i % 40, gy = by - 4 + ty, gx = bx - 4 + tx;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      size_t o = (size_t)gy * W + gx;
+      v = ((warped[o] + warped[plane + o]) + warped[2 * plane + o]) / 3.0f;
+    }
+    gray[ty][tx] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 14 * 38; i += 256) {
+    int ty = i / 38, tx = i % 38, gy = by - 3 + ty, gx = bx - 3 + tx;
+    float f = 0.f;  // zero padding of avg_pool2d outside the image
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      float c = gray[ty + 1][tx + 1];
+      float dx = (gx > 0) ? (c - gray[ty + 1][tx]) : 0.f;
+      float dy = (gy > 0) ? (c - gray[ty][tx + 1]) : 0.f;
+      f = (sqrtf((dx * dx) + (dy * dy)) > 0.05f) ? 1.f : 0.f;
+    }
+    flag[ty][tx] = f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 10 * 34; i += 256) {
+    int ty = i / 34, tx = i % 34, gy = by - 1 + ty, gx = bx - 1 + tx;
+    float m = 0.f;
+    bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    if (in) {
+      float acc = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) acc = acc + flag[ty + dy][tx + dx];
+      m = clamp01(acc / 25.0f);
+      if (edge) m = fmaxf(m, edge[(size_t)gy * W + gx]);
+    }
+    mm[ty][tx] = m;
+    float hm = hs * m;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float hv = 0.f;  // zero padding for the 3x3 pool
+      if (in) {
+        size_t o = c * plane + (size_t)gy * W + gx;
+        hv = ((1.0f - hm) * warped[o]) + (hm * orig[o]);
+      }
+      heal[c][ty][tx] = hv;
+    }
+  }
+  __syncthreads();
+  int lx = threadIdx.x & 31, ly = threadIdx.x >> 5, x = bx + lx, y = by + ly;
+  if (x >= W || y >= H) return;
+  float sm = 0.3f * mm[ly + 1][lx + 1];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) acc = acc + heal[c][ly + dy][lx + dx];
+    float soft = acc / 9.0f;
+    float v = ((1.0f - sm) * heal[c][ly + 1][lx + 1]) + (sm * soft);
+    out[c * plane + (size_t)y * W + x] = clamp01(v);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------
+void launch_heal(const float* warped, const float* orig, const float* edge, float* out, int H, int W, float hs,
+                 cudaStream_t s) {
+  dim3 g((W + 31) / 32, (H + 7) / 8);
+  k_heal<<<g, 256, 0, s>>>(warped, orig, edge, out, H, W, hs);
+}
 static inline dim3 grid2d(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
 
 void launch_ingest(const IngestArgs& a, cudaStream_t s) { k_ingest<<<grid2d(a.tw, a.th), 256, 0, s>>>(a); }

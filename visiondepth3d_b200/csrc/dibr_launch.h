@@ -113,5 +113,7 @@ cudaError_t init_kernel_attributes();
 void launch_compose(const ComposeArgs& a, cudaStream_t s);
 void launch_dof(const DofArgs& a, int eyes, cudaStream_t s);
 void launch_post(const PostArgs& a, cudaStream_t s);
+void launch_heal(const float* warped, const float* orig, const float* edge, float* out, int H, int W, float hs,
+                 cudaStream_t s);
 
 }  // namespace vd3d

@@ -1410,6 +1410,31 @@ int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor,
   return VD3D_OK;
 }
 
+// heal_missing_pixels (core/render_3d.py:431-459) on f32 RGB planes [3,h,w]; edge_mask [h,w] or null
+int vd3d_heal(vd3d_ctx* ctx, const float* warped, const float* original, const float* edge_mask, int h, int w,
+              double heal_strength, float* out, int mem) {
+  if (!ctx || !warped || !original || !out || h < 1 || w < 1) return fail(ctx, VD3D_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t bytes = sizeof(float) * 3 * (size_t)h * w;
+  const void *w_d, *o_d, *e_d = nullptr;
+  int r;
+  if ((r = copy_in(ctx, ctx->in_rgbf, warped, bytes, mem, s, &w_d))) return r;
+  if ((r = copy_in(ctx, ctx->frameB, original, bytes, mem, s, &o_d))) return r;
+  if (edge_mask && (r = copy_in(ctx, ctx->in_depthf, edge_mask, bytes / 3, mem, s, &e_d))) return r;
+  float* out_d = out;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->rgb_s, bytes))) return r;
+    out_d = (float*)ctx->rgb_s.p;
+  }
+  launch_heal((const float*)w_d, (const float*)o_d, (const float*)e_d, out_d, h, w, (float)heal_strength, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(out, out_d, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+
 // format_3d_output / generate_anaglyph_3d (core/render_3d.py:837-883) on two same-size u8 BGR eyes
 int vd3d_pack(vd3d_ctx* ctx, const uint8_t* left, const uint8_t* right, int h, int w, int fmt, uint8_t* dst, int mem) {
   if (!ctx || !left || !right || !dst || h < 1 || w < 1) return fail(ctx, VD3D_ERR_ARG, "bad argument");

@@ -174,6 +174,25 @@ def dof_grade_frame(frame_bgr, depth01, focal_depth, max_sigma=2.0, saturation=1
     return out
 
 
+def heal_missing_pixels(warped_frame, warped_depth, original_frame, edge_mask, heal_strength=0.5):
+    """core/render_3d.py:431-459 (`warped_depth` is unused there too).  f32 [3,H,W] tensors / arrays in,
+    same type out."""
+    ctx = _ctx()
+    is_t = torch is not None and isinstance(warped_frame, torch.Tensor)
+    wf = np.ascontiguousarray((warped_frame.detach().cpu().numpy() if is_t else warped_frame), dtype=np.float32)
+    of = original_frame.detach().cpu().numpy() if (torch is not None and isinstance(original_frame, torch.Tensor)) \
+        else original_frame
+    of = np.ascontiguousarray(of, dtype=np.float32)
+    em = None
+    if edge_mask is not None:
+        em = edge_mask.detach().cpu().numpy() if (torch is not None and isinstance(edge_mask, torch.Tensor)) else edge_mask
+        em = np.ascontiguousarray(np.asarray(em, dtype=np.float32).reshape(wf.shape[1:]))
+    out = np.empty_like(wf)
+    ctx.check(ctx.lib.vd3d_heal(ctx.h, wf.ctypes.data, of.ctypes.data, em.ctypes.data if em is not None else None,
+                                wf.shape[1], wf.shape[2], float(heal_strength), out.ctypes.data, _lib.MEM_HOST))
+    return torch.from_numpy(out).to(warped_frame.device) if is_t else out
+
+
 def pad_to_aspect_ratio(image, target_width, target_height, bg_color=(0, 0, 0)):
     """core/render_3d.py:101-131 (host helper kept for callers; the frame path fuses it)."""
     import cv2
