@@ -44,6 +44,8 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_compose launch (profiles/r01_ncu_full_summary.md)
 NCU_COMPOSE_TRAFFIC = {"4k": 156386048, "1080p": None}
+# same for one fc1 launch of k_umma_gemm<128,3> (DA-V2-Base: M=2443, N=3072, K=768): 8.56 MB read + 0.01 MB written
+NCU_GEMM_FC1_TRAFFIC = {"vitb": 8571136, "vitl": None, "vits": None}
 COMMON = dict(fg=4.5, mg=-1.5, bg=-6.0, sharp=0.2, feather=10.0, ksize=9, tracking=True, floating=True,
               zps=0.01, dof=0.0)
 
@@ -54,6 +56,13 @@ def peaks():
         d = json.load(open(p))
         return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
     return 6650.0, 1400.0, "fallback"
+
+
+def peaks_burst():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("bf16_tflops", 1590.0)
+    return 1590.0
 
 
 class ClockSampler:
@@ -334,15 +343,20 @@ def main():
 
     # ================= per-stage device timing (CUDA events around the stages; eager launches) ======
     lib.vd3d_profile(ctx.h, 1)
+    lib.vd3d_depth_profile(deng.h, 1)
     tot0, n0, tot1, n1, tot2, n2 = C.c_double(), C.c_int(), C.c_double(), C.c_int(), C.c_double(), C.c_int()
+    g_ms, g_n, g_gf = C.c_double(), C.c_int(), C.c_double()
     step(_lib.MEM_DEVICE)  # un-timed: first eager pass through the serial path allocates its workspaces
     for st in (0, 1, 2):
         lib.vd3d_profile_collect(ctx.h, st, C.byref(tot0), C.byref(n0))
+    lib.vd3d_depth_profile_collect(deng.h, C.byref(g_ms), C.byref(g_n), C.byref(g_gf))
     for _ in range(max(2, min(args.steps, 4))):
         step(_lib.MEM_DEVICE)
     lib.vd3d_profile_collect(ctx.h, 0, C.byref(tot0), C.byref(n0))
     lib.vd3d_profile_collect(ctx.h, 1, C.byref(tot1), C.byref(n1))
     lib.vd3d_profile_collect(ctx.h, 2, C.byref(tot2), C.byref(n2))
+    lib.vd3d_depth_profile_collect(deng.h, C.byref(g_ms), C.byref(g_n), C.byref(g_gf))
+    lib.vd3d_depth_profile(deng.h, 0)
     lib.vd3d_profile(ctx.h, 0)
 
     if rank == 0:
@@ -355,6 +369,9 @@ def main():
         stage_gbs = wl["dibr_bytes"] / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else 0.0
         depth_ms = tot2.value / max(n2.value, 1)
         depth_tf = DEPTH_GFLOP[wl["model"]] / max(depth_ms, 1e-9)
+        gemm_ms = g_ms.value / max(g_n.value, 1)
+        gemm_tf = g_gf.value / max(gemm_ms, 1e-9)
+        tf_burst = peaks_burst()
         line = {
             "metric": "end-to-end frames/sec (depth+stereo)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -372,15 +389,21 @@ def main():
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            # dominant share of the step: the depth stage (tcgen05 GEMMs + fused attention), tensor bound
-            "roofline": {"bound": "tensor", "kernel": "depth stage: k_umma_gemm<*> + k_umma_attention (+ small fused kernels)",
-                         "achieved": depth_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": depth_tf / tf_peak,
-                         "traffic": None, "peak_source": which + " (cuBLAS bf16 sustained)",
-                         "algorithmic_gflop_per_frame": DEPTH_GFLOP[wl["model"]], "avg_frame_ms": depth_ms,
-                         "note": "achieved = GFLOP / serial stage time (CUDA events, eager pass); with three frames in "
-                                 "flight the timed region sustains achieved_in_timed_region per GPU",
-                         "achieved_in_timed_region": DEPTH_GFLOP[wl["model"]] * (value / world) / 1000.0,
-                         "share_of_step": depth_ms / max(depth_ms + stage_ms, 1e-9)},
+            # dominant kernel of the step: the persistent tcgen05 GEMM (its fc1 launches are timed live with CUDA
+            # events on the engine stream: M = tokens, N = 4*hidden, K = hidden; same kernel runs every linear/conv)
+            "roofline": {"bound": "tensor", "kernel": "k_umma_gemm<128,3> (fc1 launches)",
+                         "achieved": gemm_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": gemm_tf / tf_burst,
+                         "traffic": NCU_GEMM_FC1_TRAFFIC.get(wl["model"]),
+                         "peak_source": which + " (cuBLAS bf16 burst: kernel timed alone)",
+                         "algorithmic_gflop_per_launch": g_gf.value, "avg_launch_ms": gemm_ms, "launches_timed": g_n.value},
+            # the whole depth stage (GEMMs + fused attention + small kernels), serial eager pass
+            "roofline_depth_stage": {"bound": "tensor", "achieved": depth_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                                     "frac": depth_tf / tf_peak, "peak_source": which + " (cuBLAS bf16 sustained)",
+                                     "algorithmic_gflop_per_frame": DEPTH_GFLOP[wl["model"]], "avg_frame_ms": depth_ms,
+                                     "share_of_step": depth_ms / max(depth_ms + stage_ms, 1e-9),
+                                     "achieved_in_timed_region": DEPTH_GFLOP[wl["model"]] * (value / world) / 1000.0,
+                                     "note": "with three frames in flight the timed region sustains "
+                                             "achieved_in_timed_region per GPU"},
             "roofline_dibr_compose": {"bound": "hbm", "kernel": "k_compose4", "achieved": comp_gbs, "peak": hbm_peak,
                                       "unit": "GB/s", "frac": comp_gbs / hbm_peak,
                                       "traffic": NCU_COMPOSE_TRAFFIC.get(args.workload), "peak_source": which,

@@ -56,6 +56,9 @@ struct vd3d_depth {
   bool planned = false;
   bool flash = true;  // fused attention kernel (VD3D_FLASH=0 selects the 3-kernel path)
   bool owns_weights = true;  // clones share the weight tensors of their parent
+  // optional device timing of one GEMM class (the fc1 launches) for the roofline report
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;
 };
 
 namespace {
@@ -224,6 +227,32 @@ int vd3d_depth_create(const vd3d_depth_config* cfg, void* stream, vd3d_depth** o
     return VD3D_ERR_UNSUPPORTED;
   }
   *out = e;
+  return VD3D_OK;
+}
+
+// device timing of the fc1 GEMM launches (k_umma_gemm<128,3>, M=tokens, N=4D, K=D): bench.py roofline
+int vd3d_depth_profile(vd3d_depth* e, int enable) {
+  if (!e) return VD3D_ERR_ARG;
+  e->prof = enable != 0;
+  return VD3D_OK;
+}
+int vd3d_depth_profile_collect(vd3d_depth* e, double* total_ms, int* count, double* gflop_per_launch) {
+  if (!e || !total_ms || !count) return VD3D_ERR_ARG;
+  DCK(cudaStreamSynchronize(e->stream));
+  double t = 0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < e->prof_ev.size(); i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->prof_ev[i], e->prof_ev[i + 1]) == cudaSuccess) {
+      t += ms;
+      ++n;
+    }
+  }
+  for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
+  e->prof_ev.clear();
+  *total_ms = t;
+  *count = n;
+  if (gflop_per_launch) *gflop_per_launch = 2.0 * e->ntok * (4.0 * e->cfg.hidden) * e->cfg.hidden / 1e9;
   return VD3D_OK;
 }
 
@@ -456,7 +485,18 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
       g.bias = bf1;
       g.act = 1;
       g.ldc = 4 * D;
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (e->prof) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, s);
+      }
       if ((r = gemm(e, (const __half*)xn, D, wf1, D, g))) return r;
+      if (e->prof) {
+        cudaEventRecord(e1, s);
+        e->prof_ev.push_back(e0);
+        e->prof_ev.push_back(e1);
+      }
     }
     {
       GemmArgs g = base_args(NT, D, 4 * D, EPI_RESID_LS);

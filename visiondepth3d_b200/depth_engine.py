@@ -38,6 +38,10 @@ def _bind(lib):
     lib.vd3d_depth_infer.restype = i
     lib.vd3d_depth_infer_device.argtypes = [vp, vp, i, i, vp, vp, i]
     lib.vd3d_depth_infer_device.restype = i
+    lib.vd3d_depth_profile.argtypes = [vp, i]
+    lib.vd3d_depth_profile.restype = i
+    lib.vd3d_depth_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i), C.POINTER(C.c_double)]
+    lib.vd3d_depth_profile_collect.restype = i
     lib._depth_bound = True
 
 
