@@ -197,7 +197,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 
 }  // namespace umma
 
-constexpr int kGemmThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int kGemmThreads = 320;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (2 per lane quarter)
 constexpr int kBK = 64;            // 64 f16 = 128 B = one swizzle row
 
 template <int BN, int STAGES>
@@ -237,7 +237,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       umma::mbar_init(umma::smem_u32(&tmem_full[i]), 1);
-      umma::mbar_init(umma::smem_u32(&tmem_empty[i]), 4);
+      umma::mbar_init(umma::smem_u32(&tmem_empty[i]), 8);
     }
     umma::fence_barrier_init();
   }
@@ -321,8 +321,13 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter, each taking half of the tile's 32-column chunks.  Every register
+    // array below is indexed with compile-time constants only (fully unrolled, predicated) so the 32
+    // accumulator values of a chunk stay in registers.
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the chunks
+    constexpr int kChunks = BN / 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
     int n_blk, m_blk, z, px0, py0;
@@ -345,35 +350,39 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     float head_acc = 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int ci = half; ci < kChunks; ci += 2) {
+      const int c0 = ci * 32;
       uint32_t v[32];
       umma::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       const int n0 = n_blk * BN + c0;
       if (!row_ok || n0 >= g.N) continue;
-      float a[32];
       const int nvalid = min(32, g.N - n0);
-      if (g.bias && nvalid == 32) {
+      const bool full = (nvalid == 32);
+      float a[32];
+      if (g.bias) {
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 b4 = *(const float4*)(g.bias + n0 + 4 * j);
-          a[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-          a[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-          a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-          a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          for (int j = 0; j < 8; ++j) {
+            float4 b4 = __ldg((const float4*)(g.bias + n0) + j);
+            a[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+            a[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+            a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]) + ((j < nvalid) ? g.bias[n0 + j] : 0.f);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(v[j]);
-          if (g.bias && j < nvalid) t += g.bias[n0 + j];
-          a[j] = t;
-        }
+        for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
       }
       switch (g.epi) {
         case EPI_F16: {
-          size_t o = (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
+          const size_t o = (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
+          const bool vec = full && ((o & 7) == 0);
           if (g.res_f16) {
-            if (nvalid == 32 && ((o & 7) == 0)) {
+            if (vec) {
               uint4 rv[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) rv[j] = __ldg((const uint4*)(g.res_f16 + o) + j);
@@ -393,12 +402,14 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (j < nvalid) a[j] += __half2float(g.res_f16[o + j]);
             }
           }
+          if (g.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (g.act == 1) a[j] = umma::gelu_erf(a[j]);
-            if (g.act == 2) a[j] = fmaxf(a[j], 0.f);
+            for (int j = 0; j < 32; ++j) a[j] = umma::gelu_erf(a[j]);
+          } else if (g.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.f);
           }
-          if (nvalid == 32 && ((o & 7) == 0)) {
+          if (vec) {
             uint4* dst = (uint4*)(g.out_f16 + o);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -430,26 +441,30 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           } else {
-            for (int j = 0; j < nvalid; ++j) {
-              g.out_f16[o + j] = __float2half_rn(a[j]);
-              if (g.out2_f16) g.out2_f16[o + j] = __float2half_rn(fmaxf(a[j], 0.f));
-            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) {
+                g.out_f16[o + j] = __float2half_rn(a[j]);
+                if (g.out2_f16) g.out2_f16[o + j] = __float2half_rn(fmaxf(a[j], 0.f));
+              }
           }
         } break;
         case EPI_F32: {
           float* dst = g.out_f32 + (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
-          if (nvalid == 32 && ((((size_t)m * g.ldc + n0) & 3) == 0) && ((g.out_batch_stride & 3) == 0)) {
+          if (full && ((((size_t)m * g.ldc + n0) & 3) == 0) && ((g.out_batch_stride & 3) == 0)) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
           } else {
-            for (int j = 0; j < nvalid; ++j) dst[j] = a[j];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) dst[j] = a[j];
           }
         } break;
         case EPI_RESID_LS: {
           // read-modify-write of the fp32 residual stream: issue all loads before the first store
           // (a load/store-per-element loop serialises on possible aliasing: ~800 cycles per element)
           float* dst = g.out_f32 + (size_t)m * g.ldc + n0;
-          if (nvalid == 32 && ((((size_t)m * g.ldc + n0) & 3) == 0)) {
+          if (full && ((((size_t)m * g.ldc + n0) & 3) == 0)) {
             float4 x4[8], l4[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -467,8 +482,11 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = x4[j];
           } else {
             float xv[32];
-            for (int j = 0; j < nvalid; ++j) xv[j] = dst[j];
-            for (int j = 0; j < nvalid; ++j) dst[j] = xv[j] + g.ls[n0 + j] * a[j];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xv[j] = (j < nvalid) ? dst[j] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) dst[j] = xv[j] + g.ls[n0 + j] * a[j];
           }
         } break;
         case EPI_QKV: {
@@ -514,7 +532,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int dy = tap / g.ct_k, dx = tap % g.ct_k;
           const int y = m / g.ct_w, x = m % g.ct_w;
           size_t o = ((size_t)(y * g.ct_k + dy) * (g.ct_w * g.ct_k) + (x * g.ct_k + dx)) * g.ct_cout + co;
-          if (nvalid == 32 && ((o & 7) == 0)) {
+          if (full && ((o & 7) == 0)) {
             uint4* dst = (uint4*)(g.out_f16 + o);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -530,15 +548,20 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               dst[j] = u;
             }
           } else {
-            for (int j = 0; j < nvalid; ++j) g.out_f16[o + j] = __float2half_rn(a[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) g.out_f16[o + j] = __float2half_rn(a[j]);
           }
         } break;
         case EPI_HEAD: {
-          for (int j = 0; j < nvalid; ++j) head_acc += fmaxf(a[j], 0.f) * g.w3[n0 + j];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) head_acc += fmaxf(a[j], 0.f) * __ldg(g.w3 + n0 + j);
         } break;
       }
     }
-    if (g.epi == EPI_HEAD && row_ok && n_blk == 0) g.out_f32[m] = fmaxf(head_acc + g.b3p[0], 0.f);
+    // DPT head: N == 32 is a single chunk, owned by the half-0 warps
+    if (g.epi == EPI_HEAD && half == 0 && row_ok && n_blk == 0) g.out_f32[m] = fmaxf(head_acc + g.b3p[0], 0.f);
     // this accumulator stage may be overwritten by the MMA warp
     umma::tc_fence_before();
     __syncwarp();
