@@ -212,6 +212,9 @@ class Context:
             self.h = None
 
     def __del__(self):
+        import sys
+        if sys is None or sys.is_finalizing():  # the CUDA runtime may already be torn down at interpreter exit
+            return
         try:
             self.close()
         except Exception:

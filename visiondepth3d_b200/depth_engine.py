@@ -137,6 +137,9 @@ class DepthEngine:
             self.h = None
 
     def __del__(self):
+        import sys
+        if sys is None or sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:

@@ -73,6 +73,10 @@ def hf_batch_safe_pipe(images, inference_size=None):
             from PIL import Image
             img = img.resize(tuple(inference_size), Image.BICUBIC)  # (1819-1821)
         rgb = np.asarray(img.convert("RGB"), dtype=np.uint8)
+        want = _processed_size(rgb.shape[1], rgb.shape[0])
+        if want != (_engine.image_h, _engine.image_w):
+            raise ValueError(f"depth engine was built for processed size {(_engine.image_h, _engine.image_w)}, "
+                             f"this image needs {want}: call load_depth_model(width=, height=) for this aspect")
         d32, _ = _engine.infer(np.ascontiguousarray(rgb[..., ::-1]))
         out.append({"predicted_depth": torch.from_numpy(d32) if torch is not None else d32})
     return out
