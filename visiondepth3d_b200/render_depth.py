@@ -43,6 +43,35 @@ def _processed_size(width, height, target=518, multiple=14):
     return rnd(sh * height), rnd(sw * width)
 
 
+def load_checkpoint(path):
+    """HF-format checkpoint (model.safetensors / pytorch_model.bin of
+    depth-anything/Depth-Anything-V2-{Small,Base,Large}-hf) -> state_dict.  If a config.json sits next
+    to it, the architecture is cross-checked against depth_weights.CONFIGS."""
+    import json
+    import os
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        sd = load_file(path)
+    else:
+        sd = torch.load(path, map_location="cpu")
+    arch = None
+    hidden = sd["backbone.embeddings.cls_token"].shape[-1]
+    for name, c in CONFIGS.items():
+        if c["hidden"] == hidden:
+            arch = name
+    cfg_path = os.path.join(os.path.dirname(path), "config.json")
+    if arch and os.path.exists(cfg_path):
+        cj = json.load(open(cfg_path))
+        c = CONFIGS[arch]
+        got = (cj.get("neck_hidden_sizes"), cj.get("fusion_hidden_size"),
+               cj.get("backbone_config", {}).get("out_indices"))
+        want = (c["neck"], c["fusion"], c["taps"])
+        if any(g is not None and list(g) != list(w) if isinstance(w, list) else (g is not None and g != w)
+               for g, w in zip(got, want)):
+            raise ValueError(f"config.json {got} does not match the built-in {arch} configuration {want}")
+    return arch, sd
+
+
 def load_depth_model(arch="vits", state_dict=None, width=1920, height=1080, seed=0):
     """Build the engine for frames of (width, height).  `state_dict` uses HF
     DepthAnythingForDepthEstimation naming (e.g. from a local safetensors checkpoint);
