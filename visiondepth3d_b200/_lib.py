@@ -2,6 +2,7 @@
 module without the built library, or creating a context without a CUDA device,
 raises."""
 import ctypes as C
+import sys as _sys
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -212,12 +213,11 @@ class Context:
             self.h = None
 
     def __del__(self):
-        import sys
-        if sys is None or sys.is_finalizing():  # the CUDA runtime may already be torn down at interpreter exit
-            return
-        try:
+        try:  # the CUDA runtime may already be torn down at interpreter exit: leave it to the OS then
+            if _sys is None or _sys.is_finalizing():
+                return
             self.close()
-        except Exception:
+        except BaseException:
             pass
 
     @property

@@ -1,5 +1,6 @@
 """ctypes wrapper of the libvd3d depth engine (include/vd3d.h, "depth forward")."""
 import ctypes as C
+import sys as _sys
 
 import numpy as np
 
@@ -137,10 +138,9 @@ class DepthEngine:
             self.h = None
 
     def __del__(self):
-        import sys
-        if sys is None or sys.is_finalizing():
-            return
         try:
+            if _sys is None or _sys.is_finalizing():
+                return
             self.close()
-        except Exception:
+        except BaseException:
             pass
