@@ -3,6 +3,8 @@
 // Reference: transformers 5.5.0 models/dinov2/modeling_dinov2.py and
 // models/depth_anything/modeling_depth_anything.py as called by
 // core/render_depth.py:1106-1119 (hf_batch_safe_pipe).
+#include <stdlib.h>
+
 #include "depth_launch.h"
 #include "umma_gemm.cuh"
 #include "umma_attention.cuh"
@@ -417,9 +419,13 @@ static cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, con
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, int ntok, int dmodel,
                              __half* out, int heads, cudaStream_t s) {
   static bool attr_set = false;
+  static int two_pass = 0;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_umma_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_umma_attention_1p, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return e;
+    if (const char* v = getenv("VD3D_ATTN_2PASS")) two_pass = atoi(v);
     attr_set = true;
   }
   AttnArgs a;
@@ -427,7 +433,10 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
   a.dmodel = dmodel;
   a.out = out;
   dim3 grid((ntok + 127) / 128, heads);
-  k_umma_attention<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a);
+  if (two_pass)
+    k_umma_attention<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a);
+  else
+    k_umma_attention_1p<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a);
   return cudaGetLastError();
 }
 

@@ -31,7 +31,7 @@ constexpr int kAttnThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax 
 // and 240 CTAs (20 query blocks x 12 heads) fit in a single wave of 296 slots.
 constexpr int kAttnKS = 2, kAttnVS = 1, kAttnSB = 1, kAttnPB = 1;
 constexpr int kAttnTmemCols = 256;  // S: kAttnSB x 128, O: 64
-constexpr int kAttnSmem = 16384 /*Q*/ + kAttnKS * 16384 + kAttnVS * 16384 + kAttnPB * 32768 /*P*/ + 1024 + 512 + 2048;
+constexpr int kAttnSmem = 16384 /*Q*/ + kAttnKS * 16384 + kAttnVS * 16384 + kAttnPB * 32768 /*P*/ + 1024 + 512 + 2560;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -258,6 +258,256 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     asm volatile("bar.sync 1, 256;" ::: "memory");
     sum = xch[r] + xch[128 + r];
     // ---- epilogue: O / sum -> out[m, 64h + 32*half .. +31] ----
+    umma::mbar_wait(umma::smem_u32(o_full), 0);
+    umma::tc_fence_after();
+    const int m = qblk * 128 + r;
+    const float inv = 1.0f / sum;
+    {
+      uint32_t v[32];
+      umma::tmem_ld_32x32(tmem_O + lane_off + (uint32_t)(half * 32), v);
+      if (m < g.ntok) {
+        uint4* dst = (uint4*)(g.out + (size_t)m * g.dmodel + h * 64 + half * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          uint4 u;
+          u.x = *(uint32_t*)&h0;
+          u.y = *(uint32_t*)&h1;
+          u.z = *(uint32_t*)&h2;
+          u.w = *(uint32_t*)&h3;
+          dst[i] = u;
+        }
+      }
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) umma::tmem_dealloc(tmem_base, kAttnTmemCols);
+}
+
+// ---------------------------------------------------------------------------
+// Single-pass variant (default): online softmax with LAZY rescaling.  The two-pass kernel above is
+// bound by tensor-memory read bandwidth (every score is read from TMEM twice, ~64 B/clk/SM); here S is
+// computed and read once.  Each row keeps a reference maximum m_ref; probabilities are 2^(s - m_ref) and
+// m_ref is only raised (and O, sum rescaled by 2^(m_ref_old - m_ref_new)) when the running maximum
+// exceeds it by more than 8 (log2 units), so p <= 256 stays comfortably inside f16 and rescales of the
+// TMEM accumulator (tcgen05.ld -> multiply -> tcgen05.st) are rare after the first tiles.
+// Two threads share a query row (64 keys of each tile each); their tile maxima are exchanged through
+// shared memory so both take the same rescale decision.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAttnThreads, 2)
+k_umma_attention_1p(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = sK + kAttnKS * 16384;
+  uint8_t* sP = sV + kAttnVS * 16384;
+  uint64_t* bars = (uint64_t*)(sP + kAttnPB * 32768);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + kAttnKS;
+  uint64_t* v_full = k_empty + kAttnKS;
+  uint64_t* v_empty = v_full + kAttnVS;
+  uint64_t* s_full = v_empty + kAttnVS;
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* o_full = p_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
+  float* xch = (float*)(bars + 64);  // [2 buffers][2 halves][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qblk = blockIdx.x, h = blockIdx.y;
+  const int T = (g.ntok + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmQ);
+    umma::prefetch_tmap(&tmK);
+    umma::prefetch_tmap(&tmV);
+    umma::mbar_init(umma::smem_u32(q_full), 1);
+    for (int i = 0; i < kAttnKS; ++i) {
+      umma::mbar_init(umma::smem_u32(&k_full[i]), 1);
+      umma::mbar_init(umma::smem_u32(&k_empty[i]), 1);
+    }
+    for (int i = 0; i < kAttnVS; ++i) {
+      umma::mbar_init(umma::smem_u32(&v_full[i]), 1);
+      umma::mbar_init(umma::smem_u32(&v_empty[i]), 1);
+    }
+    umma::mbar_init(umma::smem_u32(&s_full[0]), 1);
+    umma::mbar_init(umma::smem_u32(&s_empty[0]), 8);
+    umma::mbar_init(umma::smem_u32(&p_full[0]), 8);
+    umma::mbar_init(umma::smem_u32(&p_empty[0]), 1);
+    umma::mbar_init(umma::smem_u32(o_full), 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 1) umma::tmem_alloc(umma::smem_u32(tmem_slot), kAttnTmemCols);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      umma::mbar_expect_tx(umma::smem_u32(q_full), 16384);
+      umma::tma_load_3d(umma::smem_u32(sQ), &tmQ, umma::smem_u32(q_full), 0, qblk * 128, h);
+      for (int t = 0; t < T; ++t) {
+        const int ks = t % kAttnKS, vs = t % kAttnVS;
+        umma::mbar_wait(umma::smem_u32(&k_empty[ks]), ((t / kAttnKS) & 1) ^ 1);
+        umma::mbar_expect_tx(umma::smem_u32(&k_full[ks]), 16384);
+        umma::tma_load_3d(umma::smem_u32(sK + ks * 16384), &tmK, umma::smem_u32(&k_full[ks]), 0, t * 128, h);
+        umma::mbar_wait(umma::smem_u32(&v_empty[vs]), ((t / kAttnVS) & 1) ^ 1);
+        umma::mbar_expect_tx(umma::smem_u32(&v_full[vs]), 16384);
+        const uint32_t dst = umma::smem_u32(sV + vs * 16384);
+        umma::tma_load_3d(dst, &tmV, umma::smem_u32(&v_full[vs]), t * 128, 0, h);
+        umma::tma_load_3d(dst + 8192, &tmV, umma::smem_u32(&v_full[vs]), t * 128 + 64, 0, h);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma::make_idesc(128);
+      constexpr uint32_t idesc_o = umma::make_idesc(64);
+      umma::mbar_wait(umma::smem_u32(q_full), 0);
+      umma::tc_fence_after();
+      const uint64_t dq = umma::make_desc(umma::smem_u32(sQ));
+      auto issue_S = [&](int t) {
+        const int ks = t % kAttnKS;
+        umma::mbar_wait(umma::smem_u32(&k_full[ks]), (t / kAttnKS) & 1);
+        umma::mbar_wait(umma::smem_u32(&s_empty[0]), (t & 1) ^ 1);
+        umma::tc_fence_after();
+        const uint64_t dk = umma::make_desc(umma::smem_u32(sK + ks * 16384));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma::mma_f16(tmem_S, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+        umma::umma_commit(umma::smem_u32(&k_empty[ks]));
+        umma::umma_commit(umma::smem_u32(&s_full[0]));
+      };
+      issue_S(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) issue_S(t + 1);  // S of the next tile while the softmax warps work on this one
+        const int vs = t % kAttnVS;
+        umma::mbar_wait(umma::smem_u32(&p_full[0]), t & 1);
+        umma::mbar_wait(umma::smem_u32(&v_full[vs]), (t / kAttnVS) & 1);
+        umma::tc_fence_after();
+        const uint32_t pa = umma::smem_u32(sP);
+        const uint32_t va = umma::smem_u32(sV + vs * 16384);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = umma::make_desc(pa + (kk >> 2) * 16384) + (uint64_t)(2 * (kk & 3));
+          const uint64_t db = umma::make_desc(va + (kk >> 2) * 8192) + (uint64_t)(2 * (kk & 3));
+          umma::mma_f16(tmem_O, da, db, idesc_o, (t | kk) ? 1u : 0u);
+        }
+        umma::umma_commit(umma::smem_u32(&v_empty[vs]));
+        umma::umma_commit(umma::smem_u32(&p_empty[0]));
+      }
+      umma::umma_commit(umma::smem_u32(o_full));
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t col_off = (uint32_t)(half * 64);
+    const float L2E = 1.4426950408889634f;
+    float m_ref = -INFINITY;  // reference maximum (log2 units) the probabilities are expressed against
+    float sum = 0.f;
+    for (int t = 0; t < T; ++t) {
+      umma::mbar_wait(umma::smem_u32(&s_full[0]), t & 1);
+      umma::tc_fence_after();
+      const int nvalid = min(128, g.ntok - t * 128) - half * 64;
+      uint32_t v[64];
+      umma::tmem_ld_32x64(tmem_S + lane_off + col_off, v);
+      // S is in registers: the MMA warp may overwrite the buffer with the next tile's scores
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(umma::smem_u32(&s_empty[0]));
+      float mx = -INFINITY;
+      if (nvalid >= 64) {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          m0 = fmaxf(m0, __uint_as_float(v[j]));
+          m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+          m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          if (j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      float* xb = xch + (t & 1) * 256;
+      xb[half * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float m_tile = fmaxf(xb[r], xb[128 + r]) * L2E;  // both threads of the row see the same value
+      // lazy rescale: raise the reference only when it is exceeded by more than 2^8
+      float scale = 1.0f;
+      bool resc = false;
+      if (t == 0) {
+        m_ref = m_tile;
+      } else if (m_tile > m_ref + 8.0f) {
+        scale = umma::ex2_fast(m_ref - m_tile);
+        m_ref = m_tile;
+        resc = true;
+      }
+      // P buffer and the O accumulator are quiescent once the previous PV MMA has retired
+      umma::mbar_wait(umma::smem_u32(&p_empty[0]), (t & 1) ^ 1);
+      umma::tc_fence_after();
+      if (__any_sync(0xffffffffu, resc)) {
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {  // 16 columns at a time: 64 scores are live in registers
+          uint32_t o[16];
+          const uint32_t ta = tmem_O + lane_off + (uint32_t)(half * 32 + cc * 16);
+          umma::tmem_ld_32x16(ta, o);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * scale);
+          umma::tmem_st_32x16(ta, o);
+        }
+        sum *= scale;
+      }
+      uint8_t* pblk = sP + half * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+      uint32_t pk[32];
+      if (nvalid >= 64) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; j += 2) {
+          float p0 = umma::ex2_fast(fmaf(__uint_as_float(v[j]), L2E, -m_ref));
+          float p1 = umma::ex2_fast(fmaf(__uint_as_float(v[j + 1]), L2E, -m_ref));
+          s0 += p0;
+          s1 += p1;
+          __half2 hp = __floats2half2_rn(p0, p1);
+          pk[j >> 1] = *(uint32_t*)&hp;
+        }
+        sum += s0 + s1;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; j += 2) {
+          float p0 = (j < nvalid) ? umma::ex2_fast(fmaf(__uint_as_float(v[j]), L2E, -m_ref)) : 0.f;
+          float p1 = (j + 1 < nvalid) ? umma::ex2_fast(fmaf(__uint_as_float(v[j + 1]), L2E, -m_ref)) : 0.f;
+          sum += p0 + p1;
+          __half2 hp = __floats2half2_rn(p0, p1);
+          pk[j >> 1] = *(uint32_t*)&hp;
+        }
+      }
+#pragma unroll
+      for (int idx = 0; idx < 8; ++idx) {
+        const int phys = idx ^ (r & 7);
+        *(uint4*)(pblk + phys * 16) = make_uint4(pk[4 * idx], pk[4 * idx + 1], pk[4 * idx + 2], pk[4 * idx + 3]);
+      }
+      umma::fence_proxy_async();
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(umma::smem_u32(&p_full[0]));
+    }
+    float* xb = xch + (T & 1) * 256;
+    xb[half * 128 + r] = sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    sum = xb[r] + xb[128 + r];
     umma::mbar_wait(umma::smem_u32(o_full), 0);
     umma::tc_fence_after();
     const int m = qblk * 128 + r;
