@@ -247,6 +247,10 @@ int vd3d_depth_infer_device(vd3d_depth* e, const uint8_t* frame_bgr_dev, int h, 
 int vd3d_depth_get_buffer(vd3d_depth* e, const char* name, void* host_out, size_t bytes);
 /* unit-test hooks for the tensor-core kernels */
 int vd3d_gemm_f16(vd3d_depth* e, const void* A_f16, const void* B_f16, int M, int N, int K, float* C_host, int bn);
+/* tuning hook: average launch time (ms) of one M x N x K GEMM on device-resident operands. variant: 0 <128,3> two
+   CTAs/SM, 1 <128,6>, 2 <128,3> one CTA/SM, 10-12 CTA pair 256x256 (6/4/2 stages), 20-22 CTA pair 256x128;
+   dbg: 0 normal, 1 no MMAs (operand-feed rate), 2 no TMA loads (MMA rate); act: 0 none, 1 GELU */
+int vd3d_gemm_bench(vd3d_depth* e, int M, int N, int K, int variant, int dbg, int act, int iters, float* ms_out);
 int vd3d_conv_f16(vd3d_depth* e, const void* in_nhwc_f16, int H, int W, int cin, const void* w_f16, int cout,
                   int k3, const float* bias, int relu, float* out_host);
 

@@ -31,6 +31,20 @@ def test_gemm_matches_numpy(eng, shape):
         assert np.abs(out - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max()), (shape, bn)
 
 
+@pytest.mark.parametrize("bn", [256, -128])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (256, 512, 768), (300, 640, 256), (2443, 2304, 768),
+                                   (2443, 768, 3072), (129, 130, 8), (1000, 96, 128)])
+def test_gemm_cta_pair_matches_numpy(eng, shape, bn):
+    """cta_group::2 kernel (256-row tiles over two SMs): odd 128-row tile counts, ragged N and K, many k-blocks."""
+    M, N, K = shape
+    rng = np.random.default_rng(M * 11 + N + (bn & 255))
+    A = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
+    B = (rng.standard_normal((N, K)) * 0.5).astype(np.float16)
+    ref = A.astype(np.float32) @ B.astype(np.float32).T
+    out = eng.gemm(A, B, bn)
+    assert np.abs(out - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max()), (shape, bn)
+
+
 @pytest.mark.parametrize("case", [(37, 66, 64, 64, True), (74, 132, 128, 64, True), (19, 33, 64, 128, True),
                                   (148, 264, 64, 64, True), (40, 50, 64, 32, True), (37, 66, 128, 64, False)])
 def test_conv_matches_torch(eng, case):

@@ -137,13 +137,40 @@ GemmArgs base_args(int M, int N, int K, int epi) {
 
 int pick_bn(int N) { return N >= 128 ? 128 : (N >= 64 ? 64 : 32); }
 
+// B tensor-map box rows for a tile code (see launch_gemm): the CTA-pair kernels stage half the tile's N per CTA
+int box_rows(int bn) { return bn == 256 ? 128 : (bn == -128 ? 64 : bn); }
+
+// VD3D_GEMM_2CTA=1: route large plain GEMMs through the cta_group::2 kernel (256-row tiles)
+int pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* v = getenv("VD3D_GEMM_2CTA");
+    mode = v ? atoi(v) : 0;
+  }
+  return mode;
+}
+int pick_bn_gemm(int M, int N) {
+  if (pair_mode() && M >= 512) {
+    if (N >= 1536) return 256;
+    if (N >= 512) return -128;
+  }
+  return pick_bn(N);
+}
+int pick_bn_conv(int M, int N) {  // VD3D_GEMM_2CTA=2: implicit-GEMM convs too (two pixel tiles per pair)
+  if (pair_mode() >= 2 && M >= 2048) {
+    if (N >= 256) return 256;
+    if (N >= 128) return -128;
+  }
+  return pick_bn(N);
+}
+
 // plain GEMM: A [M, K] (lda), B [N, K] (ldb)
 int gemm(vd3d_depth* e, const __half* A, int lda, const __half* B, int ldb, GemmArgs g, int bn = 0) {
-  if (!bn) bn = pick_bn(g.N);  // (64-wide tiles for sub-wave grids were measured slower: L2->smem fill bound)
+  if (!bn) bn = pick_bn_gemm(g.M, g.N);  // (64-wide tiles for sub-wave grids were measured slower: L2->smem fill bound)
   CUtensorMap ma, mb;
   int r;
   if ((r = make_map(e, &ma, A, g.K, g.M, 1, lda, (uint64_t)lda * g.M, 128, 1))) return r;
-  if ((r = make_map(e, &mb, B, g.K, g.N, 1, ldb, (uint64_t)ldb * g.N, bn, 1))) return r;
+  if ((r = make_map(e, &mb, B, g.K, g.N, 1, ldb, (uint64_t)ldb * g.N, box_rows(bn), 1))) return r;
   cudaError_t ce = launch_gemm(bn, ma, mb, g, (g.M + 127) / 128, 1, e->stream);
   if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(ce));
   e->launches++;
@@ -156,7 +183,7 @@ int gemm_batched(vd3d_depth* e, const __half* A, int lda, uint64_t sa, const __h
   CUtensorMap ma, mb;
   int r;
   if ((r = make_map(e, &ma, A, g.K, g.M, batch, lda, sa, 128, 1))) return r;
-  if ((r = make_map(e, &mb, B, g.K, g.N, batch, ldb, sb, bn, 1))) return r;
+  if ((r = make_map(e, &mb, B, g.K, g.N, batch, ldb, sb, box_rows(bn), 1))) return r;
   cudaError_t ce = launch_gemm(bn, ma, mb, g, (g.M + 127) / 128, batch, e->stream);
   if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(ce));
   e->launches++;
@@ -179,7 +206,7 @@ void pick_tile(int W, int H, int& tw, int& th) {
 // conv over an NHWC f16 map [H, W, cin] (3x3 pad 1 when k3, else 1x1); weights [N, taps*cin]
 int conv(vd3d_depth* e, const __half* in, int H, int W, int cin, const __half* wt, bool k3, GemmArgs g, int bn = 0) {
   if (cin % 64) return dfail(e, VD3D_ERR_ARG, "conv: cin must be a multiple of 64");
-  if (!bn) bn = pick_bn(g.N);
+  if (!bn) bn = pick_bn_conv(H * W, g.N);
   int tw, th;
   pick_tile(W, H, tw, th);
   g.conv = k3 ? 1 : 2;
@@ -193,7 +220,7 @@ int conv(vd3d_depth* e, const __half* in, int H, int W, int cin, const __half* w
   CUtensorMap ma, mb;
   int r;
   if ((r = make_map(e, &ma, in, cin, W, H, cin, (uint64_t)cin * W, tw, th))) return r;
-  if ((r = make_map(e, &mb, wt, g.K, g.N, 1, g.K, (uint64_t)g.K * g.N, bn, 1))) return r;
+  if ((r = make_map(e, &mb, wt, g.K, g.N, 1, g.K, (uint64_t)g.K * g.N, box_rows(bn), 1))) return r;
   int m_tiles = ((W + tw - 1) / tw) * ((H + th - 1) / th);
   cudaError_t ce = launch_gemm(bn, ma, mb, g, m_tiles, 1, e->stream);
   if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("conv launch: ") + cudaGetErrorString(ce));
@@ -329,6 +356,42 @@ int vd3d_gemm_f16(vd3d_depth* e, const void* A, const void* B, int M, int N, int
   return VD3D_OK;
 }
 
+// tuning hook: time one GEMM shape (EPI_F16 epilogue, optional GELU) on device-resident operands with an explicit
+// kernel variant (launch_gemm_variant) and debug mode (GemmArgs::dbg); returns the average launch time in ms
+int vd3d_gemm_bench(vd3d_depth* e, int M, int N, int K, int variant, int dbg, int act, int iters, float* ms_out) {
+  if (!e || !ms_out || (K % 8) || iters < 1) return VD3D_ERR_ARG;
+  void *da, *db, *dc;
+  int r;
+  if ((r = get_buf(e, "t.ba", (size_t)M * K * 2, &da))) return r;
+  if ((r = get_buf(e, "t.bb", (size_t)N * K * 2, &db))) return r;
+  if ((r = get_buf(e, "t.bc", (size_t)M * N * 2, &dc))) return r;
+  DCK(cudaMemsetAsync(da, 0x2c, (size_t)M * K * 2, e->stream));  // 0x2c2c = 0.0652 in f16
+  DCK(cudaMemsetAsync(db, 0x2c, (size_t)N * K * 2, e->stream));
+  GemmArgs g = base_args(M, N, K, EPI_F16);
+  g.out_f16 = (__half*)dc;
+  g.act = act;
+  g.dbg = dbg;
+  CUtensorMap ma, mb;
+  if ((r = make_map(e, &ma, da, K, M, 1, K, (uint64_t)K * M, 128, 1))) return r;
+  if ((r = make_map(e, &mb, db, K, N, 1, K, (uint64_t)K * N, variant >= 20 ? 64 : 128, 1))) return r;
+  cudaEvent_t e0, e1;
+  DCK(cudaEventCreate(&e0));
+  DCK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3 + iters; ++i) {
+    if (i == 3) DCK(cudaEventRecord(e0, e->stream));
+    cudaError_t ce = launch_gemm_variant(variant, ma, mb, g, (M + 127) / 128, 1, e->stream);
+    if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("gemm bench launch: ") + cudaGetErrorString(ce));
+  }
+  DCK(cudaEventRecord(e1, e->stream));
+  DCK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  DCK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = ms / iters;
+  return VD3D_OK;
+}
+
 // unit-test hook: 3x3 (or 1x1) conv on an NHWC f16 map through the implicit-GEMM path
 int vd3d_conv_f16(vd3d_depth* e, const void* in_nhwc, int H, int W, int cin, const void* wt, int cout, int k3,
                   const float* bias, int relu, float* out_host) {
@@ -437,7 +500,7 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
       g.npad = NP;
       g.dmodel = D;
       g.qscale = 0.125f;  // 1/sqrt(64), exact in f16
-      if ((r = gemm(e, (const __half*)xn, D, wqkv, D, g, 128))) return r;
+      if ((r = gemm(e, (const __half*)xn, D, wqkv, D, g))) return r;
     }
     if (e->flash) {
       // fused tcgen05 attention: scores stay in TMEM, probabilities in shared memory

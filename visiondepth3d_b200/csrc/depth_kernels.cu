@@ -7,6 +7,7 @@
 
 #include "depth_launch.h"
 #include "umma_gemm.cuh"
+#include "umma_gemm2.cuh"
 #include "umma_attention.cuh"
 
 namespace vd3d {
@@ -440,20 +441,95 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
   return cudaGetLastError();
 }
 
-cudaError_t launch_gemm(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g_in, int m_tiles,
-                        int batch, cudaStream_t s) {
-  // persistent grid: two CTAs per SM (97 KB smem, 2 x BN TMEM columns each), each walks its tiles
+// CTA-pair kernel: cluster of 2, one CTA per SM, persistent over pair tiles (256 x BN)
+template <int BN, int STAGES>
+static cudaError_t launch_gemm2_t(const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int npairs,
+                                  cudaStream_t s) {
+  static bool attr_set = false;
+  constexpr int smem = Gemm2Smem<BN, STAGES>::kTotal;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_umma_gemm2<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(2 * npairs, 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_umma_gemm2<BN, STAGES>, a, b, g);
+}
+
+// tuning hook (vd3d_gemm_bench): pick the kernel instantiation / grid shape explicitly.
+//   0: <128,3> two CTAs per SM   1: <128,6> one CTA per SM   2: <128,3> one CTA per SM
+//  10..12: CTA pair 256x256, 6 / 4 / 2 stages     20..22: CTA pair 256x128, 8 / 4 stages / 4 stages two pairs per TPC
+cudaError_t launch_gemm_variant(int variant, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g_in,
+                                int m_tiles, int batch, cudaStream_t s) {
   GemmArgs g = g_in;
-  g.nt = (g.N + bn - 1) / bn;
+  const int tile_n = variant >= 20 ? 128 : (variant >= 10 ? 256 : 128);
+  g.nt = (g.N + tile_n - 1) / tile_n;
   g.mt = m_tiles;
   g.nz = batch;
-  static int resident = 0;
-  if (!resident) {
-    int dev = 0, sms = 148;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (variant >= 10) {
+    int total = g.nt * ((g.mt + 1) / 2) * g.nz;
+    int cap = variant == 22 ? sms : sms / 2;
+    int npairs = total < cap ? total : cap;
+    switch (variant) {
+      case 10: return launch_gemm2_t<256, 6>(a, b, g, npairs, s);
+      case 11: return launch_gemm2_t<256, 4>(a, b, g, npairs, s);
+      case 12: return launch_gemm2_t<256, 2>(a, b, g, npairs, s);
+      case 20: return launch_gemm2_t<128, 8>(a, b, g, npairs, s);
+      case 21:
+      case 22: return launch_gemm2_t<128, 4>(a, b, g, npairs, s);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  int total = g.nt * g.mt * g.nz;
+  int cap = variant == 0 ? 2 * sms : sms;
+  dim3 grid(total < cap ? total : cap, 1, 1);
+  switch (variant) {
+    case 0:
+    case 2: return launch_gemm_t<128, 3>(a, b, g, grid, s);
+    case 1: return launch_gemm_t<128, 6>(a, b, g, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// bn: 32 / 64 / 128 = single-CTA 128 x bn tiles; 256 = CTA-pair 256 x 256 tiles (B box 128 rows);
+//     -128 = CTA-pair 256 x 128 tiles (B box 64 rows)
+cudaError_t launch_gemm(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g_in, int m_tiles,
+                        int batch, cudaStream_t s) {
+  GemmArgs g = g_in;
+  const int tile_n = bn < 0 ? -bn : bn;
+  g.nt = (g.N + tile_n - 1) / tile_n;
+  g.mt = m_tiles;
+  g.nz = batch;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    resident = 2 * sms;
   }
+  if (bn == 256 || bn == -128) {
+    int total = g.nt * ((g.mt + 1) / 2) * g.nz;
+    int npairs = total < sms / 2 ? total : sms / 2;
+    if (bn == 256) return launch_gemm2_t<256, 6>(a, b, g, npairs, s);
+    return launch_gemm2_t<128, 8>(a, b, g, npairs, s);
+  }
+  // persistent grid: two CTAs per SM (97 KB smem, 2 x BN TMEM columns each), each walks its tiles
+  const int resident = 2 * sms;
   int total = g.nt * g.mt * g.nz;
   dim3 grid(total < resident ? total : resident, 1, 1);
   switch (bn) {

@@ -64,6 +64,10 @@ struct GemmArgs {
   // EPI_HEAD
   const float* w3;
   const float* b3p;
+  // tuning hook (vd3d_gemm_bench), low 3 bits: 0 = normal, 1 = skip the MMAs (operand-feed rate), 2 = skip the TMA
+  // loads (MMA rate), 3 = prologue + teardown only, 4 = epilogue only hands the accumulator back, 5 = epilogue
+  // reads TMEM but stores nothing; bit 3 (8): poll barriers with test_wait instead of try_wait
+  int dbg;
 };
 
 namespace umma {
@@ -88,6 +92,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+// non-suspending variant (tuning hook): polls with test_wait instead of the potentially-suspending try_wait
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_dbg(uint32_t bar, uint32_t parity, int spin) {
+  if (spin)
+    mbar_wait_spin(bar, parity);
+  else
+    mbar_wait(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -226,9 +250,235 @@ __device__ __forceinline__ float ex2_fast(float x) {
   return y;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), exact-erf form as in HF's "gelu".  erfc(z) for z >= 0 from Abramowitz-Stegun
+// 7.1.26 (|error| <= 1.5e-7): erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z), and
+// GELU(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2)  (no cancellation for x < 0).  ~14 FP32 ops + 2 MUFU instead of
+// the ~45 of erff(): the fc1 epilogue was ALU bound on erff (tools/gemm_sweep.py).  Output is stored as f16.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  const float z = ax * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  p *= t;
+  const float e = ex2_fast(x * x * -0.72134752044448170368f);  // exp(-x^2 / 2)
+  return fmaf(-0.5f * ax * p, e, fmaxf(x, 0.f));
+}
+
+// 256-bit global accesses (sm_100: LDG/STG.E.256): one full 32-byte sector per thread and instruction
+__device__ __forceinline__ void ldg_v8(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ldg_nc_v8(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 16 fp32 -> 16 f16 (32 bytes) starting at a[base]
+__device__ __forceinline__ void pack16(const float (&a)[32], int base, bool relu, uint32_t (&u)[8]) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float x = a[base + 2 * t], y = a[base + 2 * t + 1];
+    if (relu) {
+      x = fmaxf(x, 0.f);
+      y = fmaxf(y, 0.f);
+    }
+    __half2 h = __floats2half2_rn(x, y);
+    u[t] = *(uint32_t*)&h;
+  }
+}
 
 }  // namespace umma
+
+// Fused epilogue of one 32-column chunk of one accumulator row (thread == row): v = raw fp32 accumulator bits,
+// m = logical output row, n0 = first output column.  Shared by the 1-CTA and the CTA-pair kernels; every
+// register array is indexed with compile-time constants only so the chunk stays in registers.
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& g, const uint32_t (&v)[32], const int m, const int z,
+                                                    const int n0, const bool row_ok, float& head_acc) {
+  if (!row_ok || n0 >= g.N) return;
+  const int nvalid = min(32, g.N - n0);
+  const bool full = (nvalid == 32);
+  float a[32];
+  if (g.bias) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b4 = __ldg((const float4*)(g.bias + n0) + j);
+        a[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+        a[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+        a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+        a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]) + ((j < nvalid) ? g.bias[n0 + j] : 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+  }
+  switch (g.epi) {
+    case EPI_F16: {
+      const size_t o = (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
+      const bool vec = full && ((o & 15) == 0);  // 32-byte aligned: 256-bit accesses
+      if (g.res_f16) {
+        if (vec) {
+          uint32_t rv[2][8];
+          umma::ldg_nc_v8(g.res_f16 + o, rv[0]);
+          umma::ldg_nc_v8(g.res_f16 + o + 16, rv[1]);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              float2 f = __half22float2(*(const __half2*)&rv[j][t]);
+              a[16 * j + 2 * t] += f.x;
+              a[16 * j + 2 * t + 1] += f.y;
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) a[j] += __half2float(g.res_f16[o + j]);
+        }
+      }
+      if (g.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = umma::gelu_erf(a[j]);
+      } else if (g.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.f);
+      }
+      if (vec) {
+        uint32_t u[8];
+        umma::pack16(a, 0, false, u);
+        umma::stg_v8(g.out_f16 + o, u);
+        umma::pack16(a, 16, false, u);
+        umma::stg_v8(g.out_f16 + o + 16, u);
+        if (g.out2_f16) {
+          umma::pack16(a, 0, true, u);
+          umma::stg_v8(g.out2_f16 + o, u);
+          umma::pack16(a, 16, true, u);
+          umma::stg_v8(g.out2_f16 + o + 16, u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) {
+            g.out_f16[o + j] = __float2half_rn(a[j]);
+            if (g.out2_f16) g.out2_f16[o + j] = __float2half_rn(fmaxf(a[j], 0.f));
+          }
+      }
+    } break;
+    case EPI_F32: {
+      float* dst = g.out_f32 + (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
+      if (full && ((((size_t)m * g.ldc + n0) & 3) == 0) && ((g.out_batch_stride & 3) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) dst[j] = a[j];
+      }
+    } break;
+    case EPI_RESID_LS: {
+      // read-modify-write of the fp32 residual stream: issue all loads before the first store
+      // (a load/store-per-element loop serialises on possible aliasing: ~800 cycles per element);
+      // 256-bit accesses: every instruction moves whole 32-byte sectors
+      float* dst = g.out_f32 + (size_t)m * g.ldc + n0;
+      if (full && ((((size_t)m * g.ldc + n0) & 7) == 0)) {
+        uint32_t x8[4][8];
+        float4 l4[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma::ldg_v8(dst + 8 * j, x8[j]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) l4[j] = __ldg((const float4*)(g.ls + n0) + j);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const float4 l = l4[2 * j + t];
+            x8[j][4 * t + 0] = __float_as_uint(fmaf(l.x, a[8 * j + 4 * t + 0], __uint_as_float(x8[j][4 * t + 0])));
+            x8[j][4 * t + 1] = __float_as_uint(fmaf(l.y, a[8 * j + 4 * t + 1], __uint_as_float(x8[j][4 * t + 1])));
+            x8[j][4 * t + 2] = __float_as_uint(fmaf(l.z, a[8 * j + 4 * t + 2], __uint_as_float(x8[j][4 * t + 2])));
+            x8[j][4 * t + 3] = __float_as_uint(fmaf(l.w, a[8 * j + 4 * t + 3], __uint_as_float(x8[j][4 * t + 3])));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma::stg_v8(dst + 8 * j, x8[j]);
+      } else {
+        float xv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xv[j] = (j < nvalid) ? dst[j] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) dst[j] = xv[j] + g.ls[n0 + j] * a[j];
+      }
+    } break;
+    case EPI_QKV: {
+      // n0 is a multiple of 32 and head_dim is 64: the 32 columns lie in one (which, head)
+      const int which = n0 / g.dmodel;
+      const int rem = n0 - which * g.dmodel;
+      const int h = rem >> 6, d0 = rem & 63;
+      if (which < 2) {
+        __half* dst = (which == 0 ? g.q : g.k) + ((size_t)h * g.npad + m) * 64 + d0;
+        const float sc = which == 0 ? g.qscale : 1.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] *= sc;
+        uint32_t u[8];
+        umma::pack16(a, 0, false, u);
+        umma::stg_v8(dst, u);
+        umma::pack16(a, 16, false, u);
+        umma::stg_v8(dst + 16, u);
+      } else {
+        __half* dst = g.vt + ((size_t)h * 64 + d0) * g.npad + m;  // transposed: lanes -> consecutive m
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[(size_t)j * g.npad] = __float2half_rn(a[j]);
+      }
+    } break;
+    case EPI_PATCH: {
+      float* dst = g.out_f32 + (size_t)(m + 1) * g.ldc + n0;
+      const float* pe = g.pos + (size_t)(m + 1) * g.ldc + n0;
+      float pv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pv[j] = (j < nvalid) ? __ldg(pe + j) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) dst[j] = a[j] + pv[j];
+    } break;
+    case EPI_CONVT: {
+      // n = (dy*k + dx)*Cout + co ; m = y*ct_w + x ; out NHWC [(H*k), (W*k), Cout]
+      const int tap = n0 / g.ct_cout, co = n0 % g.ct_cout;
+      const int dy = tap / g.ct_k, dx = tap % g.ct_k;
+      const int y = m / g.ct_w, x = m % g.ct_w;
+      size_t o = ((size_t)(y * g.ct_k + dy) * (g.ct_w * g.ct_k) + (x * g.ct_k + dx)) * g.ct_cout + co;
+      if (full && ((o & 15) == 0)) {
+        uint32_t u[8];
+        umma::pack16(a, 0, false, u);
+        umma::stg_v8(g.out_f16 + o, u);
+        umma::pack16(a, 16, false, u);
+        umma::stg_v8(g.out_f16 + o + 16, u);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) g.out_f16[o + j] = __float2half_rn(a[j]);
+      }
+    } break;
+    case EPI_HEAD: {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) head_acc += fmaxf(a[j], 0.f) * __ldg(g.w3 + n0 + j);
+    } break;
+  }
+}
 
 constexpr int kGemmThreads = 320;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (2 per lane quarter)
 constexpr int kBK = 64;            // 64 f16 = 128 B = one swizzle row
@@ -260,6 +510,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // persistent: this CTA walks tiles blockIdx.x, +gridDim.x, ...; n fastest so co-resident CTAs share A in L2
   const int total_tiles = g.nt * g.mt * g.nz;
   const int nkb = (g.K + kBK - 1) / kBK;
+  const int dmode = g.dbg & 7, spin = g.dbg & 8;
 
   if (warp == 0 && lane == 0) {
     umma::prefetch_tmap(&tmA);
@@ -293,7 +544,9 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   };
 
-  if (warp == 0) {
+  if (dmode == 3) {
+    // tuning: prologue + teardown only
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int kit = 0;  // k-block counter across tiles (ring position)
@@ -303,8 +556,12 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int kb = 0; kb < nkb; ++kb, ++kit) {
         const int s = kit % STAGES;
         const uint32_t ph = (kit / STAGES) & 1;
-        umma::mbar_wait(umma::smem_u32(&empty[s]), ph ^ 1);
+        umma::mbar_wait_dbg(umma::smem_u32(&empty[s]), ph ^ 1, spin);
         const uint32_t fb = umma::smem_u32(&full[s]);
+        if (dmode == 2) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+          continue;
+        }
         umma::mbar_expect_tx(fb, S::kStage);
         const uint32_t sa = umma::smem_u32(smem + s * S::kStage);
         const uint32_t sb = sa + S::kABytes;
@@ -331,22 +588,24 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int kit = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;  // accumulator stage
-      umma::mbar_wait(umma::smem_u32(&tmem_empty[as]), ((it >> 1) & 1) ^ 1);
+      umma::mbar_wait_dbg(umma::smem_u32(&tmem_empty[as]), ((it >> 1) & 1) ^ 1, spin);
       umma::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
       for (int kb = 0; kb < nkb; ++kb, ++kit) {
         const int s = kit % STAGES;
         const uint32_t ph = (kit / STAGES) & 1;
-        umma::mbar_wait(umma::smem_u32(&full[s]), ph);
+        umma::mbar_wait_dbg(umma::smem_u32(&full[s]), ph, spin);
         umma::tc_fence_after();
         const uint32_t sa = umma::smem_u32(smem + s * S::kStage);
         const uint32_t sb = sa + S::kABytes;
         const uint64_t da = umma::make_desc(sa);
         const uint64_t db = umma::make_desc(sb);
+        if (dmode != 1) {
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
-          umma::mma_f16(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
+            umma::mma_f16(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
         }
         umma::umma_commit(umma::smem_u32(&empty[s]));  // frees this ring slot when the MMAs retire
       }
@@ -366,7 +625,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int n_blk, m_blk, z, px0, py0;
     decode(tile, n_blk, m_blk, z, px0, py0);
     const int as = it & 1;
-    umma::mbar_wait(umma::smem_u32(&tmem_full[as]), (it >> 1) & 1);
+    umma::mbar_wait_dbg(umma::smem_u32(&tmem_full[as]), (it >> 1) & 1, spin);
     umma::tc_fence_after();
     const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
     const int r = q * 32 + lane;  // accumulator row inside the tile
@@ -384,214 +643,16 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     float head_acc = 0.f;
 #pragma unroll 1
     for (int ci = half; ci < kChunks; ci += 2) {
+      if (dmode == 4) break;
       const int c0 = ci * 32;
       uint32_t v[32];
       umma::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       const int n0 = n_blk * BN + c0;
-      if (!row_ok || n0 >= g.N) continue;
-      const int nvalid = min(32, g.N - n0);
-      const bool full = (nvalid == 32);
-      float a[32];
-      if (g.bias) {
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b4 = __ldg((const float4*)(g.bias + n0) + j);
-            a[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
-            a[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
-            a[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
-            a[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]) + ((j < nvalid) ? g.bias[n0 + j] : 0.f);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+      if (dmode == 5) {
+        if (v[0] == 0x7fc12345u && v[17] == 0x12345u) g.out_f32[0] = 1.f;  // keep the load alive
+        continue;
       }
-      switch (g.epi) {
-        case EPI_F16: {
-          const size_t o = (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
-          const bool vec = full && ((o & 7) == 0);
-          if (g.res_f16) {
-            if (vec) {
-              uint4 rv[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rv[j] = __ldg((const uint4*)(g.res_f16 + o) + j);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const __half2* hh = (const __half2*)&rv[j];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  float2 f = __half22float2(hh[t]);
-                  a[8 * j + 2 * t] += f.x;
-                  a[8 * j + 2 * t + 1] += f.y;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) a[j] += __half2float(g.res_f16[o + j]);
-            }
-          }
-          if (g.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = umma::gelu_erf(a[j]);
-          } else if (g.act == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.f);
-          }
-          if (vec) {
-            uint4* dst = (uint4*)(g.out_f16 + o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __half2 h0 = __floats2half2_rn(a[8 * j + 0], a[8 * j + 1]);
-              __half2 h1 = __floats2half2_rn(a[8 * j + 2], a[8 * j + 3]);
-              __half2 h2 = __floats2half2_rn(a[8 * j + 4], a[8 * j + 5]);
-              __half2 h3 = __floats2half2_rn(a[8 * j + 6], a[8 * j + 7]);
-              uint4 u;
-              u.x = *(uint32_t*)&h0;
-              u.y = *(uint32_t*)&h1;
-              u.z = *(uint32_t*)&h2;
-              u.w = *(uint32_t*)&h3;
-              dst[j] = u;
-            }
-            if (g.out2_f16) {
-              uint4* d2 = (uint4*)(g.out2_f16 + o);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                __half2 h0 = __floats2half2_rn(fmaxf(a[8 * j + 0], 0.f), fmaxf(a[8 * j + 1], 0.f));
-                __half2 h1 = __floats2half2_rn(fmaxf(a[8 * j + 2], 0.f), fmaxf(a[8 * j + 3], 0.f));
-                __half2 h2 = __floats2half2_rn(fmaxf(a[8 * j + 4], 0.f), fmaxf(a[8 * j + 5], 0.f));
-                __half2 h3 = __floats2half2_rn(fmaxf(a[8 * j + 6], 0.f), fmaxf(a[8 * j + 7], 0.f));
-                uint4 u;
-                u.x = *(uint32_t*)&h0;
-                u.y = *(uint32_t*)&h1;
-                u.z = *(uint32_t*)&h2;
-                u.w = *(uint32_t*)&h3;
-                d2[j] = u;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) {
-                g.out_f16[o + j] = __float2half_rn(a[j]);
-                if (g.out2_f16) g.out2_f16[o + j] = __float2half_rn(fmaxf(a[j], 0.f));
-              }
-          }
-        } break;
-        case EPI_F32: {
-          float* dst = g.out_f32 + (size_t)z * g.out_batch_stride + (size_t)m * g.ldc + n0;
-          if (full && ((((size_t)m * g.ldc + n0) & 3) == 0) && ((g.out_batch_stride & 3) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) dst[j] = a[j];
-          }
-        } break;
-        case EPI_RESID_LS: {
-          // read-modify-write of the fp32 residual stream: issue all loads before the first store
-          // (a load/store-per-element loop serialises on possible aliasing: ~800 cycles per element)
-          float* dst = g.out_f32 + (size_t)m * g.ldc + n0;
-          if (full && ((((size_t)m * g.ldc + n0) & 3) == 0)) {
-            float4 x4[8], l4[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              x4[j] = __ldcg((const float4*)dst + j);
-              l4[j] = __ldg((const float4*)(g.ls + n0) + j);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              x4[j].x += l4[j].x * a[4 * j + 0];
-              x4[j].y += l4[j].y * a[4 * j + 1];
-              x4[j].z += l4[j].z * a[4 * j + 2];
-              x4[j].w += l4[j].w * a[4 * j + 3];
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) ((float4*)dst)[j] = x4[j];
-          } else {
-            float xv[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) xv[j] = (j < nvalid) ? dst[j] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) dst[j] = xv[j] + g.ls[n0 + j] * a[j];
-          }
-        } break;
-        case EPI_QKV: {
-          // n0 is a multiple of 32 and head_dim is 64: the 32 columns lie in one (which, head)
-          const int which = n0 / g.dmodel;
-          const int rem = n0 - which * g.dmodel;
-          const int h = rem >> 6, d0 = rem & 63;
-          if (which < 2) {
-            __half* dst = (which == 0 ? g.q : g.k) + ((size_t)h * g.npad + m) * 64 + d0;
-            const float sc = which == 0 ? g.qscale : 1.0f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __half2 h0 = __floats2half2_rn(a[8 * j + 0] * sc, a[8 * j + 1] * sc);
-              __half2 h1 = __floats2half2_rn(a[8 * j + 2] * sc, a[8 * j + 3] * sc);
-              __half2 h2 = __floats2half2_rn(a[8 * j + 4] * sc, a[8 * j + 5] * sc);
-              __half2 h3 = __floats2half2_rn(a[8 * j + 6] * sc, a[8 * j + 7] * sc);
-              uint4 u;
-              u.x = *(uint32_t*)&h0;
-              u.y = *(uint32_t*)&h1;
-              u.z = *(uint32_t*)&h2;
-              u.w = *(uint32_t*)&h3;
-              ((uint4*)dst)[j] = u;
-            }
-          } else {
-            __half* dst = g.vt + ((size_t)h * 64 + d0) * g.npad + m;  // transposed: lanes -> consecutive m
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dst[(size_t)j * g.npad] = __float2half_rn(a[j]);
-          }
-        } break;
-        case EPI_PATCH: {
-          float* dst = g.out_f32 + (size_t)(m + 1) * g.ldc + n0;
-          const float* pe = g.pos + (size_t)(m + 1) * g.ldc + n0;
-          float pv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) pv[j] = (j < nvalid) ? __ldg(pe + j) : 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) dst[j] = a[j] + pv[j];
-        } break;
-        case EPI_CONVT: {
-          // n = (dy*k + dx)*Cout + co ; m = y*ct_w + x ; out NHWC [(H*k), (W*k), Cout]
-          const int tap = n0 / g.ct_cout, co = n0 % g.ct_cout;
-          const int dy = tap / g.ct_k, dx = tap % g.ct_k;
-          const int y = m / g.ct_w, x = m % g.ct_w;
-          size_t o = ((size_t)(y * g.ct_k + dy) * (g.ct_w * g.ct_k) + (x * g.ct_k + dx)) * g.ct_cout + co;
-          if (full && ((o & 7) == 0)) {
-            uint4* dst = (uint4*)(g.out_f16 + o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __half2 h0 = __floats2half2_rn(a[8 * j + 0], a[8 * j + 1]);
-              __half2 h1 = __floats2half2_rn(a[8 * j + 2], a[8 * j + 3]);
-              __half2 h2 = __floats2half2_rn(a[8 * j + 4], a[8 * j + 5]);
-              __half2 h3 = __floats2half2_rn(a[8 * j + 6], a[8 * j + 7]);
-              uint4 u;
-              u.x = *(uint32_t*)&h0;
-              u.y = *(uint32_t*)&h1;
-              u.z = *(uint32_t*)&h2;
-              u.w = *(uint32_t*)&h3;
-              dst[j] = u;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) g.out_f16[o + j] = __float2half_rn(a[j]);
-          }
-        } break;
-        case EPI_HEAD: {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) head_acc += fmaxf(a[j], 0.f) * __ldg(g.w3 + n0 + j);
-        } break;
-      }
+      gemm_epilogue_chunk(g, v, m, z, n0, row_ok, head_acc);
     }
     // DPT head: N == 32 is a single chunk, owned by the half-0 warps
     if (g.epi == EPI_HEAD && half == 0 && row_ok && n_blk == 0) g.out_f32[m] = fmaxf(head_acc + g.b3p[0], 0.f);
