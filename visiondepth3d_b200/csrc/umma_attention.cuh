@@ -26,6 +26,7 @@ struct AttnArgs {
   __half* out;  // [ntok, dmodel], head h writes columns [64h, 64h+64)
 };
 
+constexpr bool kAttnPolyExp = false;  // true: a third of the softmax exponentials on the FMA pipe (umma::ex2_poly) -- measured 2 % SLOWER (profiles/r01_ncu_full_final.md)
 constexpr int kAttnThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (2 per TMEM lane quarter)
 // Two CTAs per SM (96 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs
 // and 240 CTAs (20 query blocks x 12 heads) fit in a single wave of 296 slots.
@@ -476,8 +477,12 @@ k_umma_attention_1p(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 64; j += 2) {
-          float p0 = umma::ex2_fast(fmaf(__uint_as_float(v[j]), L2E, -m_ref));
-          float p1 = umma::ex2_fast(fmaf(__uint_as_float(v[j + 1]), L2E, -m_ref));
+          // one exponential in three on the FMA pipe (ex2_poly), the rest on the MUFU: the loop is MUFU bound otherwise
+          const float x0 = fmaf(__uint_as_float(v[j]), L2E, -m_ref);
+          const float x1 = fmaf(__uint_as_float(v[j + 1]), L2E, -m_ref);
+          const int sel = (j >> 1) % 3;
+          float p0 = (kAttnPolyExp && sel == 0) ? umma::ex2_poly(x0) : umma::ex2_fast(x0);
+          float p1 = (kAttnPolyExp && sel == 1) ? umma::ex2_poly(x1) : umma::ex2_fast(x1);
           s0 += p0;
           s1 += p1;
           __half2 hp = __floats2half2_rn(p0, p1);

@@ -250,6 +250,21 @@ __device__ __forceinline__ float ex2_fast(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5 * 2^23,
+// degree-4 minimax of 2^f on [-0.5, 0.5] (relative error 2.7e-6 in fp32), n added to the exponent field.  Valid for
+// -125 <= x < 2^21 (clamped below).  The attention softmax runs a third of its exponentials here: ex2.approx issues at
+// a quarter of a warp per SM sub-partition clock on B200 and was the kernel's bound (ncu: XU pipe 71 % of elapsed).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.009570102207362652f, 0.05591785907745361f);
+  p = fmaf(f, p, 0.240247443318367f);
+  p = fmaf(f, p, 0.6931217908859253f);
+  p = fmaf(f, p, 0.9999992847442627f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)), exact-erf form as in HF's "gelu".  erfc(z) for z >= 0 from Abramowitz-Stegun
 // 7.1.26 (|error| <= 1.5e-7): erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z), and
 // GELU(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2)  (no cancellation for x < 0).  ~14 FP32 ops + 2 MUFU instead of
