@@ -230,7 +230,11 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dof", type=float, default=None,
+                    help="dof_strength (default 0 = the warp/fill/compose variant; 2.0 = the reference GUI default)")
     args = ap.parse_args()
+    if args.dof is not None:
+        COMMON["dof"] = args.dof
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -382,7 +386,7 @@ def main():
                 "depth_model": f"Depth-Anything-V2 {wl['model']} @518x924, random-init seed 0 (no checkpoints offline), "
                                "f16 tensor-core operands / fp32 accumulate",
                 "stage": "DPT processor + depth forward + min-max u8 handoff in HBM + DIBR frame loop + pack",
-                "launch_mode": "CUDA graph replay; depth forwards of consecutive frames overlap on two streams "
+                "launch_mode": "CUDA graph replay; depth forwards of consecutive frames overlap on three streams "
                                "(stage timings in roofline* are taken in a separate serial, eager pass)",
                 "params": COMMON, "sharding": "contiguous chunks per rank, independent temporal state per chunk",
             },
