@@ -41,7 +41,7 @@ enum {
   VD3D_FMT_FULL_SBS = 1,
   VD3D_FMT_ANAGLYPH = 2,   /* "Red-Cyan Anaglyph" */
   VD3D_FMT_INTERLACED = 3, /* "Passive Interlaced" */
-  VD3D_FMT_VR = 4          /* unsupported (cv2 INTER_LINEAR upscale to 1440x1600) */
+  VD3D_FMT_VR = 4          /* 2 x 1440x1600: eyes fitted by pad_to_aspect_ratio (INTER_AREA shrink only) */
 };
 
 /* which temporal state vd3d_reset_state clears */
@@ -201,6 +201,11 @@ int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor,
  * its render loop): f32 RGB planes [3,h,w] warped + original, optional edge mask [h,w] -> f32 [3,h,w] */
 int vd3d_heal(vd3d_ctx* ctx, const float* warped, const float* original, const float* edge_mask_or_null, int h, int w,
               double heal_strength, float* out, int mem);
+/* eye fit on one u8 BGR image [h,w,3] -> [target_h,target_w,3]: keep_aspect != 0 = pad_to_aspect_ratio (101-131, black
+ * canvas), 0 = cv2.resize(..., INTER_AREA) as in the Half-SBS branch (1413-1414).  Shrinking only: identity, integer
+ * factors, or cv2's general (fractional) area tables; enlarging returns VD3D_ERR_UNSUPPORTED */
+int vd3d_fit_eye(vd3d_ctx* ctx, const uint8_t* src, int h, int w, int target_w, int target_h, int keep_aspect,
+                 uint8_t* dst, int mem);
 /* format_3d_output / generate_anaglyph_3d (837-883) on two same-size u8 BGR eyes [h,w,3]:
  * SBS -> [h,2w,3]; anaglyph / interlaced -> [h,w,3] */
 int vd3d_pack(vd3d_ctx* ctx, const uint8_t* left, const uint8_t* right, int h, int w, int fmt, uint8_t* dst, int mem);

@@ -600,12 +600,69 @@ def resize_area_int(img: np.ndarray, ow: int, oh: int) -> np.ndarray:
     h, w = img.shape[:2]
     if (w, h) == (ow, oh):
         return img.copy()
-    assert w % ow == 0 and h % oh == 0, "oracle covers integer INTER_AREA factors only"
+    assert w % ow == 0 and h % oh == 0, "integer INTER_AREA factors only (resize_area handles the rest)"
     sx, sy = w // ow, h // oh
     v = img.reshape(oh, sy, ow, sx, -1).astype(np.int64).sum(axis=(1, 3))
     if sx == 2 and sy == 2:
         return ((v + 2) >> 2).astype(np.uint8)
     return _round_half_even_u8((v.astype(f32) * f32(1.0 / (sx * sy))).astype(f32))
+
+
+def area_tab(ssize: int, dsize: int):
+    """cv2's computeResizeAreaTab (imgproc resize.cpp; third-party, opencv 4.13 as installed): per destination
+    index the list of (source index, fp32 weight).  All geometry in double, weights rounded once to fp32."""
+    import math
+    scale = 1.0 / (dsize / ssize)  # cv2: inv_scale = dsize / ssize; scale = 1. / inv_scale
+    tab = []
+    for dx in range(dsize):
+        fsx1 = dx * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1 = math.ceil(fsx1)
+        sx2 = min(math.floor(fsx2), ssize - 1)
+        sx1 = min(sx1, sx2)
+        ent = []
+        if sx1 - fsx1 > 1e-3:
+            ent.append((sx1 - 1, f32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            ent.append((sx, f32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            ent.append((sx2, f32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+        tab.append(ent)
+    return tab
+
+
+def resize_area(img: np.ndarray, ow: int, oh: int) -> np.ndarray:
+    """cv2.resize(img, (ow, oh), interpolation=cv2.INTER_AREA) for shrinking (both scales >= 1), as called by
+    pad_to_aspect_ratio / the Half-SBS eye fit (core/render_3d.py:121, 1413-1414).  Identity -> copy; integer factors
+    on both axes -> cv2's "area fast" path (resize_area_int); otherwise cv2's ResizeArea_: per source row
+    buf[dx] = sum_k S[sx_k] * alpha_k (fp32, separate multiply and add, table order), rows combined as
+    sum = beta_0 * buf_0 (+ beta_j * buf_j ...) in fp32, saturate_cast<uchar> = round-half-even.
+    Pinned against the real cv2.resize in tests/test_oracle_golden.py (exact)."""
+    h, w = img.shape[:2]
+    if (w, h) == (ow, oh):
+        return img.copy()
+    if w % ow == 0 and h % oh == 0:
+        return resize_area_int(img, ow, oh)
+    assert ow <= w and oh <= h, "oracle covers INTER_AREA shrinking only (cv2 switches to a bilinear scheme when enlarging)"
+    squeeze = img.ndim == 2
+    S = (img[..., None] if squeeze else img).astype(f32)
+    xt, yt = area_tab(w, ow), area_tab(h, oh)
+    buf = np.zeros((h, ow, S.shape[2]), dtype=f32)
+    for k in range(max(len(e) for e in xt)):
+        idx = np.array([e[k][0] if k < len(e) else 0 for e in xt])
+        al = np.array([e[k][1] if k < len(e) else f32(0) for e in xt], dtype=f32)
+        valid = np.array([k < len(e) for e in xt])
+        term = (S[:, idx, :] * al[None, :, None]).astype(f32)
+        buf = np.where(valid[None, :, None], (buf + term).astype(f32), buf)
+    out = np.zeros((oh, ow, S.shape[2]), dtype=np.uint8)
+    for dy, ent in enumerate(yt):
+        acc = None
+        for (sy, beta) in ent:
+            t = (beta * buf[sy]).astype(f32)
+            acc = t if acc is None else (acc + t).astype(f32)
+        out[dy] = _round_half_even_u8(acc)
+    return out[..., 0] if squeeze else out
 
 
 def pad_to_aspect(img: np.ndarray, tw: int, th: int) -> np.ndarray:
@@ -617,7 +674,7 @@ def pad_to_aspect(img: np.ndarray, tw: int, th: int) -> np.ndarray:
         nw, nh = tw, int(tw / ca)
     else:
         nh, nw = th, int(ca * th)
-    rs = resize_area_int(img, nw, nh)
+    rs = resize_area(img, nw, nh)
     out = np.zeros((th, tw, 3), dtype=np.uint8)
     xo = (tw - nw) // 2
     yo = (th - nh) // 2
@@ -645,7 +702,10 @@ def anaglyph(left: np.ndarray, right: np.ndarray) -> np.ndarray:
 
 
 def format_output(left: np.ndarray, right: np.ndarray, fmt: str) -> np.ndarray:
-    """format_3d_output (837-860) (VR resize not covered: cv2 INTER_LINEAR upscale)."""
+    """format_3d_output (837-860).  VR: the eyes arrive from pad_to_aspect_ratio already 1440 x 1600 (1129-1133,
+    1415-1417), so format_3d_output's cv2.resize(..., (1440, 1600)) is the identity copy."""
+    if fmt == "VR":
+        assert left.shape[:2] == (1600, 1440) and right.shape[:2] == (1600, 1440), "VR eyes must be 1440x1600"
     if fmt == "Red-Cyan Anaglyph":
         return anaglyph(left, right)
     if fmt == "Passive Interlaced":
@@ -836,8 +896,8 @@ def render_frame(gs: GlobalState, cs: ClipState, frame_bgr: np.ndarray, depth_bg
     ls = sharpen(left, rp.sharpness_factor)
     rs = sharpen(right, rp.sharpness_factor)
     if rp.output_format == "Half-SBS":
-        lo_ = resize_area_int(ls, pl.per_eye_w, pl.per_eye_h)
-        ro_ = resize_area_int(rs, pl.per_eye_w, pl.per_eye_h)
+        lo_ = resize_area(ls, pl.per_eye_w, pl.per_eye_h)
+        ro_ = resize_area(rs, pl.per_eye_w, pl.per_eye_h)
     else:
         lo_ = pad_to_aspect(ls, pl.per_eye_w, pl.per_eye_h)
         ro_ = pad_to_aspect(rs, pl.per_eye_w, pl.per_eye_h)

@@ -38,3 +38,7 @@ LOOP_CASES = {
         rp=dict(_BASE, output_format="Passive Interlaced", preserve_original_aspect=True,
                 use_subject_tracking=False, use_floating_window=False, feather_strength=0.0, blur_ksize=1)),
 }
+
+# VR fixture (tools/gen_golden.py vr): 2880x1600 frames, stored as every 3rd row/column of the image band + sha256
+VR_CASE = dict(file="loop_vr_320x180.npz", sw=320, sh=180, n=3, kind="smooth",
+               rp=dict(_BASE, output_width=1600, output_height=900, output_format="VR"))

@@ -184,5 +184,40 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def gen_vr():
+    """H. VR format: 1600x900 eyes -> pad_to_aspect_ratio(1440, 1600) = non-integer INTER_AREA (x1.111) + black
+    bars, hstack to 2880x1600.  Separate entry (`python tools/gen_golden.py vr`) so the earlier fixtures stay
+    byte-identical.  Stored per frame: every 3rd row / column of the image band (the rest of the 2880x1600 frame is
+    black), the band position, and a sha256 of the whole frame."""
+    import hashlib
+    mods = refshim.load_reference(("render_3d",))
+    r3d = mods["render_3d"]
+    import cv2
+    import torch
+    import torchvision
+    torch.set_num_threads(os.cpu_count())
+    meta = dict(torch=torch.__version__, torchvision=torchvision.__version__, cv2=cv2.__version__,
+                numpy=np.__version__)
+    rp = dict(output_width=1600, output_height=900, sharpness_factor=0.2, output_format="VR",
+              dof_strength=0.0, feather_strength=10.0, blur_ksize=9, use_subject_tracking=True,
+              use_floating_window=True, preserve_original_aspect=False, zero_parallax_strength=0.01)
+    g = run_loop(r3d, torch, cv2, 320, 180, 3, "smooth", rp)
+    out = {}
+    for k, f in g.items():
+        assert f.shape == (1600, 2880, 3), f.shape
+        rows = np.nonzero(f.reshape(1600, -1).any(axis=1))[0]
+        y0, y1 = int(rows.min()), int(rows.max()) + 1
+        out[k + "_band"] = f[y0:y1:3, ::3]
+        out[k + "_y0"] = np.int32(y0)
+        out[k + "_y1"] = np.int32(y1)
+        out[k + "_sha256"] = np.frombuffer(hashlib.sha256(f.tobytes()).digest(), dtype=np.uint8)
+    p = os.path.join(OUT, "loop_vr_320x180.npz")
+    np.savez_compressed(p, **out, **meta)
+    print(p, os.path.getsize(p), {k: v.shape for k, v in out.items() if k.endswith("_band")})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "vr":
+        gen_vr()
+    else:
+        main()

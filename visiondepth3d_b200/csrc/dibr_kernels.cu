@@ -1129,6 +1129,22 @@ __device__ __forceinline__ int fitted_px(const PostArgs& a, const uint8_t* eye, 
                                          int bar_hi) {
   int fx = ex - a.fit_x0, fy = ey - a.fit_y0;
   if (fx < 0 || fy < 0 || fx >= a.fit_w || fy >= a.fit_h) return 0;  // pad_to_aspect_ratio canvas
+  if (a.xal) {
+    // cv2 ResizeArea_ (non-integer INTER_AREA shrink): per source row buf = sum_k S * alpha_k, rows combined as
+    // sum = beta_0 * buf_0 + beta_1 * buf_1 ... ; fp32, separate multiply and add (this unit is built with -fmad=false)
+    const int xo = a.xofs[fx], xc = a.xcnt[fx], yo = a.yofs[fy], yc = a.ycnt[fy];
+    const float* xa = a.xal + (size_t)fx * a.area_t;
+    const float* ya = a.yal + (size_t)fy * a.area_t;
+    float acc = 0.f;
+    for (int j = 0; j < yc; ++j) {
+      float buf = 0.f;
+      for (int i = 0; i < xc; ++i)
+        buf = buf + (float)sharp_px(eye, a.H, a.W, yo + j, xo + i, ch, bar_lo, bar_hi, a.kc, a.ke, a.sharpen) * xa[i];
+      const float t = ya[j] * buf;
+      acc = j ? acc + t : t;
+    }
+    return (int)rhe_u8(acc);
+  }
   if (a.sx == 1 && a.sy == 1) return sharp_px(eye, a.H, a.W, fy, fx, ch, bar_lo, bar_hi, a.kc, a.ke, a.sharpen);
   int sum = 0;
   for (int j = 0; j < a.sy; ++j)
@@ -1154,7 +1170,7 @@ __global__ void __launch_bounds__(256) k_post(PostArgs a) {
     }
   }
   uint8_t o[3];
-  if (a.fmt == VD3D_FMT_HALF_SBS || a.fmt == VD3D_FMT_FULL_SBS) {
+  if (a.fmt == VD3D_FMT_HALF_SBS || a.fmt == VD3D_FMT_FULL_SBS || a.fmt == VD3D_FMT_VR) {  // hstack of the fitted eyes
     int eye = ox / a.per_eye_w;
     int ex = ox - eye * a.per_eye_w;
     const uint8_t* e = eye ? a.right : a.left;

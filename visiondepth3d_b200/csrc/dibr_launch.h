@@ -83,6 +83,15 @@ struct PostArgs {
   int fit_x0, fit_y0, fit_w, fit_h;  // placement of the resized eye inside the per-eye canvas
   int sx, sy;                        // integer INTER_AREA factors
   float inv_area;
+  // general (non-integer) INTER_AREA shrink = cv2's ResizeArea_ tables (xal == null: integer / identity path).
+  // Per fitted column / row: first source index, tap count, fp32 weights [index * area_t + k].
+  const int* xofs;
+  const int* xcnt;
+  const float* xal;
+  const int* yofs;
+  const int* ycnt;
+  const float* yal;
+  int area_t;
   uint8_t* out;
   int out_w, out_h;
 };

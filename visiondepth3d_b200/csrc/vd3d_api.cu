@@ -61,6 +61,11 @@ struct vd3d_ctx {
   Buf tdf, dn0, dn1, rgb_s, frameB, d, shift, e2, eyeL, eyeR, eyeL2, eyeR2;
   Buf in_frame[kSlots], in_depth[kSlots], out_dev[kSlots], in_rgbf, in_depthf;
   Buf dof_kern;
+  // cv2 ResizeArea_ tables of the current non-integer eye fit (device) + the sizes they were built for
+  // ([0]: the frame path, whose CUDA graphs bake the pointers in; [1]: the stage entry points vd3d_fit_eye ...)
+  Buf area_tab[2];
+  int at_key[2][4] = {};
+  int at_t[2] = {0, 0};
   int tdf_w = 0, tdf_h = 0;
   int frame_parity = 0;
   cudaEvent_t ev_h2d[kSlots] = {}, ev_done[kSlots] = {}, ev_d2h[kSlots] = {};
@@ -405,10 +410,91 @@ void sharpen_coeffs(double factor, float& kc, float& ke) {
 
 struct FitPlan {
   int fit_x0, fit_y0, fit_w, fit_h, sx, sy;
+  // non-integer INTER_AREA shrink: device tables (null otherwise), see PostArgs
+  const int *xofs = nullptr, *xcnt = nullptr, *yofs = nullptr, *ycnt = nullptr;
+  const float *xal = nullptr, *yal = nullptr;
+  int area_t = 0;
 };
 
+// cv2's computeResizeAreaTab (imgproc/src/resize.cpp, opencv 4.13 as installed with the reference): geometry in double,
+// one fp32 weight per (destination, source) pair; the sources of one destination index are consecutive.
+void area_axis_tab(int ssize, int dsize, std::vector<int>& ofs, std::vector<int>& cnt, std::vector<std::vector<float>>& al) {
+  const double scale = 1.0 / ((double)dsize / (double)ssize);
+  ofs.assign(dsize, 0);
+  cnt.assign(dsize, 0);
+  al.assign(dsize, {});
+  for (int dx = 0; dx < dsize; ++dx) {
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    const double cell = fmin(scale, (double)ssize - fsx1);
+    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+    if (sx2 > ssize - 1) sx2 = ssize - 1;
+    if (sx1 > sx2) sx1 = sx2;
+    int first = -1;
+    auto push = [&](int si, float a) {
+      if (first < 0) first = si;
+      al[dx].push_back(a);
+    };
+    if (sx1 - fsx1 > 1e-3) push(sx1 - 1, (float)((sx1 - fsx1) / cell));
+    for (int sx = sx1; sx < sx2; ++sx) push(sx, (float)(1.0 / cell));
+    if (fsx2 - sx2 > 1e-3) push(sx2, (float)(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell));
+    ofs[dx] = first < 0 ? 0 : first;
+    cnt[dx] = (int)al[dx].size();
+  }
+}
+
+// build (or reuse) the device tables for a W x H -> nw x nh non-integer INTER_AREA shrink
+int ensure_area_tabs(vd3d_ctx* ctx, int which, int W, int H, int nw, int nh, FitPlan& f) {
+  Buf& tab = ctx->area_tab[which];
+  int* key = ctx->at_key[which];
+  const bool have = key[0] == W && key[1] == H && key[2] == nw && key[3] == nh && tab.p;
+  if (!have) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx->stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return fail(ctx, VD3D_ERR_STATE, "INTER_AREA tables missing during capture");
+    std::vector<int> xo, xc, yo, yc;
+    std::vector<std::vector<float>> xa, ya;
+    area_axis_tab(W, nw, xo, xc, xa);
+    area_axis_tab(H, nh, yo, yc, ya);
+    int T = 1;
+    for (int c : xc) T = c > T ? c : T;
+    for (int c : yc) T = c > T ? c : T;
+    if (T > 64) return fail(ctx, VD3D_ERR_UNSUPPORTED, "INTER_AREA shrink factor too large");
+    const size_t nint = (size_t)2 * nw + (size_t)2 * nh, nflt = ((size_t)nw + nh) * T;
+    std::vector<unsigned char> host(nint * 4 + nflt * 4);
+    int* ip = (int*)host.data();
+    float* fp = (float*)(host.data() + nint * 4);
+    memcpy(ip, xo.data(), (size_t)nw * 4);
+    memcpy(ip + nw, xc.data(), (size_t)nw * 4);
+    memcpy(ip + 2 * nw, yo.data(), (size_t)nh * 4);
+    memcpy(ip + 2 * nw + nh, yc.data(), (size_t)nh * 4);
+    for (int i = 0; i < nw; ++i)
+      for (int k = 0; k < T; ++k) fp[(size_t)i * T + k] = k < xc[i] ? xa[i][k] : 0.f;
+    for (int i = 0; i < nh; ++i)
+      for (int k = 0; k < T; ++k) fp[((size_t)nw + i) * T + k] = k < yc[i] ? ya[i][k] : 0.f;
+    // frames already queued may still read the previous tables
+    CK(cudaStreamSynchronize(ctx->stream));
+    int r = ensure(ctx, tab, host.size());
+    if (r) return r;
+    CK(cudaMemcpy(tab.p, host.data(), host.size(), cudaMemcpyHostToDevice));
+    key[0] = W;
+    key[1] = H;
+    key[2] = nw;
+    key[3] = nh;
+    ctx->at_t[which] = T;
+  }
+  const int* ip = (const int*)tab.p;
+  f.xofs = ip;
+  f.xcnt = ip + nw;
+  f.yofs = ip + 2 * nw;
+  f.ycnt = ip + 2 * nw + nh;
+  f.xal = (const float*)(ip + 2 * nw + 2 * nh);
+  f.yal = f.xal + (size_t)nw * ctx->at_t[which];
+  f.area_t = ctx->at_t[which];
+  return VD3D_OK;
+}
+
 // eye fit: cv2.resize INTER_AREA (Half-SBS) or pad_to_aspect_ratio (core/render_3d.py:101-131,1409-1417)
-int plan_fit(vd3d_ctx* ctx, int fmt, int W, int H, int pw, int ph, FitPlan& f) {
+int plan_fit(vd3d_ctx* ctx, int fmt, int W, int H, int pw, int ph, FitPlan& f, int tab_slot = 0) {
   int nw, nh;
   if (fmt == VD3D_FMT_HALF_SBS) {
     nw = pw;
@@ -428,13 +514,34 @@ int plan_fit(vd3d_ctx* ctx, int fmt, int W, int H, int pw, int ph, FitPlan& f) {
     f.fit_y0 = (ph - nh) / 2;
   }
   if (nw <= 0 || nh <= 0) return fail(ctx, VD3D_ERR_ARG, "degenerate eye size");
-  if (W % nw != 0 || H % nh != 0)
-    return fail(ctx, VD3D_ERR_UNSUPPORTED, "eye fit needs a non-integer INTER_AREA factor");
   f.fit_w = nw;
   f.fit_h = nh;
-  f.sx = W / nw;
-  f.sy = H / nh;
-  return VD3D_OK;
+  if (W % nw == 0 && H % nh == 0) {  // identity or cv2's integer "area fast" path
+    f.sx = W / nw;
+    f.sy = H / nh;
+    return VD3D_OK;
+  }
+  if (nw > W || nh > H)  // cv2 switches INTER_AREA to a bilinear scheme when enlarging: not on the hot path
+    return fail(ctx, VD3D_ERR_UNSUPPORTED, "eye fit would enlarge the eye (INTER_AREA upscaling)");
+  f.sx = f.sy = 0;
+  return ensure_area_tabs(ctx, tab_slot, W, H, nw, nh, f);
+}
+
+void set_fit(PostArgs& pa, const FitPlan& fp) {
+  pa.fit_x0 = fp.fit_x0;
+  pa.fit_y0 = fp.fit_y0;
+  pa.fit_w = fp.fit_w;
+  pa.fit_h = fp.fit_h;
+  pa.sx = fp.sx;
+  pa.sy = fp.sy;
+  pa.inv_area = fp.sx > 0 ? (float)(1.0 / (double)(fp.sx * fp.sy)) : 1.f;
+  pa.xofs = fp.xofs;
+  pa.xcnt = fp.xcnt;
+  pa.xal = fp.xal;
+  pa.yofs = fp.yofs;
+  pa.ycnt = fp.ycnt;
+  pa.yal = fp.yal;
+  pa.area_t = fp.area_t;
 }
 
 int copy_in(vd3d_ctx* ctx, Buf& b, const void* src, size_t bytes, int mem, cudaStream_t s, const void** dev) {
@@ -527,7 +634,8 @@ void vd3d_destroy(vd3d_ctx* ctx) {
   cudaDeviceSynchronize();
   Buf* bufs[] = {&ctx->xs,    &ctx->ys,    &ctx->tdf,   &ctx->dn0,   &ctx->dn1,      &ctx->rgb_s,
                  &ctx->frameB, &ctx->d,     &ctx->shift, &ctx->e2,    &ctx->eyeL,     &ctx->eyeR,
-                 &ctx->eyeL2, &ctx->eyeR2, &ctx->in_rgbf, &ctx->in_depthf, &ctx->dof_kern};
+                 &ctx->eyeL2, &ctx->eyeR2, &ctx->in_rgbf, &ctx->in_depthf, &ctx->dof_kern,
+                 &ctx->area_tab[0], &ctx->area_tab[1]};
   for (Buf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (int i = 0; i < kSlots; ++i) {
@@ -716,7 +824,6 @@ int vd3d_plan_sizes(int src_w, int src_h, const vd3d_render_params* rp, vd3d_siz
   }
   int rw, rh, pw, ph, outw, outh, tew, teh;
   int fmt = rp->output_format;
-  if (fmt == VD3D_FMT_VR) return VD3D_ERR_UNSUPPORTED;
   if (rp->preserve_original_aspect) {
     // original_video_* default to the FIRST frame tensor's size (pre-crop) (core/render_3d.py:1087-1092)
     int ow = src_w, oh = src_h;
@@ -730,6 +837,8 @@ int vd3d_plan_sizes(int src_w, int src_h, const vd3d_render_params* rp, vd3d_siz
       pw = rw; ph = rh; outw = rw * 2; outh = rh;
     } else if (fmt == VD3D_FMT_HALF_SBS) {
       pw = rw / 2; ph = rh; outw = rw; outh = rh;
+    } else if (fmt == VD3D_FMT_VR) {  // core/render_3d.py:1104-1108
+      pw = 1440; ph = 1600; outw = 2880; outh = 1600;
     } else {
       pw = rw; ph = rh; outw = rw * 2; outh = rh;
     }
@@ -743,6 +852,8 @@ int vd3d_plan_sizes(int src_w, int src_h, const vd3d_render_params* rp, vd3d_siz
       pw = 1920; ph = 1080; outw = 3840; outh = 1080;
     } else if (fmt == VD3D_FMT_HALF_SBS) {
       pw = rw / 2; ph = rh; outw = rw; outh = rh;
+    } else if (fmt == VD3D_FMT_VR) {  // core/render_3d.py:1129-1133
+      pw = 1440; ph = 1600; outw = 2880; outh = 1600;
     } else {
       pw = rw; ph = rh; outw = rw * 2; outh = rh;
     }
@@ -953,13 +1064,7 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
   pa.fmt = rp->output_format;
   pa.per_eye_w = pl.per_eye_w;
   pa.per_eye_h = pl.per_eye_h;
-  pa.fit_x0 = fp.fit_x0;
-  pa.fit_y0 = fp.fit_y0;
-  pa.fit_w = fp.fit_w;
-  pa.fit_h = fp.fit_h;
-  pa.sx = fp.sx;
-  pa.sy = fp.sy;
-  pa.inv_area = (float)(1.0 / (double)(fp.sx * fp.sy));
+  set_fit(pa, fp);
   pa.out = out_d;
   if (rp->output_format == VD3D_FMT_ANAGLYPH || rp->output_format == VD3D_FMT_INTERLACED) {
     pa.out_w = pl.per_eye_w;
@@ -1438,11 +1543,15 @@ int vd3d_heal(vd3d_ctx* ctx, const float* warped, const float* original, const f
 // format_3d_output / generate_anaglyph_3d (core/render_3d.py:837-883) on two same-size u8 BGR eyes
 int vd3d_pack(vd3d_ctx* ctx, const uint8_t* left, const uint8_t* right, int h, int w, int fmt, uint8_t* dst, int mem) {
   if (!ctx || !left || !right || !dst || h < 1 || w < 1) return fail(ctx, VD3D_ERR_ARG, "bad argument");
-  if (fmt < VD3D_FMT_HALF_SBS || fmt > VD3D_FMT_INTERLACED) return fail(ctx, VD3D_ERR_UNSUPPORTED, "format");
+  if (fmt < VD3D_FMT_HALF_SBS || fmt > VD3D_FMT_VR) return fail(ctx, VD3D_ERR_UNSUPPORTED, "format");
+  // VR: format_3d_output resizes each eye to 1440x1600 (846-849); the render loop hands it eyes that already have that
+  // size (pad_to_aspect_ratio, 1415-1417), where cv2.resize is the identity.  Other sizes (INTER_LINEAR) are off-path.
+  if (fmt == VD3D_FMT_VR && (w != 1440 || h != 1600))
+    return fail(ctx, VD3D_ERR_UNSUPPORTED, "VR pack expects 1440x1600 eyes (pad_to_aspect_ratio output)");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   size_t bytes = (size_t)h * w * 3;
-  bool sbs = (fmt == VD3D_FMT_HALF_SBS || fmt == VD3D_FMT_FULL_SBS);
+  bool sbs = (fmt == VD3D_FMT_HALF_SBS || fmt == VD3D_FMT_FULL_SBS || fmt == VD3D_FMT_VR);
   size_t obytes = sbs ? bytes * 2 : bytes;
   const void *l_d, *r_d;
   int r;
@@ -1469,6 +1578,46 @@ int vd3d_pack(vd3d_ctx* ctx, const uint8_t* left, const uint8_t* right, int h, i
   pa.out = o_d;
   pa.out_w = sbs ? 2 * w : w;
   pa.out_h = h;
+  launch_post(pa, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(dst, o_d, obytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+
+// eye fit on one u8 BGR image: keep_aspect != 0 -> pad_to_aspect_ratio(image, target_w, target_h) with a black canvas
+// (core/render_3d.py:101-131); 0 -> cv2.resize(image, (target_w, target_h), interpolation=cv2.INTER_AREA) (1413-1414).
+// INTER_AREA shrinking only (identity, integer "area fast", or cv2's general ResizeArea_ tables).
+int vd3d_fit_eye(vd3d_ctx* ctx, const uint8_t* src, int h, int w, int target_w, int target_h, int keep_aspect,
+                 uint8_t* dst, int mem) {
+  if (!ctx || !src || !dst || h < 1 || w < 1 || target_w < 1 || target_h < 1) return fail(ctx, VD3D_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t bytes = (size_t)h * w * 3, obytes = (size_t)target_h * target_w * 3;
+  const void* s_d;
+  int r;
+  if ((r = copy_in(ctx, ctx->eyeL, src, bytes, mem, s, &s_d))) return r;
+  uint8_t* o_d = dst;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->out_dev[0], obytes))) return r;
+    o_d = (uint8_t*)ctx->out_dev[0].p;
+  }
+  FitPlan fp;
+  if ((r = plan_fit(ctx, keep_aspect ? VD3D_FMT_FULL_SBS : VD3D_FMT_HALF_SBS, w, h, target_w, target_h, fp, 1))) return r;
+  PostArgs pa;
+  memset(&pa, 0, sizeof pa);
+  pa.left = (const uint8_t*)s_d;
+  pa.right = (const uint8_t*)s_d;
+  pa.H = h;
+  pa.W = w;
+  pa.fmt = VD3D_FMT_INTERLACED;  // single-eye pass-through layout
+  pa.per_eye_w = target_w;
+  pa.per_eye_h = target_h;
+  set_fit(pa, fp);
+  pa.out = o_d;
+  pa.out_w = target_w;
+  pa.out_h = target_h;
   launch_post(pa, s);
   ctx->launches += 1;
   CK(cudaGetLastError());

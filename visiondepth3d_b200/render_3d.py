@@ -193,20 +193,29 @@ def heal_missing_pixels(warped_frame, warped_depth, original_frame, edge_mask, h
     return torch.from_numpy(out).to(warped_frame.device) if is_t else out
 
 
-def pad_to_aspect_ratio(image, target_width, target_height, bg_color=(0, 0, 0)):
-    """core/render_3d.py:101-131 (host helper kept for callers; the frame path fuses it)."""
-    import cv2
-    h, w = image.shape[:2]
-    ta, ca = target_width / target_height, w / h
-    if ca > ta:
-        nw, nh = target_width, int(target_width / ca)
-    else:
-        nh, nw = target_height, int(ca * target_height)
-    rs = cv2.resize(image, (nw, nh), interpolation=cv2.INTER_AREA)
-    out = np.full((target_height, target_width, 3), bg_color, dtype=np.uint8)
-    xo, yo = (target_width - nw) // 2, (target_height - nh) // 2
-    out[yo:yo + nh, xo:xo + nw] = rs
+def _fit_eye(image, target_width, target_height, keep_aspect):
+    ctx = _ctx()
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    assert img.ndim == 3 and img.shape[2] == 3, "expected a BGR u8 image"
+    h, w = img.shape[:2]
+    out = np.empty((int(target_height), int(target_width), 3), dtype=np.uint8)
+    ctx.check(ctx.lib.vd3d_fit_eye(ctx.h, img.ctypes.data, h, w, int(target_width), int(target_height),
+                                   int(bool(keep_aspect)), out.ctypes.data, _lib.MEM_HOST))
     return out
+
+
+def pad_to_aspect_ratio(image, target_width, target_height, bg_color=(0, 0, 0)):
+    """core/render_3d.py:101-131 on the GPU (vd3d_fit_eye): aspect-preserving cv2 INTER_AREA shrink (identity, integer
+    or fractional factors) centred on a black canvas.  Enlarging fits raise (cv2 changes algorithm there)."""
+    if tuple(int(c) for c in bg_color) != (0, 0, 0):
+        raise NotImplementedError("pad_to_aspect_ratio: only the black canvas the render loop uses is supported")
+    return _fit_eye(image, target_width, target_height, True)
+
+
+def resize_area(image, width, height):
+    """cv2.resize(image, (width, height), interpolation=cv2.INTER_AREA) as in the Half-SBS eye fit
+    (core/render_3d.py:1413-1414), shrinking only."""
+    return _fit_eye(image, width, height, False)
 
 
 def _pack(left, right, fmt):
@@ -217,7 +226,7 @@ def _pack(left, right, fmt):
     assert l.shape == r.shape and l.ndim == 3 and l.shape[2] == 3, "Shape mismatch"
     h, w = l.shape[:2]
     code = _lib.FMT[fmt]
-    out = np.empty((h, 2 * w, 3) if code in (0, 1) else (h, w, 3), dtype=np.uint8)
+    out = np.empty((h, 2 * w, 3) if code in (0, 1, 4) else (h, w, 3), dtype=np.uint8)
     ctx.check(ctx.lib.vd3d_pack(ctx.h, l.ctypes.data, r.ctypes.data, h, w, code, out.ctypes.data, _lib.MEM_HOST))
     return out
 
@@ -229,9 +238,10 @@ def generate_anaglyph_3d(left_frame, right_frame):
 
 def format_3d_output(left, right, fmt):
     """core/render_3d.py:837-860."""
-    if fmt == "VR":
-        raise NotImplementedError("VR (1440x1600 INTER_LINEAR) is outside the B200 hot path")
-    if fmt not in ("Half-SBS", "Full-SBS", "Red-Cyan Anaglyph", "Passive Interlaced"):
+    if fmt == "VR" and tuple(left.shape[:2]) != (1600, 1440):
+        # the render loop always hands 1440x1600 eyes (pad_to_aspect_ratio) where the reference's cv2.resize is the identity
+        raise NotImplementedError("VR pack of eyes that are not 1440x1600 (cv2 INTER_LINEAR resize) is outside the hot path")
+    if fmt not in ("Half-SBS", "Full-SBS", "Red-Cyan Anaglyph", "Passive Interlaced", "VR"):
         fmt = "Half-SBS"  # the reference falls back to hstack (860)
     return _pack(left, right, fmt)
 
