@@ -374,20 +374,25 @@ int vd3d_gemm_bench(vd3d_depth* e, int M, int N, int K, int variant, int dbg, in
   CUtensorMap ma, mb;
   if ((r = make_map(e, &ma, da, K, M, 1, K, (uint64_t)K * M, 128, 1))) return r;
   if ((r = make_map(e, &mb, db, K, N, 1, K, (uint64_t)K * N, variant >= 20 ? 64 : 128, 1))) return r;
-  cudaEvent_t e0, e1;
-  DCK(cudaEventCreate(&e0));
-  DCK(cudaEventCreate(&e1));
-  for (int i = 0; i < 3 + iters; ++i) {
-    if (i == 3) DCK(cudaEventRecord(e0, e->stream));
-    cudaError_t ce = launch_gemm_variant(variant, ma, mb, g, (M + 127) / 128, 1, e->stream);
-    if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("gemm bench launch: ") + cudaGetErrorString(ce));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto done = [&](int rc) {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+  };
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
+    return done(dfail(e, VD3D_ERR_CUDA, "gemm bench: event creation failed"));
+  cudaError_t ce = cudaSuccess;
+  for (int i = 0; i < 3 + iters && ce == cudaSuccess; ++i) {
+    if (i == 3) ce = cudaEventRecord(e0, e->stream);
+    if (ce == cudaSuccess) ce = launch_gemm_variant(variant, ma, mb, g, (M + 127) / 128, 1, e->stream);
   }
-  DCK(cudaEventRecord(e1, e->stream));
-  DCK(cudaEventSynchronize(e1));
+  if (ce == cudaSuccess) ce = cudaEventRecord(e1, e->stream);
+  if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
   float ms = 0.f;
-  DCK(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
+  if (ce != cudaSuccess) return done(dfail(e, VD3D_ERR_CUDA, std::string("gemm bench: ") + cudaGetErrorString(ce)));
+  done(0);
   *ms_out = ms / iters;
   return VD3D_OK;
 }
