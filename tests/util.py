@@ -42,3 +42,12 @@ LOOP_CASES = {
 # VR fixture (tools/gen_golden.py vr): 2880x1600 frames, stored as every 3rd row/column of the image band + sha256
 VR_CASE = dict(file="loop_vr_320x180.npz", sw=320, sh=180, n=3, kind="smooth",
                rp=dict(_BASE, output_width=1600, output_height=900, output_format="VR"))
+
+# Extra loop fixtures (tools/gen_golden.py extra): crop / aspect / fractional-fit branches of render_sbs_3d.
+# Oracle-vs-reference only (CPU); the CUDA path is compared with the oracle on the same branches in test_dibr_gpu.py.
+LOOP_CASES_EXTRA = {
+    "loop_crop43_320x240.npz": dict(sw=320, sh=240, n=3, kind="smooth", rp=dict(_BASE)),
+    "loop_scope239_320x180.npz": dict(sw=320, sh=180, n=3, kind="smooth", rp=dict(_BASE, aspect_ratio=2.39)),
+    "loop_halfsbs_odd_321x180.npz": dict(sw=321, sh=180, n=3, kind="smooth",
+                                         rp=dict(_BASE, preserve_original_aspect=True)),
+}

@@ -103,7 +103,7 @@ def run_loop(r3d, torch, cv2, src_w, src_h, n_frames, kind, rp):
     try:
         r3d.render_sbs_3d(
             "rgb", "depth", "out.avi", "XVID", 24.0, rp["output_width"], rp["output_height"],
-            4.5, -1.5, -6.0, rp["sharpness_factor"], rp["output_format"], Var("Default (16:9)"),
+            4.5, -1.5, -6.0, rp["sharpness_factor"], rp["output_format"], Var(rp.get("aspect_name", "Default (16:9)")),
             r3d.aspect_ratios, rp["dof_strength"],
             feather_strength=rp["feather_strength"], blur_ksize=rp["blur_ksize"],
             use_subject_tracking=rp["use_subject_tracking"],
@@ -216,8 +216,38 @@ def gen_vr():
     print(p, os.path.getsize(p), {k: v.shape for k, v in out.items() if k.endswith("_band")})
 
 
+def gen_extra():
+    """I-K. loop cases that pin the crop / aspect / fractional-fit branches of render_sbs_3d
+    (`python tools/gen_golden.py extra`; the earlier fixtures stay byte-identical)."""
+    mods = refshim.load_reference(("render_3d",))
+    r3d = mods["render_3d"]
+    import cv2
+    import torch
+    import torchvision
+    torch.set_num_threads(os.cpu_count())
+    meta = dict(torch=torch.__version__, torchvision=torchvision.__version__, cv2=cv2.__version__,
+                numpy=np.__version__)
+    base = dict(output_width=320, output_height=180, sharpness_factor=0.2, output_format="Half-SBS",
+                dof_strength=0.0, feather_strength=10.0, blur_ksize=9, use_subject_tracking=True,
+                use_floating_window=True, preserve_original_aspect=False, zero_parallax_strength=0.01)
+    # I. 4:3 source against the 16:9 target: centre crop of the height (1244-1248)
+    g = run_loop(r3d, torch, cv2, 320, 240, 3, "smooth", base)
+    np.savez_compressed(os.path.join(OUT, "loop_crop43_320x240.npz"), **g, **meta)
+    # J. CinemaScope 2.39:1 target on a 16:9 source: crop + 430x180 warp + 215x180 eyes
+    g = run_loop(r3d, torch, cv2, 320, 180, 3, "smooth", dict(base, aspect_name="CinemaScope (2.39:1)"))
+    np.savez_compressed(os.path.join(OUT, "loop_scope239_320x180.npz"), **g, **meta)
+    # K. preserve_original_aspect with an odd width: 321 -> 160 per eye = fractional INTER_AREA (x2.00625)
+    g = run_loop(r3d, torch, cv2, 321, 180, 3, "smooth", dict(base, preserve_original_aspect=True))
+    np.savez_compressed(os.path.join(OUT, "loop_halfsbs_odd_321x180.npz"), **g, **meta)
+    for f in ("loop_crop43_320x240.npz", "loop_scope239_320x180.npz", "loop_halfsbs_odd_321x180.npz"):
+        z = np.load(os.path.join(OUT, f))
+        print(f, os.path.getsize(os.path.join(OUT, f)), {k: z[k].shape for k in z.files if k.startswith("final")})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "vr":
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        gen_extra()
+    elif len(sys.argv) > 1 and sys.argv[1] == "vr":
         gen_vr()
     else:
         main()
