@@ -50,4 +50,11 @@ LOOP_CASES_EXTRA = {
     "loop_scope239_320x180.npz": dict(sw=320, sh=180, n=3, kind="smooth", rp=dict(_BASE, aspect_ratio=2.39)),
     "loop_halfsbs_odd_321x180.npz": dict(sw=321, sh=180, n=3, kind="smooth",
                                          rp=dict(_BASE, preserve_original_aspect=True)),
+    # the reference was ALSO given parallax_balance=0.6, depth_pop_gamma=0.7, fg_pop_multiplier=1.4 here: render_sbs_3d
+    # accepts them but does not forward them to pixel_shift_cuda, so they must not change the output
+    "loop_controls_320x180.npz": dict(
+        sw=320, sh=180, n=4, kind="smooth",
+        rp=dict(_BASE, sharpness_factor=0.0, ipd_factor=0.8, convergence_strength=0.3,
+                enable_dynamic_convergence=False, enable_edge_masking=False)),
+    "loop_dof_halfsbs_320x180.npz": dict(sw=320, sh=180, n=3, kind="smooth", rp=dict(_BASE, dof_strength=1.5)),
 }

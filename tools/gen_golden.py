@@ -115,6 +115,9 @@ def run_loop(r3d, torch, cv2, src_w, src_h, n_frames, kind, rp):
             color_saturation=rp.get("color_saturation", 1.0),
             color_contrast=rp.get("color_contrast", 1.0),
             color_brightness=rp.get("color_brightness", 0.0),
+            **{k: rp[k] for k in ("enable_edge_masking", "enable_feathering",
+                                  "convergence_strength", "enable_dynamic_convergence", "ipd_factor",
+                                  "parallax_balance", "depth_pop_gamma", "fg_pop_multiplier") if k in rp},
         )
     finally:
         cv2.VideoCapture, cv2.VideoWriter = real_cap, real_wr
@@ -239,7 +242,18 @@ def gen_extra():
     # K. preserve_original_aspect with an odd width: 321 -> 160 per eye = fractional INTER_AREA (x2.00625)
     g = run_loop(r3d, torch, cv2, 321, 180, 3, "smooth", dict(base, preserve_original_aspect=True))
     np.savez_compressed(os.path.join(OUT, "loop_halfsbs_odd_321x180.npz"), **g, **meta)
-    for f in ("loop_crop43_320x240.npz", "loop_scope239_320x180.npz", "loop_halfsbs_odd_321x180.npz"):
+    # L. the remaining loop-level controls: IPD factor, fixed convergence, edge masking off, sharpness factor 0 (still a
+    #    5/-1 kernel), and the parallax/pop controls the loop accepts but does not forward to pixel_shift_cuda
+    g = run_loop(r3d, torch, cv2, 320, 180, 4, "smooth",
+                 dict(base, sharpness_factor=0.0, ipd_factor=0.8, convergence_strength=0.3,
+                      enable_dynamic_convergence=False, enable_edge_masking=False, parallax_balance=0.6,
+                      depth_pop_gamma=0.7, fg_pop_multiplier=1.4))
+    np.savez_compressed(os.path.join(OUT, "loop_controls_320x180.npz"), **g, **meta)
+    # M. DOF on the Half-SBS path: the normalised depth (160x90) is upsampled to the eye size for apply_dof_cuda
+    g = run_loop(r3d, torch, cv2, 320, 180, 3, "smooth", dict(base, dof_strength=1.5))
+    np.savez_compressed(os.path.join(OUT, "loop_dof_halfsbs_320x180.npz"), **g, **meta)
+    for f in ("loop_crop43_320x240.npz", "loop_scope239_320x180.npz", "loop_halfsbs_odd_321x180.npz",
+              "loop_controls_320x180.npz", "loop_dof_halfsbs_320x180.npz"):
         z = np.load(os.path.join(OUT, f))
         print(f, os.path.getsize(os.path.join(OUT, f)), {k: z[k].shape for k in z.files if k.startswith("final")})
 
