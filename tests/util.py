@@ -20,6 +20,17 @@ PS_CASES = {
                                          use_subject_tracking=False)),
 }
 
+# oracle-vs-reference only for now (CPU); add to the GPU golden test once run on a B200
+PS_CASES_EXTRA = {
+    # tools/gen_golden.py extra: every shaping / balance control of pixel_shift_cuda off its default
+    "ps_controls_256x144.npz": dict(w=256, h=144, iw=256, ih=144, n=2, kind="smooth",
+                                    kw=dict(blur_ksize=5, feather_strength=20.0, convergence_strength=0.3,
+                                            enable_dynamic_convergence=False, depth_pop_gamma=0.7, depth_pop_mid=0.4,
+                                            depth_stretch_lo=0.1, depth_stretch_hi=0.9, fg_pop_multiplier=1.5,
+                                            bg_push_multiplier=0.9, subject_lock_strength=0.5, parallax_balance=0.6,
+                                            max_pixel_shift_percent=0.03, zero_parallax_strength=0.02)),
+}
+
 _BASE = dict(output_width=320, output_height=180, sharpness_factor=0.2, output_format="Half-SBS",
              dof_strength=0.0, feather_strength=10.0, blur_ksize=9, use_subject_tracking=True,
              use_floating_window=True, preserve_original_aspect=False, zero_parallax_strength=0.01)

@@ -252,6 +252,14 @@ def gen_extra():
     # M. DOF on the Half-SBS path: the normalised depth (160x90) is upsampled to the eye size for apply_dof_cuda
     g = run_loop(r3d, torch, cv2, 320, 180, 3, "smooth", dict(base, dof_strength=1.5))
     np.savez_compressed(os.path.join(OUT, "loop_dof_halfsbs_320x180.npz"), **g, **meta)
+    # N. pixel_shift_cuda with every shaping / balance control off its default (the preview path passes them)
+    g = run_pixel_shift(r3d, torch, 256, 144, 256, 144, 2, "smooth",
+                        blur_ksize=5, feather_strength=20.0, convergence_strength=0.3, enable_dynamic_convergence=False,
+                        depth_pop_gamma=0.7, depth_pop_mid=0.4, depth_stretch_lo=0.1, depth_stretch_hi=0.9,
+                        fg_pop_multiplier=1.5, bg_push_multiplier=0.9, subject_lock_strength=0.5,
+                        parallax_balance=0.6, max_pixel_shift_percent=0.03, zero_parallax_strength=0.02)
+    np.savez_compressed(os.path.join(OUT, "ps_controls_256x144.npz"), **g, **meta)
+    print("ps_controls_256x144.npz", os.path.getsize(os.path.join(OUT, "ps_controls_256x144.npz")))
     for f in ("loop_crop43_320x240.npz", "loop_scope239_320x180.npz", "loop_halfsbs_odd_321x180.npz",
               "loop_controls_320x180.npz", "loop_dof_halfsbs_320x180.npz"):
         z = np.load(os.path.join(OUT, f))
