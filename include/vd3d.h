@@ -206,6 +206,9 @@ int vd3d_heal(vd3d_ctx* ctx, const float* warped, const float* original, const f
  * factors, or cv2's general (fractional) area tables; enlarging returns VD3D_ERR_UNSUPPORTED */
 int vd3d_fit_eye(vd3d_ctx* ctx, const uint8_t* src, int h, int w, int target_w, int target_h, int keep_aspect,
                  uint8_t* dst, int mem);
+/* host-only test hook (no GPU needed): the cv2 area-resize tables vd3d_fit_eye / the frame path build for a
+ * ssize -> dsize shrink; ofs/cnt [dsize], alpha [dsize*cap]; returns the largest tap count or a negative error */
+int vd3d_area_table(int ssize, int dsize, int* ofs, int* cnt, float* alpha, int cap);
 /* format_3d_output / generate_anaglyph_3d (837-883) on two same-size u8 BGR eyes [h,w,3]:
  * SBS -> [h,2w,3]; anaglyph / interlaced -> [h,w,3] */
 int vd3d_pack(vd3d_ctx* ctx, const uint8_t* left, const uint8_t* right, int h, int w, int fmt, uint8_t* dst, int mem);

@@ -52,7 +52,20 @@ def test_plan_sizes_matches_oracle(lib):
         (2048, 858, dict(output_height=858, output_format="Half-SBS", aspect_ratio=2.39)),
         (1440, 1080, dict(output_height=1080, output_format="Half-SBS")),  # 4:3 source, 16:9 target -> crop
         (1920, 800, dict(output_height=1080, output_format="Half-SBS")),   # wide source -> crop width
+        (1920, 1080, dict(output_height=1080, output_format="VR")),        # 2 x 1440x1600 (core/render_3d.py:1129-1133)
+        (1920, 1080, dict(output_format="VR", preserve_original_aspect=True)),
+        (321, 180, dict(output_format="Half-SBS", preserve_original_aspect=True)),  # odd width -> 160 per eye
     ]
+    # seeded sweep over sources, heights, aspects, formats and both sizing modes
+    import random
+    rnd = random.Random(5)
+    ratios = [16 / 9, 2.39, 21 / 9, 4 / 3, 1.0, 2.35, 2.76]
+    fmts = ["Half-SBS", "Full-SBS", "VR", "Red-Cyan Anaglyph", "Passive Interlaced"]
+    for _ in range(300):
+        sw, sh = rnd.randrange(64, 4097), rnd.randrange(64, 2305)
+        cases.append((sw, sh, dict(output_width=rnd.randrange(64, 4097), output_height=rnd.randrange(64, 2305),
+                                   output_format=rnd.choice(fmts), aspect_ratio=rnd.choice(ratios),
+                                   preserve_original_aspect=rnd.random() < 0.5)))
     for sw, sh, kw in cases:
         orp = O.RenderParams(**kw)
         rp = R.make_render_params(orp.output_width, orp.output_height, 4.5, -1.5, -6.0, 0.2, orp.output_format,
@@ -63,6 +76,28 @@ def test_plan_sizes_matches_oracle(lib):
         exp = (op.crop_x0, op.crop_y0, op.crop_w, op.crop_h, op.target_eye_w, op.target_eye_h, op.resized_width,
                op.resized_height, op.per_eye_w, op.per_eye_h, op.out_width, op.out_height)
         assert got == exp, (sw, sh, kw)
+
+
+def test_area_tables_match_cv2_restatement(lib):
+    """Host half of the fractional INTER_AREA fit: the C tables equal the oracle's, which reproduce cv2.resize exactly
+    (tests/test_oracle_golden.py::test_inter_area_matches_cv2)."""
+    import numpy as np
+    from oracle.dibr import area_tab
+    for ss, ds in ((1920, 1440), (1080, 810), (1600, 1440), (640, 427), (1000, 333), (800, 799), (48, 47), (3840, 1440),
+                   (321, 160), (96, 96), (96, 48)):
+        cap = 16
+        ofs = np.zeros(ds, np.int32)
+        cnt = np.zeros(ds, np.int32)
+        al = np.zeros((ds, cap), np.float32)
+        T = lib.vd3d_area_table(ss, ds, ofs.ctypes.data_as(C.POINTER(C.c_int)), cnt.ctypes.data_as(C.POINTER(C.c_int)),
+                                al.ctypes.data_as(C.POINTER(C.c_float)), cap)
+        tab = area_tab(ss, ds)
+        assert T == max(len(e) for e in tab)
+        for dx, ent in enumerate(tab):
+            assert cnt[dx] == len(ent) and ofs[dx] == ent[0][0], (ss, ds, dx)
+            assert [e[0] for e in ent] == list(range(ofs[dx], ofs[dx] + cnt[dx]))  # consecutive sources
+            assert np.array_equal(al[dx, :cnt[dx]], np.array([e[1] for e in ent], np.float32)), (ss, ds, dx)
+    assert lib.vd3d_area_table(10, 20, None, None, None, 4) < 0  # enlarging is not an area shrink
 
 
 def test_create_fails_loudly_without_gpu(lib):

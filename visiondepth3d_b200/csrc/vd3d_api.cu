@@ -1626,6 +1626,24 @@ int vd3d_fit_eye(vd3d_ctx* ctx, const uint8_t* src, int h, int w, int target_w, 
   return VD3D_OK;
 }
 
+// host-only test hook: the cv2 computeResizeAreaTab restatement used by the fractional INTER_AREA fit.
+// ofs/cnt [dsize], alpha [dsize * cap] (zero padded); returns the largest tap count, or a negative error.
+int vd3d_area_table(int ssize, int dsize, int* ofs, int* cnt, float* alpha, int cap) {
+  if (ssize < 1 || dsize < 1 || dsize > ssize || !ofs || !cnt || !alpha || cap < 1) return VD3D_ERR_ARG;
+  std::vector<int> o, c;
+  std::vector<std::vector<float>> a;
+  area_axis_tab(ssize, dsize, o, c, a);
+  int T = 0;
+  for (int i = 0; i < dsize; ++i) {
+    if (c[i] > cap) return VD3D_ERR_ARG;
+    T = c[i] > T ? c[i] : T;
+    ofs[i] = o[i];
+    cnt[i] = c[i];
+    for (int k = 0; k < cap; ++k) alpha[(size_t)i * cap + k] = k < c[i] ? a[i][k] : 0.f;
+  }
+  return T;
+}
+
 int vd3d_dof_grade(vd3d_ctx* ctx, const uint8_t* eye_bgr, int h, int w, const float* depth01, int dh, int dw,
                    double focal, double max_sigma, double sat, double con, double bri, uint8_t* dst, int mem) {
   if (!ctx || !eye_bgr || !dst || h < 2 || w < 2) return fail(ctx, VD3D_ERR_ARG, "bad argument");
