@@ -632,19 +632,59 @@ def area_tab(ssize: int, dsize: int):
     return tab
 
 
+def _area_linear_tab(ssize: int, dsize: int):
+    """cv2 resize(): coefficient table of the bilinear scheme INTER_AREA falls back to when an axis is enlarged
+    ("area_mode" branch of the generic path): source index and two 11-bit fixed-point weights per destination."""
+    import math
+    scale = 1.0 / (dsize / ssize)
+    inv = dsize / ssize
+    ofs = np.zeros(dsize, dtype=np.int64)
+    a = np.zeros((dsize, 2), dtype=np.int64)
+    for dx in range(dsize):
+        sx = math.floor(dx * scale)
+        fx = f32((dx + 1) - (sx + 1) * inv)
+        fx = f32(0) if fx <= 0 else f32(fx - math.floor(fx))
+        if sx < 0:
+            fx, sx = f32(0), 0
+        if sx >= ssize - 1:
+            fx, sx = f32(0), ssize - 1
+        a[dx, 0] = int(np.rint(f32(f32(f32(1.0) - fx) * f32(2048))))  # saturate_cast<short>(c * INTER_RESIZE_COEF_SCALE)
+        a[dx, 1] = int(np.rint(f32(fx * f32(2048))))
+        ofs[dx] = sx
+    return ofs, a
+
+
+def _resize_area_enlarge(img: np.ndarray, ow: int, oh: int) -> np.ndarray:
+    """cv2.resize(INTER_AREA) when at least one axis grows: fixed-point bilinear with area-style coefficients
+    (HResizeLinear int rows, VResizeLinear<uchar,int,short>: ((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2)."""
+    h, w = img.shape[:2]
+    xo, xa = _area_linear_tab(w, ow)
+    yo, ya = _area_linear_tab(h, oh)
+    S = img.astype(np.int64)
+    x1 = np.minimum(xo + 1, w - 1)
+    rows = S[:, xo, :] * xa[None, :, 0, None] + S[:, x1, :] * xa[None, :, 1, None]
+    y1 = np.minimum(yo + 1, h - 1)
+    b0, b1 = ya[:, 0][:, None, None], ya[:, 1][:, None, None]
+    out = (((b0 * (rows[yo] >> 4)) >> 16) + ((b1 * (rows[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 def resize_area(img: np.ndarray, ow: int, oh: int) -> np.ndarray:
-    """cv2.resize(img, (ow, oh), interpolation=cv2.INTER_AREA) for shrinking (both scales >= 1), as called by
-    pad_to_aspect_ratio / the Half-SBS eye fit (core/render_3d.py:121, 1413-1414).  Identity -> copy; integer factors
-    on both axes -> cv2's "area fast" path (resize_area_int); otherwise cv2's ResizeArea_: per source row
-    buf[dx] = sum_k S[sx_k] * alpha_k (fp32, separate multiply and add, table order), rows combined as
-    sum = beta_0 * buf_0 (+ beta_j * buf_j ...) in fp32, saturate_cast<uchar> = round-half-even.
-    Pinned against the real cv2.resize in tests/test_oracle_golden.py (exact)."""
+    """cv2.resize(img, (ow, oh), interpolation=cv2.INTER_AREA) as called by pad_to_aspect_ratio / the Half-SBS eye fit
+    (core/render_3d.py:121, 1413-1414).  Identity -> copy; integer factors on both axes -> cv2's "area fast" path
+    (resize_area_int); both axes shrinking -> cv2's ResizeArea_: per source row buf[dx] = sum_k S[sx_k] * alpha_k
+    (fp32, separate multiply and add, table order), rows combined as sum = beta_0 * buf_0 (+ beta_j * buf_j ...) in
+    fp32, saturate_cast<uchar> = round-half-even; any axis enlarging -> cv2's fixed-point bilinear emulation
+    (_resize_area_enlarge; e.g. 1280x720 eyes into the hard-coded 1920x1080 Full-SBS canvas, core/render_3d.py:1121).
+    Every branch is pinned against the real cv2.resize in tests/test_oracle_golden.py (exact)."""
     h, w = img.shape[:2]
     if (w, h) == (ow, oh):
         return img.copy()
     if w % ow == 0 and h % oh == 0:
         return resize_area_int(img, ow, oh)
-    assert ow <= w and oh <= h, "oracle covers INTER_AREA shrinking only (cv2 switches to a bilinear scheme when enlarging)"
+    if ow > w or oh > h:
+        assert img.ndim == 3, "enlarging branch restated for BGR images"
+        return _resize_area_enlarge(img, ow, oh)
     squeeze = img.ndim == 2
     S = (img[..., None] if squeeze else img).astype(f32)
     xt, yt = area_tab(w, ow), area_tab(h, oh)
