@@ -209,6 +209,8 @@ int vd3d_fit_eye(vd3d_ctx* ctx, const uint8_t* src, int h, int w, int target_w, 
 /* host-only test hook (no GPU needed): the cv2 area-resize tables vd3d_fit_eye / the frame path build for a
  * ssize -> dsize shrink; ofs/cnt [dsize], alpha [dsize*cap]; returns the largest tap count or a negative error */
 int vd3d_area_table(int ssize, int dsize, int* ofs, int* cnt, float* alpha, int cap);
+/* same for the enlarging case (cv2 emulates INTER_AREA with fixed-point bilinear weights): ofs [dsize], a01 [2*dsize] */
+int vd3d_area_linear_table(int ssize, int dsize, int* ofs, int* a01);
 /* format_3d_output / generate_anaglyph_3d (837-883) on two same-size u8 BGR eyes [h,w,3]:
  * SBS -> [h,2w,3]; anaglyph / interlaced -> [h,w,3] */
 int vd3d_pack(vd3d_ctx* ctx, const uint8_t* left, const uint8_t* right, int h, int w, int fmt, uint8_t* dst, int mem);

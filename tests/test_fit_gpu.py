@@ -33,6 +33,7 @@ def test_fit_eye_matches_oracle(R, case):
         assert np.array_equal(R.resize_area(img, tw, th), O.resize_area(img, tw, th)), case
 
 
+@pytest.mark.skipif(os.environ.get("VD3D_FIT_ENLARGE") == "1", reason="enlarging enabled")
 def test_fit_eye_rejects_enlarging(R):
     from visiondepth3d_b200._lib import Vd3dError
     img = np.zeros((90, 160, 3), dtype=np.uint8)
@@ -40,6 +41,18 @@ def test_fit_eye_rejects_enlarging(R):
         R.pad_to_aspect_ratio(img, 1440, 1600)  # cv2 switches INTER_AREA to a bilinear scheme when enlarging
     # the context stays usable
     assert R.pad_to_aspect_ratio(img, 160, 90).shape == (90, 160, 3)
+
+
+@pytest.mark.skipif(os.environ.get("VD3D_FIT_ENLARGE") != "1",
+                    reason="enlarging fits are opt-in until this test has been run on a B200 (DESIGN.md section 9)")
+@pytest.mark.parametrize("case", [(1280, 720, 1920, 1080), (160, 90, 1440, 1600), (100, 70, 133, 91), (100, 70, 80, 140)])
+def test_fit_eye_enlarge_matches_oracle(R, case):
+    """cv2 INTER_AREA with an enlarged axis = fixed-point bilinear emulation; integer arithmetic, exact."""
+    w, h, tw, th = case
+    rng = np.random.default_rng(w * 17 + th)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    assert np.array_equal(R.pad_to_aspect_ratio(img, tw, th), O.pad_to_aspect(img, tw, th)), case
+    assert np.array_equal(R.resize_area(img, tw, th), O.resize_area(img, tw, th)), case
 
 
 def test_vr_loop_vs_oracle_and_golden(R, golden_dir):

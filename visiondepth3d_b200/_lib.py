@@ -81,7 +81,7 @@ SYMBOLS = [
     "vd3d_create", "vd3d_destroy", "vd3d_last_error", "vd3d_reset_state", "vd3d_host_alloc",
     "vd3d_host_free", "vd3d_stream", "vd3d_sync", "vd3d_launch_count", "vd3d_set_graphs",
     "vd3d_pixel_shift", "vd3d_plan_sizes", "vd3d_render_frame", "vd3d_render_clip",
-    "vd3d_sharpen", "vd3d_dof_grade", "vd3d_struct_size", "vd3d_pack", "vd3d_fit_eye", "vd3d_area_table", "vd3d_heal",
+    "vd3d_sharpen", "vd3d_dof_grade", "vd3d_struct_size", "vd3d_pack", "vd3d_fit_eye", "vd3d_area_table", "vd3d_area_linear_table", "vd3d_heal",
     "vd3d_profile", "vd3d_profile_collect",
     # depth forward (bound in depth_engine.py)
     "vd3d_depth_create", "vd3d_depth_destroy", "vd3d_depth_last_error", "vd3d_depth_launch_count",
@@ -156,6 +156,8 @@ def load():
     lib.vd3d_fit_eye.restype = i
     lib.vd3d_area_table.argtypes = [i, i, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float), i]
     lib.vd3d_area_table.restype = i
+    lib.vd3d_area_linear_table.argtypes = [i, i, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.vd3d_area_linear_table.restype = i
     lib.vd3d_advance_state.argtypes = [vp, u8p, u8p, i, i, i, C.POINTER(RenderParams), i]
     lib.vd3d_advance_state.restype = i
     lib.vd3d_state_bytes.argtypes = [vp]

@@ -1129,6 +1129,18 @@ __device__ __forceinline__ int fitted_px(const PostArgs& a, const uint8_t* eye, 
                                          int bar_hi) {
   int fx = ex - a.fit_x0, fy = ey - a.fit_y0;
   if (fx < 0 || fy < 0 || fx >= a.fit_w || fy >= a.fit_h) return 0;  // pad_to_aspect_ratio canvas
+  if (a.lin) {
+    // cv2 resize(INTER_AREA) with an enlarged axis: HResizeLinear on int rows, then VResizeLinear<uchar, int, short>
+    const int sx0 = a.xofs[fx], sx1 = min(sx0 + 1, a.W - 1), sy0 = a.yofs[fy], sy1 = min(sy0 + 1, a.H - 1);
+    const int a0 = (int)a.xal[2 * fx], a1 = (int)a.xal[2 * fx + 1];
+    const int b0 = (int)a.yal[2 * fy], b1 = (int)a.yal[2 * fy + 1];
+    const int r0 = sharp_px(eye, a.H, a.W, sy0, sx0, ch, bar_lo, bar_hi, a.kc, a.ke, a.sharpen) * a0 +
+                   sharp_px(eye, a.H, a.W, sy0, sx1, ch, bar_lo, bar_hi, a.kc, a.ke, a.sharpen) * a1;
+    const int r1 = sharp_px(eye, a.H, a.W, sy1, sx0, ch, bar_lo, bar_hi, a.kc, a.ke, a.sharpen) * a0 +
+                   sharp_px(eye, a.H, a.W, sy1, sx1, ch, bar_lo, bar_hi, a.kc, a.ke, a.sharpen) * a1;
+    const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+    return min(max(v, 0), 255);
+  }
   if (a.xal) {
     // cv2 ResizeArea_ (non-integer INTER_AREA shrink): per source row buf = sum_k S * alpha_k, rows combined as
     // sum = beta_0 * buf_0 + beta_1 * buf_1 ... ; fp32, separate multiply and add (this unit is built with -fmad=false)

@@ -92,6 +92,9 @@ struct PostArgs {
   const int* ycnt;
   const float* yal;
   int area_t;
+  // lin != 0: cv2's INTER_AREA emulation when an axis is enlarged (fixed-point bilinear): xofs/yofs = first source
+  // index, xal/yal = the two 11-bit weights per index stored as floats (exact integers), area_t == 2
+  int lin;
   uint8_t* out;
   int out_w, out_h;
 };

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -414,6 +415,7 @@ struct FitPlan {
   const int *xofs = nullptr, *xcnt = nullptr, *yofs = nullptr, *ycnt = nullptr;
   const float *xal = nullptr, *yal = nullptr;
   int area_t = 0;
+  int lin = 0;  // enlarged axis: cv2's fixed-point bilinear emulation of INTER_AREA (opt-in, see plan_fit)
 };
 
 // cv2's computeResizeAreaTab (imgproc/src/resize.cpp, opencv 4.13 as installed with the reference): geometry in double,
@@ -442,8 +444,33 @@ void area_axis_tab(int ssize, int dsize, std::vector<int>& ofs, std::vector<int>
   }
 }
 
+// cv2 resize(): the "area_mode" coefficients of the bilinear scheme INTER_AREA falls back to when an axis grows
+// (generic path of imgproc/src/resize.cpp): source index + two weights, saturate_cast<short>(c * 2048)
+void area_linear_tab(int ssize, int dsize, std::vector<int>& ofs, std::vector<int>& a01) {
+  const double inv = (double)dsize / (double)ssize, scale = 1.0 / inv;
+  ofs.assign(dsize, 0);
+  a01.assign((size_t)2 * dsize, 0);
+  for (int dx = 0; dx < dsize; ++dx) {
+    int sx = (int)floor(dx * scale);
+    float fx = (float)((dx + 1) - (sx + 1) * inv);
+    fx = fx <= 0 ? 0.f : fx - floorf(fx);
+    if (sx < 0) {
+      fx = 0.f;
+      sx = 0;
+    }
+    if (sx >= ssize - 1) {
+      fx = 0.f;
+      sx = ssize - 1;
+    }
+    const float c0 = 1.f - fx;
+    ofs[dx] = sx;
+    a01[2 * dx] = (int)lrintf(c0 * 2048.f);
+    a01[2 * dx + 1] = (int)lrintf(fx * 2048.f);
+  }
+}
+
 // build (or reuse) the device tables for a W x H -> nw x nh non-integer INTER_AREA shrink
-int ensure_area_tabs(vd3d_ctx* ctx, int which, int W, int H, int nw, int nh, FitPlan& f) {
+int ensure_area_tabs(vd3d_ctx* ctx, int which, int W, int H, int nw, int nh, FitPlan& f, bool lin = false) {
   Buf& tab = ctx->area_tab[which];
   int* key = ctx->at_key[which];
   const bool have = key[0] == W && key[1] == H && key[2] == nw && key[3] == nh && tab.p;
@@ -453,9 +480,21 @@ int ensure_area_tabs(vd3d_ctx* ctx, int which, int W, int H, int nw, int nh, Fit
     if (cs != cudaStreamCaptureStatusNone) return fail(ctx, VD3D_ERR_STATE, "INTER_AREA tables missing during capture");
     std::vector<int> xo, xc, yo, yc;
     std::vector<std::vector<float>> xa, ya;
-    area_axis_tab(W, nw, xo, xc, xa);
-    area_axis_tab(H, nh, yo, yc, ya);
-    int T = 1;
+    if (lin) {
+      std::vector<int> ax, ay;
+      area_linear_tab(W, nw, xo, ax);
+      area_linear_tab(H, nh, yo, ay);
+      xc.assign(nw, 2);
+      yc.assign(nh, 2);
+      xa.resize(nw);
+      ya.resize(nh);
+      for (int i = 0; i < nw; ++i) xa[i] = {(float)ax[2 * i], (float)ax[2 * i + 1]};
+      for (int i = 0; i < nh; ++i) ya[i] = {(float)ay[2 * i], (float)ay[2 * i + 1]};
+    } else {
+      area_axis_tab(W, nw, xo, xc, xa);
+      area_axis_tab(H, nh, yo, yc, ya);
+    }
+    int T = lin ? 2 : 1;
     for (int c : xc) T = c > T ? c : T;
     for (int c : yc) T = c > T ? c : T;
     if (T > 64) return fail(ctx, VD3D_ERR_UNSUPPORTED, "INTER_AREA shrink factor too large");
@@ -490,6 +529,7 @@ int ensure_area_tabs(vd3d_ctx* ctx, int which, int W, int H, int nw, int nh, Fit
   f.xal = (const float*)(ip + 2 * nw + 2 * nh);
   f.yal = f.xal + (size_t)nw * ctx->at_t[which];
   f.area_t = ctx->at_t[which];
+  f.lin = lin ? 1 : 0;
   return VD3D_OK;
 }
 
@@ -521,8 +561,19 @@ int plan_fit(vd3d_ctx* ctx, int fmt, int W, int H, int pw, int ph, FitPlan& f, i
     f.sy = H / nh;
     return VD3D_OK;
   }
-  if (nw > W || nh > H)  // cv2 switches INTER_AREA to a bilinear scheme when enlarging: not on the hot path
-    return fail(ctx, VD3D_ERR_UNSUPPORTED, "eye fit would enlarge the eye (INTER_AREA upscaling)");
+  if (nw > W || nh > H) {
+    // cv2 switches INTER_AREA to a fixed-point bilinear scheme as soon as one axis grows.  The k_post branch for it is
+    // written against the cv2-pinned oracle but has not been run on a GPU yet: opt-in until it has
+    static int enlarge = -1;
+    if (enlarge < 0) {
+      const char* v = getenv("VD3D_FIT_ENLARGE");
+      enlarge = v ? atoi(v) : 0;
+    }
+    if (!enlarge) return fail(ctx, VD3D_ERR_UNSUPPORTED, "eye fit would enlarge the eye (INTER_AREA upscaling)");
+    f.sx = f.sy = 0;
+    // the key of the cached tables does not encode the mode: W x H -> nw x nh is either a shrink or an enlargement
+    return ensure_area_tabs(ctx, tab_slot, W, H, nw, nh, f, true);
+  }
   f.sx = f.sy = 0;
   return ensure_area_tabs(ctx, tab_slot, W, H, nw, nh, f);
 }
@@ -542,6 +593,7 @@ void set_fit(PostArgs& pa, const FitPlan& fp) {
   pa.ycnt = fp.ycnt;
   pa.yal = fp.yal;
   pa.area_t = fp.area_t;
+  pa.lin = fp.lin;
 }
 
 int copy_in(vd3d_ctx* ctx, Buf& b, const void* src, size_t bytes, int mem, cudaStream_t s, const void** dev) {
@@ -1642,6 +1694,16 @@ int vd3d_area_table(int ssize, int dsize, int* ofs, int* cnt, float* alpha, int 
     for (int k = 0; k < cap; ++k) alpha[(size_t)i * cap + k] = k < c[i] ? a[i][k] : 0.f;
   }
   return T;
+}
+
+// host-only test hook: the fixed-point bilinear tables of cv2's INTER_AREA emulation for an enlarged axis
+int vd3d_area_linear_table(int ssize, int dsize, int* ofs, int* a01) {
+  if (ssize < 1 || dsize < 1 || !ofs || !a01) return VD3D_ERR_ARG;
+  std::vector<int> o, a;
+  area_linear_tab(ssize, dsize, o, a);
+  memcpy(ofs, o.data(), (size_t)dsize * sizeof(int));
+  memcpy(a01, a.data(), (size_t)2 * dsize * sizeof(int));
+  return VD3D_OK;
 }
 
 int vd3d_dof_grade(vd3d_ctx* ctx, const uint8_t* eye_bgr, int h, int w, const float* depth01, int dh, int dw,
