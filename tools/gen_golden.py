@@ -266,8 +266,48 @@ def gen_extra():
         print(f, os.path.getsize(os.path.join(OUT, f)), {k: z[k].shape for k in z.files if k.startswith("final")})
 
 
+def gen_depth_gray():
+    """O. convert_depth_to_grayscale (core/render_depth.py:585-611) on the input kinds it accepts
+    (`python tools/gen_golden.py depthgray`): tensor / ndarray, 2-D, [C,H,W], [H,W,C], flat and NaN frames."""
+    # core/render_depth.py drags in diffusers / DepthCrafter at import; run just this (unmodified) function by
+    # compiling its definition out of the reference file at generation time -- nothing is copied into the repo
+    import ast
+    import types
+    import torch
+    from PIL import Image
+    path = os.path.join(refshim.REF_ROOT, "core", "render_depth.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "convert_depth_to_grayscale"]
+    ns = {"np": np, "torch": torch, "Image": Image}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+    rd = types.SimpleNamespace(convert_depth_to_grayscale=ns["convert_depth_to_grayscale"])
+    rng = np.random.default_rng(77)
+    base = (rng.standard_normal((24, 32)) * 3.0 + 5.0).astype(np.float32)
+    inputs = {
+        "hw": base,
+        "chw1": base[None],
+        "chw3": np.stack([base, base * 0.5, base + 1.0]).astype(np.float32),
+        "hwc1": base[..., None],
+        "hwc3": np.stack([base, base * 0.5, base + 1.0], axis=-1).astype(np.float32),
+        "flat": np.full((24, 32), 2.5, dtype=np.float32),
+        "nan": np.where(rng.random((24, 32)) < 0.05, np.nan, base).astype(np.float32),
+        "f64": base.astype(np.float64) * 1e-3,
+        "neg": -base,
+    }
+    out = {}
+    for k, v in inputs.items():
+        out["in_" + k] = v
+        out["np_" + k] = rd.convert_depth_to_grayscale(v.copy())
+        out["pt_" + k] = rd.convert_depth_to_grayscale(torch.from_numpy(v.copy()))
+    p = os.path.join(OUT, "depth_gray.npz")
+    np.savez_compressed(p, **out)
+    print(p, os.path.getsize(p))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+    if len(sys.argv) > 1 and sys.argv[1] == "depthgray":
+        gen_depth_gray()
+    elif len(sys.argv) > 1 and sys.argv[1] == "extra":
         gen_extra()
     elif len(sys.argv) > 1 and sys.argv[1] == "vr":
         gen_vr()

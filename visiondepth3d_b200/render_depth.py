@@ -119,9 +119,31 @@ def depth_u8_from_frame(frame_bgr, invert=False):
 
 
 def convert_depth_to_grayscale(depth):
-    """core/render_depth.py:585-611 (tensor path): per-frame min-max -> uint8, truncating.
-    Host helper for callers holding a CPU tensor; the frame path does this on the GPU."""
-    d = depth.detach().cpu().numpy() if hasattr(depth, "detach") else np.asarray(depth)
-    d = d.astype(np.float32)
-    lo, hi = d.min(), d.max()
-    return ((d - lo) / (hi - lo + np.float32(1e-6)) * 255).astype(np.uint8)
+    """core/render_depth.py:585-611: PIL / tensor / ndarray, [H,W], [C,H,W] or [H,W,C] (C in {1,3}: first channel or the
+    channel mean) -> per-frame min-max -> uint8 (truncating); NaN or flat frames give zeros, other types / ranks raise.
+    Host helper for callers holding CPU data, like the reference's; the frame path does this on the GPU
+    (k_depth_upsample_minmax + k_depth_to_u8)."""
+    try:
+        from PIL import Image
+    except Exception:  # pragma: no cover
+        Image = None
+    if Image is not None and isinstance(depth, Image.Image):
+        d = np.array(depth).astype(np.float32)
+    elif torch is not None and isinstance(depth, torch.Tensor):
+        d = depth.detach().cpu().float().numpy()
+    elif isinstance(depth, np.ndarray):
+        d = depth.astype(np.float32)
+    else:
+        raise TypeError(f"Unsupported depth type: {type(depth)}")
+    if d.ndim == 3:
+        if d.shape[0] in (1, 3):
+            d = d[0] if d.shape[0] == 1 else d.mean(axis=0)
+        elif d.shape[2] in (1, 3):
+            d = d[..., 0] if d.shape[2] == 1 else d.mean(axis=-1)
+    elif d.ndim != 2:
+        raise ValueError(f"Unexpected depth shape: {d.shape}")
+    lo, hi = np.min(d), np.max(d)
+    if np.isnan(lo) or np.isnan(hi) or hi - lo < 1e-6:
+        print("⚠️ Skipping frame with invalid depth values.")
+        return np.zeros_like(d, dtype=np.uint8)
+    return ((d - lo) / (hi - lo + 1e-6) * 255).astype(np.uint8)
