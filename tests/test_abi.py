@@ -109,6 +109,23 @@ def test_area_tables_match_cv2_restatement(lib):
         assert np.array_equal(ofs, eo) and np.array_equal(a01, ea), (ss, ds)
 
 
+def test_python_surface_matches_reference_signatures(golden_dir):
+    """the drop-in keeps parameter names, order and defaults of the reference's hot-path functions
+    (snapshot of the unmodified reference: tools/gen_golden.py signatures)."""
+    import inspect
+    import json
+    import os
+    from visiondepth3d_b200 import render_3d as R
+    g = json.load(open(os.path.join(golden_dir, "signatures.json")))
+    assert {k: float(v) for k, v in R.aspect_ratios.items()} == g.pop("aspect_ratios")
+    assert len(g) == 10
+    for name, ref in g.items():
+        sig = inspect.signature(getattr(R, name))
+        mine = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+                for p in sig.parameters.values() if not p.name.startswith("_")]  # private test taps excluded
+        assert mine == ref, name
+
+
 def test_create_fails_loudly_without_gpu(lib):
     import torch
     if torch.cuda.is_available():

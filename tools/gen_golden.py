@@ -304,8 +304,30 @@ def gen_depth_gray():
     print(p, os.path.getsize(p))
 
 
+def gen_signatures():
+    """P. the call surface of the boundary: parameter names, order and defaults of the reference's
+    hot-path functions (`python tools/gen_golden.py signatures`) -> tests/golden/signatures.json."""
+    import inspect
+    import json
+    mods = refshim.load_reference(("render_3d",))
+    r3d = mods["render_3d"]
+    names = ["pixel_shift_cuda", "render_sbs_3d", "format_3d_output", "generate_anaglyph_3d", "apply_sharpening",
+             "pad_to_aspect_ratio", "frame_to_tensor", "depth_to_tensor", "tensor_to_frame", "heal_missing_pixels"]
+    out = {}
+    for n in names:
+        sig = inspect.signature(getattr(r3d, n))
+        out[n] = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+                  for p in sig.parameters.values()]
+    out["aspect_ratios"] = {k: float(v) for k, v in r3d.aspect_ratios.items()}
+    p = os.path.join(OUT, "signatures.json")
+    json.dump(out, open(p, "w"), indent=1, sort_keys=True)
+    print(p, os.path.getsize(p))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "depthgray":
+    if len(sys.argv) > 1 and sys.argv[1] == "signatures":
+        gen_signatures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "depthgray":
         gen_depth_gray()
     elif len(sys.argv) > 1 and sys.argv[1] == "extra":
         gen_extra()
