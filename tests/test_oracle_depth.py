@@ -22,6 +22,27 @@ def test_oracle_matches_transformers_small_input():
         assert float((mine - ref).abs().max()) / scale < 1e-4
 
 
+import pytest
+
+
+@pytest.mark.parametrize("name", ["vitb", "vitl"])
+def test_oracle_matches_transformers_base_and_large_configs(name):
+    """The Base / Large configurations (taps, neck widths, fusion width, 24 layers) through the same oracle code:
+    the GPU tests compare the CUDA engine with oracle/depth.py for these, so the oracle itself must equal transformers."""
+    from transformers import DepthAnythingForDepthEstimation
+    torch.manual_seed(0)
+    model = DepthAnythingForDepthEstimation(hf_config(name)).eval()
+    sd = model.state_dict()
+    torch.manual_seed(2)
+    px = torch.randn(3, 70, 98)
+    with torch.no_grad():
+        ref = model(pixel_values=px[None]).predicted_depth[0]
+        mine = OD.forward(sd, CONFIGS[name], px)
+    assert mine.shape == ref.shape
+    scale = float(ref.max() - ref.min()) + 1e-12
+    assert float((mine - ref).abs().max()) / scale < 1e-4
+
+
 def test_weight_preparation_shapes():
     from transformers import DepthAnythingForDepthEstimation
     from visiondepth3d_b200.depth_weights import prepare
