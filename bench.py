@@ -2,17 +2,25 @@
 """bench.py -- end-to-end frames/s of the depth -> stereo hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 1080p|4k] [--impl ours|reference]
+                    [--no-4k] [--no-cpu-baseline] [--dof S] [--exact]
 
-A step = one batch of `frames_per_step` synthetic frames through the hot path
-(depth forward when a depth engine is built + the DIBR frame loop of render_sbs_3d).
-`value`  : frames/s, inputs resident in HBM, timed with CUDA events on the engine's stream.
-`e2e`    : the same through the public host-buffer API (vd3d_render_clip, pinned host
-           frames in, packed frames out, H2D/D2H inside the timed region).
-`roofline`: dominant DIBR kernel (compose) and the whole DIBR stage vs measured HBM peak.
-`cpu_baseline`: the oracle port timed on a bounded sample on the host cores (rank 0, N=1).
-`--impl reference`: the CPU port of the reference path, same JSON line.
-Multi-GPU: one process per GPU (torchrun), contiguous chunks of frames per rank, no
-per-frame collective; max-over-ranks device time.
+A step = one batch of `frames_per_step` synthetic frames through the hot path (DPT processor + Depth-Anything-V2
+forward + u8 depth handoff in HBM + the DIBR frame loop of render_sbs_3d + pack).  With the defaults (20 steps of
+15 frames) the timed region is the 300-frame clip of BASELINE.json configs[1].
+`value`   : frames/s, inputs resident in HBM, CUDA events on the engine's stream, max over ranks.
+`e2e`     : the same through the public host-buffer API (vd3d_render_clip_depth on pinned host frames, H2D and D2H
+            inside the timed region).
+`roofline`: the dominant kernel of the step -- the persistent tcgen05 GEMM (its fc1 launches timed live with CUDA
+            events) against the measured bf16 peak; `roofline_depth_stage`, `roofline_dibr_stage` (whole DIBR frame,
+            SURVEY 8(d) algorithmic bytes) and `roofline_dibr_render` (the fused warp/feather/compose/pack kernel)
+            against the measured HBM peak explain the rest.  `dibr_only` is the DIBR stage run back to back on
+            device-resident depth (its throughput form: bytes_per_frame x stage_fps).
+`arm_4k`  : the same measurement on configs[2]'s per-GPU share (4K, DA-V2-Large, Full-SBS), emitted in the same run.
+`cpu_baseline`: the oracle port of the reference path timed on a bounded sample on the host cores (rank 0, N=1).
+`--impl reference`: that CPU port as the timed arm, same JSON line and the same `config`.
+Multi-GPU: one process per GPU (torchrun), contiguous chunks of frames per rank, one NCCL broadcast of the weights,
+no per-frame collective; max-over-ranks device time.  `--sharding exact` hands the temporal state from rank to
+rank (bit-identical to one GPU); the default `replicas` keeps independent state per chunk.
 """
 import argparse
 import ctypes as C
@@ -32,18 +40,19 @@ sys.path.insert(0, ROOT)
 DEPTH_GFLOP = {"vits": 253.8, "vitb": 775.3, "vitl": 2583.1}
 
 WORKLOADS = {
-    # BASELINE.json configs[1]
-    "1080p": dict(name="1080p synthetic clip, Depth-Anything-V2-Base, Half-SBS", w=1920, h=1080,
-                  fmt="Half-SBS", preserve=False, model="vitb", pool=24, frames_per_step=8,
+    # BASELINE.json configs[1]: 300-frame clip = 20 steps x 15 frames
+    "1080p": dict(name="1080p 300-frame synthetic clip, Depth-Anything-V2-Base, Half-SBS", w=1920, h=1080,
+                  fmt="Half-SBS", preserve=False, model="vitb", pool=30, frames_per_step=15,
                   # 3*Ws*Hs + 1*Ws*Hs + 8*Wt*Ht + 3*Wout*Hout
                   dibr_bytes=3 * 1920 * 1080 + 1920 * 1080 + 8 * 960 * 540 + 3 * 1920 * 1080),
-    # BASELINE.json configs[2] (per-GPU share)
-    "4k": dict(name="4K synthetic clip, Depth-Anything-V2-Large, Full-SBS", w=3840, h=2160,
-               fmt="Full-SBS", preserve=True, model="vitl", pool=6, frames_per_step=6,
+    # BASELINE.json configs[2] (per-GPU share of the 1000-frame clip)
+    "4k": dict(name="4K synthetic clip, Depth-Anything-V2-Large, Full-SBS (per-GPU share of the 1000-frame clip)",
+               w=3840, h=2160, fmt="Full-SBS", preserve=True, model="vitl", pool=10, frames_per_step=10,
                dibr_bytes=18 * 3840 * 2160),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_compose launch (profiles/r01_ncu_full_summary.md)
-NCU_COMPOSE_TRAFFIC = {"4k": 156386048, "1080p": None}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused render kernel from `ncu --set full`
+# (profiles/r02_ncu_dibr.md); None until captured for that configuration
+NCU_RENDER_TRAFFIC = {"4k": None, "1080p": None}
 # same for one fc1 launch of k_umma_gemm<128,3> (DA-V2-Base: M=2443, N=3072, K=768): 8.56 MB read + 0.01 MB written
 NCU_GEMM_FC1_TRAFFIC = {"vitb": 8571136, "vitl": None, "vits": None}
 COMMON = dict(fg=4.5, mg=-1.5, bg=-6.0, sharp=0.2, feather=10.0, ksize=9, tracking=True, floating=True,
@@ -63,6 +72,19 @@ def peaks_burst():
     if os.path.exists(p):
         return json.load(open(p)).get("bf16_tflops", 1590.0)
     return 1590.0
+
+
+def common_config(wl, world, sharding="replicas"):
+    """The workload description: identical in the `ours` and the `reference` arm."""
+    return {
+        "workload": wl["name"], "resolution": [wl["w"], wl["h"]], "output_format": wl["fmt"],
+        "depth_model": f"Depth-Anything-V2 {wl['model']} @518x924, random-init seed 0 (no checkpoints offline)",
+        "frames_per_step": wl["frames_per_step"], "frame_pool": wl["pool"],
+        "l2_policy": "inputs+outputs larger than L2 (pool of distinct frames cycled)",
+        "params": dict(COMMON),
+        "sharding": ("contiguous chunks per rank, temporal state handed from rank to rank (exact)" if sharding == "exact"
+                     else "contiguous chunks per rank, independent temporal state per chunk (replicas)"),
+    }
 
 
 class ClockSampler:
@@ -94,7 +116,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, pw, reasons = [], None, [], set()
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
@@ -102,13 +124,14 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx = float(f[2])
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def make_pool(wl, n, seed0=0):
@@ -117,7 +140,7 @@ def make_pool(wl, n, seed0=0):
     return [synth_frame(seed0 + i, wl["w"], wl["h"], "noise") for i in range(n)]
 
 
-def render_params(R, wl, depth_channels=3):
+def render_params(R, wl):
     return R.make_render_params(
         wl["w"], wl["h"], COMMON["fg"], COMMON["mg"], COMMON["bg"], COMMON["sharp"], wl["fmt"], 16 / 9,
         COMMON["dof"], COMMON["feather"], COMMON["ksize"], COMMON["tracking"], COMMON["floating"],
@@ -133,19 +156,43 @@ def oracle_params(wl):
                           preserve_original_aspect=wl["preserve"], zero_parallax_strength=COMMON["zps"])
 
 
+# ======================================================================================================
+# CPU arm: the port of the reference path (oracle/) on the host cores.  Depth forward = torch fp32 on all threads;
+# the DIBR loop (numpy, one thread per clip) runs one independent chunk per worker process so that every core works.
+# ======================================================================================================
 _CPU_MODEL = {}
 
 
-class CpuPort:
-    """CPU port of the reference path on the same workload: depth = oracle/depth.py (torch fp32, up to 32
-    host threads; DPT resize via torch bicubic antialias), stereo = oracle/dibr.py (numpy, one thread)."""
+def _cpu_threads():
+    return min(32, os.cpu_count() or 1)
 
+
+def _dibr_workers():
+    return max(1, min(8, (os.cpu_count() or 1) // 2))
+
+
+def _dibr_chunk(job):
+    """Worker: render one chunk with its own temporal state; returns (seconds for the timed frames, frames)."""
+    wl, frames_idx, depths = job
+    from oracle import dibr as O
+    from visiondepth3d_b200.synth import synth_frame
+    gs, cs, rp = O.GlobalState(), O.ClipState(), oracle_params(wl)
+    t = 0.0
+    for k, (i, d8) in enumerate(zip(frames_idx, depths)):
+        fr, _ = synth_frame(i, wl["w"], wl["h"], "noise")
+        t0 = time.perf_counter()
+        O.render_frame(gs, cs, fr, np.repeat(d8[..., None], 3, axis=2), rp)
+        if k > 0:  # the first frame of a chunk initialises the trackers (untimed warm-up)
+            t += time.perf_counter() - t0
+    return t, max(len(frames_idx) - 1, 0)
+
+
+class CpuPort:
     def __init__(self, wl):
         import torch
-        from oracle import dibr as O
         from visiondepth3d_b200.depth_weights import CONFIGS, hf_config
-        self.wl, self.O, self.torch = wl, O, torch
-        torch.set_num_threads(min(32, os.cpu_count()))
+        self.wl, self.torch = wl, torch
+        torch.set_num_threads(_cpu_threads())
         if wl["model"] not in _CPU_MODEL:
             from transformers import DepthAnythingForDepthEstimation
             torch.manual_seed(0)
@@ -153,73 +200,296 @@ class CpuPort:
         self.sd, self.cfg = _CPU_MODEL[wl["model"]], CONFIGS[wl["model"]]
         self.mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
         self.std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
-        self.gs, self.cs, self.rp = O.GlobalState(), O.ClipState(), oracle_params(wl)
         self.i = 0
-        self.frame()  # warm-up frame (first-frame state initialisation, lazy imports)
+        self.pool = None
 
-    def frame(self):
+    def depth_u8(self, i):
         import torch.nn.functional as F
         from oracle import depth as OD
         from visiondepth3d_b200.synth import synth_frame
         torch, wl = self.torch, self.wl
-        fr, _ = synth_frame(self.i, wl["w"], wl["h"], "noise")
-        self.i += 1
+        fr, _ = synth_frame(i, wl["w"], wl["h"], "noise")
         with torch.no_grad():
             t = torch.from_numpy(fr[..., ::-1].copy()).permute(2, 0, 1)[None].float()
             t = F.interpolate(t, size=(518, 924), mode="bicubic", align_corners=False, antialias=True).round().clamp(0, 255)
             pv = (t[0] / 255.0 - self.mean) / self.std
             d = OD.forward(self.sd, self.cfg, pv)
             d = F.interpolate(d[None, None], size=(wl["h"], wl["w"]), mode="bicubic", align_corners=False)[0, 0].numpy()
-        d8 = ((d - d.min()) / (d.max() - d.min() + np.float32(1e-6)) * 255).astype(np.uint8)
-        self.O.render_frame(self.gs, self.cs, fr, np.repeat(d8[..., None], 3, axis=2), self.rp)
+        return ((d - d.min()) / (d.max() - d.min() + np.float32(1e-6)) * 255).astype(np.uint8)
 
-    def timed(self, n_frames):
+    def sample(self, frames_per_worker=1):
+        """One bounded sample: W chunks of (1 warm-up + frames_per_worker) frames.  Returns (frames/s, frames)."""
+        import multiprocessing as mp
+        W = _dibr_workers()
+        per = frames_per_worker + 1
+        idx = [[self.i + c * per + k for k in range(per)] for c in range(W)]
+        self.i += W * per
         t0 = time.perf_counter()
-        for _ in range(n_frames):
-            self.frame()
-        return n_frames / (time.perf_counter() - t0)
+        depths = [[self.depth_u8(i) for i in ch] for ch in idx]
+        t_depth = time.perf_counter() - t0
+        n_depth = W * per
+        if self.pool is None:
+            self.pool = mp.get_context("fork").Pool(W)
+        res = self.pool.map(_dibr_chunk, [(self.wl, ch, dp) for ch, dp in zip(idx, depths)])
+        t_dibr = max(r[0] for r in res)          # chunks run concurrently: the slowest one is the stage time
+        n = sum(r[1] for r in res)
+        # per-frame cost = depth (all threads, one frame at a time) + DIBR (W chunks in parallel)
+        sec_per_frame = t_depth / n_depth + t_dibr / max(n, 1)
+        return 1.0 / sec_per_frame, n, {"depth_s_per_frame": t_depth / n_depth, "dibr_s_per_frame_effective": t_dibr / max(n, 1),
+                                        "dibr_workers": W}
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.terminate()
+            self.pool = None
 
 
-def cpu_port_fps(wl, seconds_budget=15.0, max_frames=2):
+def cpu_baseline_obj(wl):
     port = CpuPort(wl)
-    n, t0 = 0, time.perf_counter()
-    while n < max_frames and (time.perf_counter() - t0) < seconds_budget:
-        port.frame()
-        n += 1
-    return n / (time.perf_counter() - t0), n
+    try:
+        fps, n, parts = port.sample(1)
+    finally:
+        port.close()
+    return {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} timed frames of the workload ({parts['dibr_workers']} independent chunks of 1 warm-up + 1 timed frame): "
+                      f"depth forward oracle/depth.py torch fp32 on {_cpu_threads()} threads ({parts['depth_s_per_frame']:.2f} s/frame) + "
+                      f"DIBR oracle/dibr.py numpy, one process per chunk ({parts['dibr_s_per_frame_effective']:.2f} s/frame effective); "
+                      "the reference is Python and cannot travel to the GPU box"}
 
 
 def run_reference(args, wl, rank, world):
-    """--impl reference: the reference's CPU path (port: oracle/dibr.py; /root/reference does not
-    exist on the GPU box and its Python cannot travel).  Rank 0 only."""
+    """--impl reference: the reference's CPU path (port: oracle/; /root/reference does not exist on the GPU box and
+    its Python cannot travel).  Rank 0 only.  A step is a bounded sample of the workload."""
     if rank != 0:
         return
     t_all = time.perf_counter()
-    port = CpuPort(wl)           # includes one warm-up frame
-    per_step = []
-    total = 0
-    # a step is a bounded sample of the workload: ONE frame (~5 s of CPU work at 1080p / DA-V2-Base),
-    # temporal state carried across steps like the reference's frame loop; capped at ~4 minutes overall
-    for s in range(args.warmup + args.steps):
-        if time.perf_counter() - t_all > 240.0 and per_step:
-            break
-        fps = port.timed(1)
-        if s >= args.warmup:
-            per_step.append(fps)
-            total += 1
+    port = CpuPort(wl)
+    per_step, total, parts = [], 0, {}
+    try:
+        for s in range(args.warmup + args.steps):
+            if time.perf_counter() - t_all > 200.0 and per_step:
+                break
+            if s >= args.warmup or s == 0:   # one warm-up sample is enough for a CPU path (lazy imports, page-in)
+                fps, n, parts = port.sample(1)
+                if s >= args.warmup:
+                    per_step.append(fps)
+                    total += n
+    finally:
+        port.close()
     value = float(np.mean(per_step))
     line = {
         "impl": "reference", "metric": "end-to-end frames/sec (depth+stereo)", "value": value, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wl["frames_per_step"] / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "stage": "CPU port: DPT processor + DA-V2 forward (torch fp32) + DIBR loop (numpy)"},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": min(32, os.cpu_count()), "kind": "port",
-                         "sample": f"{total} frames of the workload; depth forward torch fp32 on {min(32, os.cpu_count())} threads, "
-                                   "DIBR numpy port on 1 thread (the reference is Python and cannot travel to the GPU box)"},
+        "config": common_config(wl, world, args.sharding),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{len(per_step)} samples x {parts.get('dibr_workers', 0)} timed frames (each step a bounded sample of the "
+                                   f"{wl['frames_per_step']}-frame step): depth forward torch fp32 on {_cpu_threads()} threads + DIBR numpy port, "
+                                   f"{parts.get('dibr_workers', 0)} chunks in parallel processes"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": time.perf_counter() - t_all,
+        "stage_seconds": parts, "wall_s": time.perf_counter() - t_all,
     }
     print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================
+# GPU arm
+# ======================================================================================================
+class GpuArm:
+    def __init__(self, args, key, rank, local_rank, world, dist):
+        import torch
+        wl = WORKLOADS[key]
+        self.key = key
+        from visiondepth3d_b200 import _lib
+        from visiondepth3d_b200 import render_3d as R
+        from visiondepth3d_b200.depth_engine import DepthEngine
+        from visiondepth3d_b200.depth_weights import hf_config
+        from visiondepth3d_b200.sharding import broadcast_state_dict
+        from transformers import DepthAnythingForDepthEstimation
+        self.args, self.wl, self.rank, self.world, self.dist, self.torch, self._lib = args, wl, rank, world, dist, torch, _lib
+        self.dev = torch.device("cuda", local_rank)
+        self.ctx = _lib.Context(local_rank)
+        self.lib = self.ctx.lib
+        if args.exact:
+            self.ctx.set_exact(True)
+        # depth model: the architecture BASELINE names, random-init (seed 0) -- no checkpoints offline.
+        # One NCCL broadcast of the weights at init (rank 0 builds them), no per-frame collective.
+        sd = None
+        if rank == 0:
+            torch.manual_seed(0)
+            with torch.device("cpu"):
+                sd = DepthAnythingForDepthEstimation(hf_config(wl["model"])).eval().state_dict()
+        else:
+            with torch.device("meta"):
+                sd = DepthAnythingForDepthEstimation(hf_config(wl["model"])).state_dict()
+        sd = broadcast_state_dict(sd, src=0, device=self.dev)
+        self.deng = DepthEngine(wl["model"], 518, 924, ctx=self.ctx)
+        self.deng.load_state_dict(sd)
+        del sd
+        self.rp = render_params(R, wl)
+        self.pl = R.plan_sizes(wl["w"], wl["h"], self.rp)
+        self.oshape = R.output_shape(self.rp, self.pl)
+        self.B, self.P = wl["frames_per_step"], wl["pool"]
+        pool = make_pool(wl, self.P, seed0=rank * 1000)
+        self.f_dev = [torch.from_numpy(f).to(self.dev) for f, _ in pool]
+        self.d_dev = [torch.from_numpy(d).to(self.dev) for _, d in pool]      # synthetic depth (DIBR-only arm)
+        self.o_dev = [torch.empty(self.oshape, dtype=torch.uint8, device=self.dev) for _ in range(self.P)]
+        self.f_host = [torch.from_numpy(f).pin_memory() for f, _ in pool]
+        self.o_host = [torch.empty(self.oshape, dtype=torch.uint8).pin_memory() for _ in range(self.P)]
+        self.in_bytes = sum(t.numel() for t in self.f_dev) + sum(t.numel() for t in self.o_dev)
+        torch.cuda.synchronize()
+        self.stream = torch.cuda.ExternalStream(self.lib.vd3d_stream(self.ctx.h), device=self.dev)
+        self.step_idx = 0
+
+    def ptr_array(self, ts, idx):
+        return (C.c_void_p * len(idx))(*[ts[i].data_ptr() for i in idx])
+
+    def _idx(self):
+        i0 = (self.step_idx * self.B) % self.P
+        self.step_idx += 1
+        return [(i0 + k) % self.P for k in range(self.B)]
+
+    def step(self, mem):
+        idx, wl, _lib = self._idx(), self.wl, self._lib
+        if mem == _lib.MEM_DEVICE:
+            a, c = self.ptr_array(self.f_dev, idx), self.ptr_array(self.o_dev, idx)
+        else:
+            a, c = self.ptr_array(self.f_host, idx), self.ptr_array(self.o_host, idx)
+        self.ctx.check(self.lib.vd3d_render_clip_depth(self.ctx.h, self.deng.h, self.B, a, wl["h"], wl["w"],
+                                                       C.byref(self.rp), c, mem))
+
+    def step_dibr(self):
+        idx, wl, _lib = self._idx(), self.wl, self._lib
+        a, d, c = self.ptr_array(self.f_dev, idx), self.ptr_array(self.d_dev, idx), self.ptr_array(self.o_dev, idx)
+        self.ctx.check(self.lib.vd3d_render_clip(self.ctx.h, self.B, a, d, 3, wl["h"], wl["w"], C.byref(self.rp), c,
+                                                 _lib.MEM_DEVICE, None))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce_max(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps, warmup):
+        torch = self.torch
+        self.ctx.reset()
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(self.stream)
+        self.barrier()
+        wall = self.reduce_max(time.perf_counter() - t0)
+        return self.reduce_max(e0.elapsed_time(e1)), wall
+
+    def measure(self, local_rank, full=True):
+        args, wl, _lib, lib, ctx, deng = self.args, self.wl, self._lib, self.lib, self.ctx, self.deng
+        B, world = self.B, self.world
+        frames = args.steps * B
+        # ---------------- device-resident arm (value) ----------------
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        l0 = ctx.launches + deng.launches
+        ms, _ = self.timed(lambda: self.step(_lib.MEM_DEVICE), args.steps, args.warmup)
+        launches = ctx.launches + deng.launches - l0 - 0
+        value = world * frames / (ms / 1000.0)
+        # ---------------- end-to-end arm (pinned host buffers through the public API) ----------------
+        _, e2e_s = self.timed(lambda: self.step(_lib.MEM_HOST), args.steps, args.warmup)
+        clk = clocks.stop()
+        e2e_value = world * frames / e2e_s
+        h2d = B * (wl["w"] * wl["h"] * 3)
+        d2h = B * int(np.prod(self.oshape))
+        # ---------------- DIBR stage alone, back to back on device-resident u8 depth (graph replay) ----------------
+        dsteps = max(4, min(args.steps, 10))
+        dms, _ = self.timed(self.step_dibr, dsteps, 3)
+        dibr_fps = dsteps * B / (dms / 1000.0)          # per GPU
+        # ---------------- per-stage device timing (CUDA events around the stages; serial eager launches) ----------
+        lib.vd3d_profile(ctx.h, 1)
+        lib.vd3d_depth_profile(deng.h, 1)
+        tot = [C.c_double() for _ in range(3)]
+        cnt = [C.c_int() for _ in range(3)]
+        g_ms, g_n, g_gf = C.c_double(), C.c_int(), C.c_double()
+        self.step(_lib.MEM_DEVICE)  # un-timed: first eager pass through the serial path allocates its workspaces
+        for st in (0, 1, 2):
+            lib.vd3d_profile_collect(ctx.h, st, C.byref(tot[st]), C.byref(cnt[st]))
+        lib.vd3d_depth_profile_collect(deng.h, C.byref(g_ms), C.byref(g_n), C.byref(g_gf))
+        for _ in range(2):
+            self.step(_lib.MEM_DEVICE)
+        for st in (0, 1, 2):
+            lib.vd3d_profile_collect(ctx.h, st, C.byref(tot[st]), C.byref(cnt[st]))
+        lib.vd3d_depth_profile_collect(deng.h, C.byref(g_ms), C.byref(g_n), C.byref(g_gf))
+        lib.vd3d_depth_profile(deng.h, 0)
+        lib.vd3d_profile(ctx.h, 0)
+        if self.rank != 0:
+            return None
+        hbm_peak, tf_peak, which = peaks()
+        pl = self.pl
+        # fused render kernel: source RGB in (u8 at the source size on the identity path, f32 RGBx otherwise is an
+        # intermediate -- algorithmic = the u8 frame) + packed output out
+        src_px = wl["w"] * wl["h"]
+        out_px = int(np.prod(self.oshape[:2]))
+        rend_bytes = 3 * src_px + 3 * out_px
+        rend_ms = tot[1].value / max(cnt[1].value, 1)
+        stage_ms = tot[0].value / max(cnt[0].value, 1)
+        rend_gbs = rend_bytes / (rend_ms * 1e-3) / 1e9 if rend_ms > 0 else 0.0
+        stage_gbs = wl["dibr_bytes"] / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else 0.0
+        tput_gbs = wl["dibr_bytes"] * dibr_fps / 1e9
+        depth_ms = tot[2].value / max(cnt[2].value, 1)
+        depth_tf = DEPTH_GFLOP[wl["model"]] / max(depth_ms, 1e-9)
+        gemm_ms = g_ms.value / max(g_n.value, 1)
+        gemm_tf = g_gf.value / max(gemm_ms, 1e-9)
+        tf_burst = peaks_burst()
+        cfg = common_config(wl, world, args.sharding)
+        line = {
+            "metric": "end-to-end frames/sec (depth+stereo)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 GEMM operands, fp32 accumulate; DIBR fp32", "data": "synthetic",
+            "config": cfg,
+            "run": {
+                "timed_frames": frames, "timed_region_s": ms / 1000.0,
+                "pool_mb": self.in_bytes / 1e6,
+                "stage": "DPT processor + depth forward + min-max u8 handoff in HBM + DIBR frame loop + pack",
+                "launch_mode": "CUDA graph replay; depth forwards of consecutive frames overlap on three streams "
+                               "(stage timings in roofline* are taken in a separate serial, eager pass)",
+                "dibr_mode": "exact" if args.exact else "fast",
+                "graphs_active": int(lib.vd3d_graphs_active(ctx.h)),
+            },
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "k_umma_gemm<128,3> (fc1 launches)",
+                         "achieved": gemm_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": gemm_tf / tf_burst,
+                         "traffic": NCU_GEMM_FC1_TRAFFIC.get(wl["model"]),
+                         "peak_source": which + " (cuBLAS bf16 burst: kernel timed alone)",
+                         "algorithmic_gflop_per_launch": g_gf.value, "avg_launch_ms": gemm_ms, "launches_timed": g_n.value},
+            "roofline_depth_stage": {"bound": "tensor", "achieved": depth_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                                     "frac": depth_tf / tf_peak, "peak_source": which + " (cuBLAS bf16 sustained)",
+                                     "algorithmic_gflop_per_frame": DEPTH_GFLOP[wl["model"]], "avg_frame_ms": depth_ms,
+                                     "share_of_step": depth_ms / max(depth_ms + stage_ms, 1e-9),
+                                     "achieved_in_timed_region": DEPTH_GFLOP[wl["model"]] * (value / world) / 1000.0},
+            "roofline_dibr_render": {"bound": "hbm", "kernel": "k_render (warp edges + box feather + compose + sharpen + fit + pack)",
+                                     "achieved": rend_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rend_gbs / hbm_peak,
+                                     "traffic": NCU_RENDER_TRAFFIC.get(self.key),
+                                     "peak_source": which, "algorithmic_bytes_per_launch": rend_bytes, "avg_launch_ms": rend_ms},
+            "roofline_dibr_stage": {"bound": "hbm", "what": "whole DIBR frame (ingest..pack), serial eager launches",
+                                    "achieved": stage_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,
+                                    "algorithmic_bytes_per_frame": wl["dibr_bytes"], "avg_frame_ms": stage_ms},
+            "dibr_only": {"what": "DIBR stage back to back on device-resident u8 depth (vd3d_render_clip, graph replay)",
+                          "frames_per_s_per_gpu": dibr_fps, "achieved": tput_gbs, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": tput_gbs / hbm_peak, "ms_per_frame": 1000.0 / dibr_fps},
+        }
+        return line
 
 
 def main():
@@ -230,6 +500,9 @@ def main():
     ap.add_argument("--workload", default="1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-4k", action="store_true", help="skip the 4K / DA-V2-Large / Full-SBS arm of the default run")
+    ap.add_argument("--exact", action="store_true", help="DIBR in the bit-exact one-kernel-per-op mode")
+    ap.add_argument("--sharding", default="replicas", choices=["replicas", "exact"])
     ap.add_argument("--dof", type=float, default=None,
                     help="dof_strength (default 0 = the warp/fill/compose variant; 2.0 = the reference GUI default)")
     args = ap.parse_args()
@@ -251,176 +524,27 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from visiondepth3d_b200 import _lib
-    from visiondepth3d_b200 import render_3d as R
-    from visiondepth3d_b200.depth_engine import DepthEngine
-    from visiondepth3d_b200.depth_weights import hf_config
-    ctx = _lib.Context(local_rank)
-    lib = ctx.lib
-    # depth model: the architecture BASELINE names, random-init (seed 0) -- no checkpoints offline.
-    # One NCCL broadcast of the weights at init (rank 0 builds them), no per-frame collective.
-    from transformers import DepthAnythingForDepthEstimation
-    torch.manual_seed(0)
-    with torch.device("cpu"):
-        sd = DepthAnythingForDepthEstimation(hf_config(wl["model"])).eval().state_dict()
-    from visiondepth3d_b200.sharding import broadcast_state_dict
-    sd = broadcast_state_dict(sd, src=0, device=torch.device("cuda", local_rank))
-    deng = DepthEngine(wl["model"], 518, 924, ctx=ctx)
-    deng.load_state_dict(sd)
-    rp = render_params(R, wl)
-    pl = R.plan_sizes(wl["w"], wl["h"], rp)
-    oshape = R.output_shape(rp, pl)
-    B, P = wl["frames_per_step"], wl["pool"]
-    pool = make_pool(wl, P, seed0=rank * 1000)
-
-    # ---- device-resident inputs / outputs (pool larger than L2: 126 MB) ----
-    dev = torch.device("cuda", local_rank)
-    f_dev = [torch.from_numpy(f).to(dev) for f, _ in pool]
-    o_dev = [torch.empty(oshape, dtype=torch.uint8, device=dev) for _ in range(P)]
-    in_bytes = sum(t.numel() for t in f_dev) + sum(t.numel() for t in o_dev)
-    # ---- pinned host buffers for the end-to-end arm ----
-    f_host = [torch.from_numpy(f).pin_memory() for f, _ in pool]
-    o_host = [torch.empty(oshape, dtype=torch.uint8).pin_memory() for _ in range(P)]
-    torch.cuda.synchronize()
-
-    def ptr_array(ts, idx):
-        return (C.c_void_p * len(idx))(*[ts[i].data_ptr() for i in idx])
-
-    stream = torch.cuda.ExternalStream(lib.vd3d_stream(ctx.h), device=dev)
-    step_idx = [0]
-
-    def step(mem):
-        i0 = (step_idx[0] * B) % P
-        idx = [(i0 + k) % P for k in range(B)]
-        step_idx[0] += 1
-        if mem == _lib.MEM_DEVICE:
-            a, c = ptr_array(f_dev, idx), ptr_array(o_dev, idx)
-        else:
-            a, c = ptr_array(f_host, idx), ptr_array(o_host, idx)
-        ctx.check(lib.vd3d_render_clip_depth(ctx.h, deng.h, B, a, wl["h"], wl["w"], C.byref(rp), c, mem))
-
-    def barrier():
+    if args.sharding == "exact":
+        from visiondepth3d_b200 import sharding_bench
+        sharding_bench.run(args, wl, rank, local_rank, world, dist, common_config)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ================= device-resident arm (value) =================
-    ctx.reset()
-    for _ in range(args.warmup):
-        step(_lib.MEM_DEVICE)
-    barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    l0 = ctx.launches + deng.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step(_lib.MEM_DEVICE)
-    e1.record(stream)
-    barrier()
-    ms = reduce_max(e0.elapsed_time(e1))
-    launches = ctx.launches + deng.launches - l0
-    frames = args.steps * B
-    value = world * frames / (ms / 1000.0)
-
-    # ================= end-to-end arm (host buffers through the public API) =================
-    ctx.reset()
-    for _ in range(args.warmup):
-        step(_lib.MEM_HOST)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(_lib.MEM_HOST)
-    barrier()
-    e2e_s = reduce_max(time.perf_counter() - t0)
-    clk = clocks.stop()
-    e2e_value = world * frames / e2e_s
-    h2d = B * (wl["w"] * wl["h"] * 3)
-    d2h = B * int(np.prod(oshape))
-
-    # ================= per-stage device timing (CUDA events around the stages; eager launches) ======
-    lib.vd3d_profile(ctx.h, 1)
-    lib.vd3d_depth_profile(deng.h, 1)
-    tot0, n0, tot1, n1, tot2, n2 = C.c_double(), C.c_int(), C.c_double(), C.c_int(), C.c_double(), C.c_int()
-    g_ms, g_n, g_gf = C.c_double(), C.c_int(), C.c_double()
-    step(_lib.MEM_DEVICE)  # un-timed: first eager pass through the serial path allocates its workspaces
-    for st in (0, 1, 2):
-        lib.vd3d_profile_collect(ctx.h, st, C.byref(tot0), C.byref(n0))
-    lib.vd3d_depth_profile_collect(deng.h, C.byref(g_ms), C.byref(g_n), C.byref(g_gf))
-    for _ in range(max(2, min(args.steps, 4))):
-        step(_lib.MEM_DEVICE)
-    lib.vd3d_profile_collect(ctx.h, 0, C.byref(tot0), C.byref(n0))
-    lib.vd3d_profile_collect(ctx.h, 1, C.byref(tot1), C.byref(n1))
-    lib.vd3d_profile_collect(ctx.h, 2, C.byref(tot2), C.byref(n2))
-    lib.vd3d_depth_profile_collect(deng.h, C.byref(g_ms), C.byref(g_n), C.byref(g_gf))
-    lib.vd3d_depth_profile(deng.h, 0)
-    lib.vd3d_profile(ctx.h, 0)
-
+            dist.destroy_process_group()
+        return
+    arm = GpuArm(args, args.workload, rank, local_rank, world, dist)
+    line = arm.measure(local_rank)
+    del arm
+    torch.cuda.empty_cache()
+    if args.workload == "1080p" and not args.no_4k:
+        a4 = GpuArm(args, "4k", rank, local_rank, world, dist)
+        l4 = a4.measure(local_rank)
+        del a4
+        if rank == 0:
+            keep = ("value", "unit", "ms_per_step", "config", "run", "clocks", "e2e", "gpu_launches", "roofline",
+                    "roofline_depth_stage", "roofline_dibr_render", "roofline_dibr_stage", "dibr_only")
+            line["arm_4k"] = {k: l4[k] for k in keep}
     if rank == 0:
-        hbm_peak, tf_peak, which = peaks()
-        px = wl["w"] * wl["h"] if wl["preserve"] else pl.resized_width * pl.resized_height
-        comp_bytes = 3 * px + 6 * px  # compose: RGB in (u8) + two u8 eyes out
-        comp_ms = tot1.value / max(n1.value, 1)
-        stage_ms = tot0.value / max(n0.value, 1)
-        comp_gbs = comp_bytes / (comp_ms * 1e-3) / 1e9 if comp_ms > 0 else 0.0
-        stage_gbs = wl["dibr_bytes"] / (stage_ms * 1e-3) / 1e9 if stage_ms > 0 else 0.0
-        depth_ms = tot2.value / max(n2.value, 1)
-        depth_tf = DEPTH_GFLOP[wl["model"]] / max(depth_ms, 1e-9)
-        gemm_ms = g_ms.value / max(g_n.value, 1)
-        gemm_tf = g_gf.value / max(gemm_ms, 1e-9)
-        tf_burst = peaks_burst()
-        line = {
-            "metric": "end-to-end frames/sec (depth+stereo)", "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 GEMM operands, fp32 accumulate; DIBR fp32", "data": "synthetic",
-            "config": {
-                "workload": wl["name"], "frames_per_step": B, "frame_pool": P,
-                "l2_policy": f"inputs+outputs larger than L2 ({in_bytes / 1e6:.0f} MB pool cycled)",
-                "depth_model": f"Depth-Anything-V2 {wl['model']} @518x924, random-init seed 0 (no checkpoints offline), "
-                               "f16 tensor-core operands / fp32 accumulate",
-                "stage": "DPT processor + depth forward + min-max u8 handoff in HBM + DIBR frame loop + pack",
-                "launch_mode": "CUDA graph replay; depth forwards of consecutive frames overlap on three streams "
-                               "(stage timings in roofline* are taken in a separate serial, eager pass)",
-                "params": COMMON, "sharding": "contiguous chunks per rank, independent temporal state per chunk",
-            },
-            "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
-            # dominant kernel of the step: the persistent tcgen05 GEMM (its fc1 launches are timed live with CUDA
-            # events on the engine stream: M = tokens, N = 4*hidden, K = hidden; same kernel runs every linear/conv)
-            "roofline": {"bound": "tensor", "kernel": "k_umma_gemm<128,3> (fc1 launches)",
-                         "achieved": gemm_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": gemm_tf / tf_burst,
-                         "traffic": NCU_GEMM_FC1_TRAFFIC.get(wl["model"]),
-                         "peak_source": which + " (cuBLAS bf16 burst: kernel timed alone)",
-                         "algorithmic_gflop_per_launch": g_gf.value, "avg_launch_ms": gemm_ms, "launches_timed": g_n.value},
-            # the whole depth stage (GEMMs + fused attention + small kernels), serial eager pass
-            "roofline_depth_stage": {"bound": "tensor", "achieved": depth_tf, "peak": tf_peak, "unit": "TFLOP/s",
-                                     "frac": depth_tf / tf_peak, "peak_source": which + " (cuBLAS bf16 sustained)",
-                                     "algorithmic_gflop_per_frame": DEPTH_GFLOP[wl["model"]], "avg_frame_ms": depth_ms,
-                                     "share_of_step": depth_ms / max(depth_ms + stage_ms, 1e-9),
-                                     "achieved_in_timed_region": DEPTH_GFLOP[wl["model"]] * (value / world) / 1000.0,
-                                     "note": "with three frames in flight the timed region sustains "
-                                             "achieved_in_timed_region per GPU"},
-            "roofline_dibr_compose": {"bound": "hbm", "kernel": "k_compose4", "achieved": comp_gbs, "peak": hbm_peak,
-                                      "unit": "GB/s", "frac": comp_gbs / hbm_peak,
-                                      "traffic": NCU_COMPOSE_TRAFFIC.get(args.workload), "peak_source": which,
-                                      "algorithmic_bytes_per_launch": comp_bytes, "avg_launch_ms": comp_ms},
-            "roofline_dibr_stage": {"bound": "hbm", "what": "whole DIBR frame (ingest..pack)", "achieved": stage_gbs,
-                                    "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,
-                                    "algorithmic_bytes_per_frame": wl["dibr_bytes"], "avg_frame_ms": stage_ms},
-        }
         if world == 1 and not args.no_cpu_baseline:
-            fps, n = cpu_port_fps(wl)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": min(32, os.cpu_count()), "kind": "port",
-                                    "sample": f"{n} frames of the workload after 1 warm-up frame; depth forward torch fp32 "
-                                              f"on {min(32, os.cpu_count())} threads + DIBR numpy port on 1 thread"}
+            line["cpu_baseline"] = cpu_baseline_obj(wl)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -142,6 +142,14 @@ int vd3d_profile(vd3d_ctx* ctx, int enable);
 int vd3d_profile_collect(vd3d_ctx* ctx, int stage, double* total_ms, int* count);
 /* replay the per-frame kernel sequence from a captured CUDA graph (default 1) */
 int vd3d_set_graphs(vd3d_ctx* ctx, int enable);
+/* DIBR arithmetic mode.  0 (default): persistent statistics kernel + fused warp/feather/compose/pack kernel, fp32
+ * hardware pow/exp, separable box sums -- inside the 1e-3 / 1-LSB tolerances of the reference's outputs.
+ * 1: one kernel per reference op, correctly rounded transcendentals, the reference's row-major summation order
+ * (bit-for-bit with oracle/dibr.py; what the exactness tests drive).  Env VD3D_EXACT=1 makes 1 the default. */
+int vd3d_set_exact(vd3d_ctx* ctx, int enable);
+int vd3d_get_exact(vd3d_ctx* ctx);
+/* 1 while CUDA-graph replay is on; 0 after vd3d_set_graphs(ctx, 0) or after a failed capture fell back to eager launches */
+int vd3d_graphs_active(vd3d_ctx* ctx);
 
 /* ---- DIBR ------------------------------------------------------------ */
 /* pixel_shift_cuda (core/render_3d.py:561-712).

@@ -2,10 +2,16 @@
 on seeded inputs, against the reference goldens, and through size-independent properties
 at BASELINE sizes.
 
-Tolerances (north_star): uint8 eyes <= 1 LSB; float intermediates <= 1e-3 (we assert
-1e-5: the kernels follow the oracle's rounding op for op; only powf/expf differ by ulps).
-The CUDA path and the oracle share one arithmetic, so the post-chain frames are also
-compared tightly (see test_oracle_golden.py for why reference-vs-anything cannot be).
+Tolerances (north_star): uint8 eyes <= 1 LSB; float intermediates <= 1e-3.
+
+Every oracle / golden comparison runs in both DIBR arithmetic modes (include/vd3d.h: vd3d_set_exact):
+  "fast"  (the default, what bench.py times): persistent stats kernel + fused render kernel, fp32 hardware
+          pow/exp, separable box sums.  Gated at eyes <= 1 LSB with <= 0.5 % of bytes off by one, shift map and
+          scalars <= 2e-5 (50x inside the north-star 1e-3).
+  "exact" one kernel per reference op, correctly rounded transcendentals: follows the oracle's rounding op for
+          op, gated at <= 0.2 % one-LSB flips / 1e-5 / 1e-6 (in practice bit-identical).
+Full frames after apply_sharpening may amplify an isolated one-LSB flip up to 7.7 LSB (kernel centre 5.2/1.2...):
+gated at <= 8 LSB with <= 0.2 % (exact) / 0.5 % (fast) of bytes off by more than one.
 """
 import os
 
@@ -13,7 +19,7 @@ import numpy as np
 import pytest
 
 from oracle import dibr as O
-from tests.util import LOOP_CASES, PS_CASES, u8_diff
+from tests.util import LOOP_CASES, LOOP_CASES_EXTRA, PS_CASES, PS_CASES_EXTRA, u8_diff
 from visiondepth3d_b200.synth import synth_frame
 
 pytestmark = pytest.mark.gpu
@@ -23,6 +29,22 @@ pytestmark = pytest.mark.gpu
 def R():
     from visiondepth3d_b200 import render_3d
     return render_3d
+
+
+MODES = ["fast", "exact"]
+
+
+@pytest.fixture
+def mode(request, R):
+    m = getattr(request, "param", "fast")
+    R._ctx().set_exact(m == "exact")
+    yield m
+    R._ctx().set_exact(False)
+
+
+def _tol(mode):
+    """(scalar abs tol, shift abs tol, max fraction of bytes that may differ by one LSB, by more than one)"""
+    return (1e-6, 1e-5, 0.002, 0.002) if mode == "exact" else (2e-5, 2e-5, 0.005, 0.005)
 
 
 def _ps(R, fr, dp, w, h, kw, infos=None):
@@ -54,7 +76,9 @@ PARAMS = [
 @pytest.mark.parametrize("size", SIZES)
 @pytest.mark.parametrize("pi", range(len(PARAMS)))
 @pytest.mark.parametrize("kind", ["smooth", "noise"])
-def test_pixel_shift_vs_oracle(R, size, pi, kind):
+@pytest.mark.parametrize("mode", MODES, indirect=True)
+def test_pixel_shift_vs_oracle(R, size, pi, kind, mode):
+    ts, tsh, tf0, _ = _tol(mode)
     w, h, iw, ih = size
     kw = PARAMS[pi]
     R.reset_temporal_state()
@@ -67,20 +91,21 @@ def test_pixel_shift_vs_oracle(R, size, pi, kind):
         ol, orr, os_, parts = O.pixel_shift(gs, O.bgr_to_rgb01(fr), O.depth_bgr_to_01(dp), w, h, p,
                                             return_parts=True)
         inf = infos[0]
-        assert inf.subj_raw == pytest.approx(float(parts["subj_raw"]), abs=1e-6)
-        assert inf.stretch_lo == pytest.approx(float(parts["lo"]), abs=1e-6)
-        assert inf.stretch_hi == pytest.approx(float(parts["hi"]), abs=1e-6)
+        assert inf.subj_raw == pytest.approx(float(parts["subj_raw"]), abs=ts)
+        assert inf.stretch_lo == pytest.approx(float(parts["lo"]), abs=ts)
+        assert inf.stretch_hi == pytest.approx(float(parts["hi"]), abs=ts)
         assert inf.subj_shaped == pytest.approx(float(parts["subj"]), abs=2e-5)
-        assert inf.zero_parallax_offset == pytest.approx(parts["zpo"], abs=1e-7)
-        assert np.abs(s.numpy() - os_).max() <= 1e-5
+        assert inf.zero_parallax_offset == pytest.approx(parts["zpo"], abs=1e-7 if mode == "exact" else 1e-6)
+        assert np.abs(s.numpy() - os_).max() <= tsh
         for mine, ref in ((l, ol), (r, orr)):
             mx, f0, f1 = u8_diff(mine, ref)
-            assert mx <= 1 and f0 <= 0.002, (size, pi, kind, i, mx, f0)
+            assert mx <= 1 and f0 <= tf0, (size, pi, kind, i, mode, mx, f0)
 
 
-@pytest.mark.parametrize("name", sorted(PS_CASES))
-def test_pixel_shift_vs_reference_golden(R, golden_dir, name):
-    c = PS_CASES[name]
+@pytest.mark.parametrize("name", sorted(PS_CASES) + sorted(PS_CASES_EXTRA))
+@pytest.mark.parametrize("mode", MODES, indirect=True)
+def test_pixel_shift_vs_reference_golden(R, golden_dir, name, mode):
+    c = {**PS_CASES, **PS_CASES_EXTRA}[name]
     g = np.load(os.path.join(golden_dir, name))
     R.reset_temporal_state()
     for i in range(c["n"]):
@@ -104,9 +129,11 @@ def _rp(R, d, w, h):
         o.color_brightness), o
 
 
-@pytest.mark.parametrize("name", sorted(LOOP_CASES))
-def test_render_loop_vs_oracle_and_golden(R, golden_dir, name):
-    c = LOOP_CASES[name]
+@pytest.mark.parametrize("name", sorted(LOOP_CASES) + sorted(LOOP_CASES_EXTRA))
+@pytest.mark.parametrize("mode", MODES, indirect=True)
+def test_render_loop_vs_oracle_and_golden(R, golden_dir, name, mode):
+    ts, _, tf0, tf1 = _tol(mode)
+    c = {**LOOP_CASES, **LOOP_CASES_EXTRA}[name]
     g = np.load(os.path.join(golden_dir, name))
     rp, orp = _rp(R, c["rp"], c["sw"], c["sh"])
     R.reset_temporal_state()
@@ -117,13 +144,13 @@ def test_render_loop_vs_oracle_and_golden(R, golden_dir, name):
         ref, parts = O.render_frame(gs, cs, fr, dp, orp, return_parts=True)
         assert out.shape == ref.shape
         assert inf.dyn_scale == pytest.approx(parts["dyn"], abs=1e-6)
-        assert inf.focal_depth == pytest.approx(parts["focal"], abs=1e-6)
-        assert inf.stable_zero == pytest.approx(parts["stable_zero"], abs=1e-7)
+        assert inf.focal_depth == pytest.approx(parts["focal"], abs=ts)
+        assert inf.stable_zero == pytest.approx(parts["stable_zero"], abs=1e-7 if mode == "exact" else 1e-6)
         assert inf.bar_width == parts["bar"]
         assert inf.pct_lo == pytest.approx(float(gs.pct_lo), abs=1e-6)
         assert inf.pct_hi == pytest.approx(float(gs.pct_hi), abs=1e-6)
         mx, f0, f1 = u8_diff(out, ref)
-        assert mx <= 8 and f1 <= 0.002 and f0 <= 0.01, (name, j, mx, f0, f1)
+        assert mx <= 8 and f1 <= tf1 and f0 <= 0.01, (name, mode, j, mx, f0, f1)
         mx, f0, f1 = u8_diff(out, g[f"final{j}"])  # vs the real reference: see test_oracle_golden docstring
         assert mx <= 12 and f1 <= 0.03, (name, j, mx, f0, f1)
 
@@ -169,7 +196,14 @@ def test_stage_sharpen_and_dof(R):
     assert mx <= 1 and f0 <= 0.002
 
 
-def test_edge_cases(R):
+@pytest.mark.parametrize("mode", MODES, indirect=True)
+def test_edge_cases(R, mode):
+    def same(a, b):
+        if mode == "exact":
+            return np.array_equal(a, b)
+        mx, f0, f1 = u8_diff(a, b)
+        return a.shape == b.shape and mx <= 8 and f1 <= 0.005
+
     # flat depth: both percentile guards trip (core/render_3d.py:252-253, 538-540), subject fallback 0.5
     fr = np.full((90, 160, 3), 128, dtype=np.uint8)
     dp = np.full((90, 160, 3), 77, dtype=np.uint8)
@@ -179,7 +213,7 @@ def test_edge_cases(R):
     for _ in range(2):
         out, inf = R.render_frame(fr, dp, rp, want_info=True)
         ref = O.render_frame(gs, cs, fr, dp, orp)
-        assert np.array_equal(out, ref)
+        assert same(out, ref)
     assert gs.pct_lo is None and inf.pct_lo == 0.0
     # black and white frames
     for v in (0, 255):
@@ -187,7 +221,7 @@ def test_edge_cases(R):
         dp[:] = v
         R.reset_temporal_state()
         gs, cs = O.GlobalState(), O.ClipState()
-        assert np.array_equal(R.render_frame(fr, dp, rp), O.render_frame(gs, cs, fr, dp, orp))
+        assert same(R.render_frame(fr, dp, rp), O.render_frame(gs, cs, fr, dp, orp))
     # single-channel depth == grey BGR depth
     f2, d2 = synth_frame(2, 160, 90, "smooth")
     R.reset_temporal_state()
@@ -203,11 +237,15 @@ def test_edge_cases(R):
     out = R.render_frame(f3, d3, rp3)
     ref = O.render_frame(gs, cs, f3, d3, orp3)
     mx, f0, f1 = u8_diff(out, ref)
-    assert out.shape == ref.shape and mx <= 8 and f1 <= 0.002
+    assert out.shape == ref.shape and mx <= 8 and f1 <= 0.005
+
+
+_FULL_SIZE_ORACLE = {}
 
 
 @pytest.mark.parametrize("cfg", ["1080p_halfsbs", "4k_fullsbs"])
-def test_full_size_properties(R, cfg):
+@pytest.mark.parametrize("mode", MODES, indirect=True)
+def test_full_size_properties(R, cfg, mode):
     """BASELINE sizes: oracle comparison on one frame (seconds on CPU) plus properties."""
     if cfg == "1080p_halfsbs":
         sw, sh = 1920, 1080
@@ -223,13 +261,16 @@ def test_full_size_properties(R, cfg):
     fr, dp = synth_frame(1, sw, sh, "smooth")
     R.reset_temporal_state()
     out, inf = R.render_frame(fr, dp, rp, want_info=True)
-    gs, cs = O.GlobalState(), O.ClipState()
-    ref, parts = O.render_frame(gs, cs, fr, dp, orp, return_parts=True)
+    if cfg not in _FULL_SIZE_ORACLE:  # the CPU oracle takes a minute at 4K: computed once for both modes
+        gs, cs = O.GlobalState(), O.ClipState()
+        ref, parts = O.render_frame(gs, cs, fr, dp, orp, return_parts=True)
+        _FULL_SIZE_ORACLE[cfg] = (ref, parts, float(gs.pct_lo))
+    ref, parts, pct_lo = _FULL_SIZE_ORACLE[cfg]
     assert out.shape == ref.shape == ((1080, 1920, 3) if cfg == "1080p_halfsbs" else (2160, 7680, 3))
     assert inf.dyn_scale == pytest.approx(parts["dyn"], abs=1e-6)
-    assert inf.pct_lo == pytest.approx(float(gs.pct_lo), abs=1e-6)
+    assert inf.pct_lo == pytest.approx(pct_lo, abs=1e-6)
     mx, f0, f1 = u8_diff(out, ref)
-    assert mx <= 8 and f1 <= 0.002 and f0 <= 0.01, (mx, f0, f1)
+    assert mx <= 8 and f1 <= _tol(mode)[3] and f0 <= 0.01, (mode, mx, f0, f1)
     # property: zero shifts -> both eyes identical
     d0 = dict(d, fg_shift=0.0, mg_shift=0.0, bg_shift=0.0, use_subject_tracking=False, use_floating_window=False)
     rp0, _ = _rp(R, d0, sw, sh)
@@ -286,3 +327,54 @@ def test_heal_missing_pixels(R, golden_dir):
     w = rng.random((3, 37, 53), dtype=np.float32)
     o = rng.random((3, 37, 53), dtype=np.float32)
     assert np.array_equal(R.heal_missing_pixels(w, None, o, None, 0.8), O.heal_missing_pixels(w, o, None, 0.8))
+
+
+def _clip(ctx, rp, frames, h, w):
+    import ctypes as C
+    from visiondepth3d_b200 import _lib
+    n = len(frames)
+    rp_, _ = rp
+    from visiondepth3d_b200 import render_3d as R_
+    pl = R_.plan_sizes(w, h, rp_)
+    outs = [np.empty(R_.output_shape(rp_, pl), dtype=np.uint8) for _ in range(n)]
+    fp = (C.c_void_p * n)(*[f.ctypes.data for f, _ in frames])
+    dp = (C.c_void_p * n)(*[d.ctypes.data for _, d in frames])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    ctx.check(ctx.lib.vd3d_render_clip(ctx.h, n, fp, dp, 3, h, w, C.byref(rp_), op, _lib.MEM_HOST, None))
+    return outs
+
+
+@pytest.mark.parametrize("mode", MODES, indirect=True)
+def test_graph_replay_survives_other_entry_points(R, mode):
+    """captured frame graphs bake in device pointers and host-cached tables (linspace axes, INTER_AREA
+    tables, workspaces).  Another entry point at another size in between must not leave stale graphs behind:
+    clip(A) -> render_frame(B) / pixel_shift(B) / fit_eye -> clip(A) equals the same sequence launched eagerly."""
+    from visiondepth3d_b200 import _lib
+    ctx = _lib.default_context(0)
+    rpA = _rp(R, LOOP_CASES["loop_halfsbs_320x180.npz"]["rp"], 320, 180)
+    rpB = _rp(R, dict(LOOP_CASES["loop_halfsbs_320x180.npz"]["rp"], output_width=256, output_height=144,
+                      output_format="Full-SBS", preserve_original_aspect=True), 256, 144)
+    fa = [synth_frame(i, 320, 180, "smooth") for i in range(16)]
+    fb, db = synth_frame(3, 256, 144, "smooth")
+    img = np.random.default_rng(5).integers(0, 256, (270, 480, 3), dtype=np.uint8)
+
+    def sequence():
+        R.reset_temporal_state()
+        res = _clip(ctx, rpA, fa[:8], 180, 320)          # 3 eager frames, then captured graphs
+        res.append(R.render_frame(fb, db, rpB[0]))        # other size: axes, workspaces, state planes
+        l, r, s = _ps(R, fb, db, 400, 226, dict(blur_ksize=5, feather_strength=4.0))
+        res += [l, r]
+        res.append(R.pad_to_aspect_ratio(img, 360, 400))  # INTER_AREA tables
+        res += _clip(ctx, rpA, fa[8:], 180, 320)
+        return res
+
+    ctx.check(ctx.lib.vd3d_set_graphs(ctx.h, 1))
+    with_graphs = sequence()
+    ctx.check(ctx.lib.vd3d_set_graphs(ctx.h, 0))
+    try:
+        eager = sequence()
+    finally:
+        ctx.check(ctx.lib.vd3d_set_graphs(ctx.h, 1))
+    assert len(with_graphs) == len(eager)
+    for k, (a, b) in enumerate(zip(with_graphs, eager)):
+        assert np.array_equal(a, b), k

@@ -33,7 +33,7 @@ def test_fit_eye_matches_oracle(R, case):
         assert np.array_equal(R.resize_area(img, tw, th), O.resize_area(img, tw, th)), case
 
 
-@pytest.mark.skipif(os.environ.get("VD3D_FIT_ENLARGE") == "1", reason="enlarging enabled")
+@pytest.mark.skipif(os.environ.get("VD3D_FIT_ENLARGE") != "0", reason="enlarging fits are on by default")
 def test_fit_eye_rejects_enlarging(R):
     from visiondepth3d_b200._lib import Vd3dError
     img = np.zeros((90, 160, 3), dtype=np.uint8)
@@ -43,8 +43,7 @@ def test_fit_eye_rejects_enlarging(R):
     assert R.pad_to_aspect_ratio(img, 160, 90).shape == (90, 160, 3)
 
 
-@pytest.mark.skipif(os.environ.get("VD3D_FIT_ENLARGE") != "1",
-                    reason="enlarging fits are opt-in until this test has been run on a B200 (DESIGN.md section 9)")
+@pytest.mark.skipif(os.environ.get("VD3D_FIT_ENLARGE") == "0", reason="enlarging fits switched off")
 @pytest.mark.parametrize("case", [(1280, 720, 1920, 1080), (160, 90, 1440, 1600), (100, 70, 133, 91), (100, 70, 80, 140)])
 def test_fit_eye_enlarge_matches_oracle(R, case):
     """cv2 INTER_AREA with an enlarged axis = fixed-point bilinear emulation; integer arithmetic, exact."""

@@ -80,6 +80,7 @@ class FrameInfo(C.Structure):
 SYMBOLS = [
     "vd3d_create", "vd3d_destroy", "vd3d_last_error", "vd3d_reset_state", "vd3d_host_alloc",
     "vd3d_host_free", "vd3d_stream", "vd3d_sync", "vd3d_launch_count", "vd3d_set_graphs",
+    "vd3d_set_exact", "vd3d_get_exact", "vd3d_graphs_active",
     "vd3d_pixel_shift", "vd3d_plan_sizes", "vd3d_render_frame", "vd3d_render_clip",
     "vd3d_sharpen", "vd3d_dof_grade", "vd3d_struct_size", "vd3d_pack", "vd3d_fit_eye", "vd3d_area_table", "vd3d_area_linear_table", "vd3d_heal",
     "vd3d_profile", "vd3d_profile_collect",
@@ -135,6 +136,12 @@ def load():
     lib.vd3d_profile_collect.restype = i
     lib.vd3d_set_graphs.argtypes = [vp, i]
     lib.vd3d_set_graphs.restype = i
+    lib.vd3d_set_exact.argtypes = [vp, i]
+    lib.vd3d_set_exact.restype = i
+    lib.vd3d_get_exact.argtypes = [vp]
+    lib.vd3d_get_exact.restype = i
+    lib.vd3d_graphs_active.argtypes = [vp]
+    lib.vd3d_graphs_active.restype = i
     lib.vd3d_pixel_shift.argtypes = [vp, fp, fp, i, i, i, i, C.POINTER(ShiftParams), u8p, u8p, fp, i,
                                      C.POINTER(FrameInfo)]
     lib.vd3d_pixel_shift.restype = i
@@ -199,6 +206,10 @@ class Context:
 
     def reset(self, which=STATE_GLOBAL | STATE_CLIP):
         self.check(self.lib.vd3d_reset_state(self.h, which))
+
+    def set_exact(self, enable=True):
+        """DIBR arithmetic mode (include/vd3d.h: vd3d_set_exact): True = bit-for-bit with the oracle."""
+        self.check(self.lib.vd3d_set_exact(self.h, int(bool(enable))))
 
     def export_state(self):
         """Temporal state after the last frame as a uint8 numpy blob (SURVEY 8(e) exact sharding)."""

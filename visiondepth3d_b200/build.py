@@ -14,6 +14,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path
 # op at a time, so FMA contraction is off there and fused ops are spelled __fmaf_rn.
 UNITS = [
     ("dibr_kernels.cu", ["-fmad=false"]),
+    ("dibr_fast.cu", ["-fmad=false"]),
     ("vd3d_api.cu", ["-fmad=false"]),
     ("depth_kernels.cu", []),
     ("depth_engine.cu", []),

@@ -56,6 +56,7 @@ struct vd3d_depth {
   bool planned = false;
   bool flash = true;  // fused attention kernel (VD3D_FLASH=0 selects the 3-kernel path)
   bool owns_weights = true;  // clones share the weight tensors of their parent
+  uint64_t weights_version = 0;  // bumped whenever a weight tensor moves (clones / captured graphs hold raw pointers)
   // optional device timing of one GEMM class (the fc1 launches) for the roofline report
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -319,14 +320,29 @@ void vd3d_depth_add_launches(vd3d_depth* e, uint64_t n) {
 
 int vd3d_depth_set_tensor(vd3d_depth* e, const char* name, const void* host_data, size_t bytes) {
   if (!e || !name || !host_data || !bytes) return VD3D_ERR_ARG;
+  if (!e->owns_weights) return dfail(e, VD3D_ERR_STATE, "weights of an engine clone belong to its parent");
   DTensor& t = e->w[name];
-  if (t.p) cudaFree(t.p);
+  const size_t cap = (bytes + 255) / 256 * 256;
+  if (t.p && (t.bytes + 255) / 256 * 256 == cap) {
+    // same footprint: overwrite in place so that clones and captured graphs (raw pointers) stay valid; work already
+    // enqueued on any stream finishes first
+    DCK(cudaDeviceSynchronize());
+    t.bytes = bytes;
+    DCK(cudaMemcpy(t.p, host_data, bytes, cudaMemcpyHostToDevice));
+    return VD3D_OK;
+  }
+  if (t.p) {
+    DCK(cudaDeviceSynchronize());
+    cudaFree(t.p);
+  }
   t.p = nullptr;
-  DCK(cudaMalloc(&t.p, (bytes + 255) / 256 * 256));
+  e->weights_version++;  // the tensor moves: vd3d_ctx rebuilds its clones and drops its graphs (vd3d_api.cu)
+  DCK(cudaMalloc(&t.p, cap));
   t.bytes = bytes;
   DCK(cudaMemcpy(t.p, host_data, bytes, cudaMemcpyHostToDevice));
   return VD3D_OK;
 }
+uint64_t vd3d_depth_weights_version(vd3d_depth* e) { return e ? e->weights_version : 0; }
 
 int vd3d_depth_get_buffer(vd3d_depth* e, const char* name, void* host_out, size_t bytes) {
   if (!e || !name || !host_out) return VD3D_ERR_ARG;

@@ -387,6 +387,8 @@ __global__ void __launch_bounds__(256) k_shape(float* __restrict__ d, int n, con
 // ---------------------------------------------------------------------------
 // K5 shift map + suppress_artifacts_with_edge_mask (core/render_3d.py:198-216,620-680)
 // ---------------------------------------------------------------------------
+// FAST: fp32 SFU exp / sqrt instead of the correctly rounded fp64 forms (<= 2e-7 on the mask and the fg weight)
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_shift(const float* __restrict__ d, float* __restrict__ shift, int H, int W,
                                                const FrameScalars* fs, int edge_mask, float feather) {
   __shared__ float sd[13][38];   // d over x in [bx-3, bx+34), y in [by-3, by+10)
@@ -412,7 +414,8 @@ __global__ void __launch_bounds__(256) k_shift(const float* __restrict__ d, floa
         float dy = (gy > 0) ? fabsf(c - sd[ty][tx + 1]) : 0.f;
         float g = sqrtf((dx * dx) + (dy * dy));
         float z = ((g - 0.02f) * feather) * 5.0f;
-        float e = 1.0f / (1.0f + (float)exp((double)(-z)));  // exp correctly rounded via fp64
+        float e = FAST ? (1.0f / (1.0f + __expf(-z)))
+                       : (1.0f / (1.0f + (float)exp((double)(-z))));  // exp correctly rounded via fp64
         m = 1.0f - e;
       }
       sm[ty][tx] = m;
@@ -423,8 +426,14 @@ __global__ void __launch_bounds__(256) k_shift(const float* __restrict__ d, floa
   int x = bx + lx, y = by + ly;
   if (x >= W || y >= H) return;
   float v = edge_mask ? sd[ly + 3][lx + 3] : d[(size_t)y * W + x];
-  double omv = (double)(1.0f - v);
-  float fgw = clamp01((float)(omv * sqrt(omv)));  // (1-d)^1.5, correctly rounded via fp64
+  float fgw;
+  if (FAST) {
+    float o1 = 1.0f - v;
+    fgw = clamp01(o1 * sqrtf(o1));
+  } else {
+    double omv = (double)(1.0f - v);
+    fgw = clamp01((float)(omv * sqrt(omv)));  // (1-d)^1.5, correctly rounded via fp64
+  }
   float mgw = clamp01(1.0f - (fabsf(v - fs->c_mid) * 3.0f));
   float bgw = clamp01(v);
   float raw = (((fgw * fs->c_fg) * fs->c_fgm) + (mgw * fs->c_mg)) + ((bgw * fs->c_bg) * fs->c_bgm);
@@ -1032,7 +1041,11 @@ void launch_fin_shape(const SelJob& sj, const ShiftArgs& sa, DevState* st, Frame
 }
 void launch_shift(const float* d, float* shift, int H, int W, const FrameScalars* fs, int edge_mask, float feather,
                   cudaStream_t s) {
-  k_shift<<<grid2d(W, H), 256, 0, s>>>(d, shift, H, W, fs, edge_mask, feather);
+  k_shift<false><<<grid2d(W, H), 256, 0, s>>>(d, shift, H, W, fs, edge_mask, feather);
+}
+void launch_shift_fast(const float* d, float* shift, int H, int W, const FrameScalars* fs, int edge_mask, float feather,
+                       cudaStream_t s) {
+  k_shift<true><<<grid2d(W, H), 256, 0, s>>>(d, shift, H, W, fs, edge_mask, feather);
 }
 void launch_warp_edges(const float* d, const float* shift, float2* e2, int H, int W, const float* xs,
                        const float* ys, float feather, cudaStream_t s) {

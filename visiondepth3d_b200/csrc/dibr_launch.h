@@ -128,4 +128,59 @@ void launch_post(const PostArgs& a, cudaStream_t s);
 void launch_heal(const float* warped, const float* orig, const float* edge, float* out, int H, int W, float hs,
                  cudaStream_t s);
 
+// ---- fast path (dibr_fast.cu) ------------------------------------------------------------------------------------
+struct JobMem {  // device memory of one selection job
+  uint32_t* hist1;   // [4096]
+  uint32_t* hist2;   // [4][4096]
+  uint32_t* hist3;   // [4][64]
+  uint32_t* hist64;  // [64]
+  uint32_t* count;
+  SelTarget* tg;     // [4] (exact path only)
+};
+
+struct StatsArgs {
+  int loop;          // 1: one render_sbs_3d loop iteration (from ingest); 0: pixel_shift_cuda entry (from d0)
+  IngestArgs ia;     // loop only; ia.rgb_s unused
+  float4* rgbx_s;    // [th, tw] RGBx of the frame resized to target_eye (null on the identity path)
+  float4* rgbx;      // [H, W] RGBx upsampled to the warp resolution (null when not needed)
+  float* dn;         // normalised depth of this frame [th, tw]
+  const float* dn_prev;
+  const float* core_depth;  // source of d0 [sh, sw] (== dn in loop mode)
+  int sh, sw;
+  float* d;          // [H, W] d0 -> shaped depth (in place)
+  int H, W;
+  const float* xs;
+  const float* ys;
+  LoopArgs la;
+  ShiftArgs sa;
+  uint32_t pct_rank[4];
+  float pct_wlo, pct_whi;
+  uint32_t q_rank[4];
+  float q_wlo, q_whi;
+  JobMem jm[5];
+  DevState* st;
+  FrameScalars* fs;  // zeroed by the host before the launch (the centre / motion sums accumulate into it)
+  unsigned* bar;     // grid barrier counter, zeroed by the host before the launch
+};
+
+struct RenderArgs {
+  ComposeArgs c;           // c.e2 unused; c.left / c.right only when fuse == 0
+  const float4* src_rgbx;  // [H, W] RGBx source (resize paths); else c.src_u8 or c.src_f32
+  const float* d;          // shaped depth [H, W]
+  float feather_strength;
+  int fuse;                // 0: write eyes; 1: bars + sharpen + 1:1 fit + SBS pack; 2: same with the 2:1 Half-SBS fit
+  const FrameScalars* fs;  // bars (fuse != 0; may be null)
+  int sharpen;
+  float kc, ke;
+  uint8_t* out;
+  int out_w, per_eye_w;    // packed row length in pixels; width of one eye in the packed frame
+};
+
+bool render_supports(int feather, int k);
+cudaError_t launch_render(const RenderArgs& a, cudaStream_t s);
+cudaError_t stats_grid(int device, int* blocks);
+cudaError_t launch_stats(const StatsArgs& a, int blocks, cudaStream_t s);
+void launch_shift_fast(const float* d, float* shift, int H, int W, const FrameScalars* fs, int edge_mask, float feather,
+                       cudaStream_t s);
+
 }  // namespace vd3d

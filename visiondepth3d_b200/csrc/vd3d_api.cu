@@ -23,18 +23,10 @@ struct Buf {
   size_t cap = 0;
 };
 
-struct JobMem {  // device memory of one selection job
-  uint32_t* hist1;
-  uint32_t* hist2;
-  uint32_t* hist3;
-  uint32_t* hist64;
-  uint32_t* count;
-  SelTarget* tg;
-};
-
 constexpr int kSlots = 3;  // frames in flight (staging buffers, depth streams)
 constexpr int kJobs = 5;  // pct, subj(norm), quantile(d0), subj(d0), subj(shaped)
 constexpr size_t kJobWords = 4096 + 4 * 4096 + 4 * 64 + 64 + 64;  // + count (padded)
+constexpr size_t kBarWords = 64;
 
 }  // namespace
 
@@ -45,6 +37,14 @@ struct vd3d_ctx {
   uint64_t launches = 0;
   int use_graphs = 1;
   int stats_only = 0;  // advance temporal state only (exact multi-GPU sharding: SURVEY 8(e))
+  int exact = 0;       // 1: one-kernel-per-op path with correctly rounded transcendentals (dibr_kernels.cu);
+                       // 0: persistent stats kernel + fused render kernel (dibr_fast.cu)
+  int stats_blocks = 0;
+  // bumped whenever a device resource that captured graphs bake in moves or changes content (ensure() reallocations,
+  // linspace axes, INTER_AREA tables, DOF kernel bank); run_frame_slot drops stale graphs
+  uint64_t res_epoch = 0, fg_epoch = 0;
+  uint64_t dclone_wver = 0;
+  unsigned* bar = nullptr;  // grid barrier counter of k_stats (inside jobwords: zeroed by begin_frame)
 
   DevState* st = nullptr;
   FrameScalars* fs = nullptr;
@@ -99,6 +99,7 @@ struct vd3d_ctx {
 };
 
 extern "C" {
+uint64_t vd3d_depth_weights_version(vd3d_depth* e);
 static void drop_graphs(vd3d_ctx* ctx);
 static void drop_depth_graphs(vd3d_ctx* ctx);
 int vd3d_depth_clone(vd3d_depth* e, void* cuda_stream, vd3d_depth** out);
@@ -154,9 +155,13 @@ int fail(vd3d_ctx* ctx, int code, const char* msg) {
 
 int ensure(vd3d_ctx* ctx, Buf& b, size_t bytes) {
   if (b.cap >= bytes) return VD3D_OK;
-  if (b.p) CK(cudaFree(b.p));
+  if (b.p) {
+    CK(cudaDeviceSynchronize());  // frames still in flight (other streams, graph replays) may read the old block
+    CK(cudaFree(b.p));
+  }
   b.p = nullptr;
   b.cap = 0;
+  ctx->res_epoch++;
   CK(cudaMalloc(&b.p, bytes));
   b.cap = bytes;
   return VD3D_OK;
@@ -176,6 +181,7 @@ void linspace32(float start, float end, int n, std::vector<float>& out) {
 
 int ensure_axes(vd3d_ctx* ctx, int W, int H) {
   std::vector<float> v;
+  if (ctx->xs_n != W || ctx->ys_n != H) CK(cudaDeviceSynchronize());  // queued frames may still read the old axes
   if (ctx->xs_n != W) {
     int r = ensure(ctx, ctx->xs, sizeof(float) * W);
     if (r) return r;
@@ -183,6 +189,7 @@ int ensure_axes(vd3d_ctx* ctx, int W, int H) {
     CK(cudaMemcpyAsync(ctx->xs.p, v.data(), sizeof(float) * W, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->xs_n = W;
+    ctx->res_epoch++;
   }
   if (ctx->ys_n != H) {
     int r = ensure(ctx, ctx->ys, sizeof(float) * H);
@@ -191,6 +198,7 @@ int ensure_axes(vd3d_ctx* ctx, int W, int H) {
     CK(cudaMemcpyAsync(ctx->ys.p, v.data(), sizeof(float) * H, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ys_n = H;
+    ctx->res_epoch++;
   }
   return VD3D_OK;
 }
@@ -323,8 +331,138 @@ int run_core(vd3d_ctx* ctx, const CoreIn& in) {
   return VD3D_OK;
 }
 
+// ---------------------------------------------------------------------------
+// fast path (dibr_fast.cu): k_stats -> k_shift<fast> -> k_render
+// ---------------------------------------------------------------------------
+struct FastLoop {  // loop-level inputs of k_stats (null for the pixel_shift_cuda entry)
+  const IngestArgs* ia;
+  float4* rgbx_s;
+  float4* rgbx;
+  float* dn;
+  const float* dn_prev;
+  const LoopArgs* la;
+};
+struct FastPost {  // fused bars + sharpen + fit + pack (fuse == 0: write the eyes)
+  int fuse = 0;
+  int sharpen = 0;
+  float kc = 0.f, ke = 0.f;
+  uint8_t* out = nullptr;
+  int out_w = 0, per_eye_w = 0;
+  const float4* src_rgbx = nullptr;
+};
+
+int run_core_fast(vd3d_ctx* ctx, const CoreIn& in, const FastLoop* lp, const FastPost& post) {
+  cudaStream_t s = ctx->stream;
+  const int W = in.W, H = in.H;
+  int r;
+  if ((r = ensure_axes(ctx, W, H))) return r;
+  if ((r = ensure(ctx, ctx->d, sizeof(float) * (size_t)W * H))) return r;
+  if ((r = ensure(ctx, ctx->shift, sizeof(float) * (size_t)W * H))) return r;
+  const float* xs = (const float*)ctx->xs.p;
+  const float* ys = (const float*)ctx->ys.p;
+  float* d = (float*)ctx->d.p;
+  float* shift = (float*)ctx->shift.p;
+  int feather = in.p.enable_feathering ? 1 : 0;
+  if (feather && (in.p.blur_ksize < 1 || in.p.blur_ksize > 63))
+    return fail(ctx, VD3D_ERR_UNSUPPORTED, "blur_ksize must be in [1,63]");
+
+  StatsArgs sa;
+  memset(&sa, 0, sizeof sa);
+  sa.loop = lp ? 1 : 0;
+  if (lp) {
+    sa.ia = *lp->ia;
+    sa.rgbx_s = lp->rgbx_s;
+    sa.rgbx = lp->rgbx;
+    sa.dn = lp->dn;
+    sa.dn_prev = lp->dn_prev;
+    sa.la = *lp->la;
+    quantile_rank(0.02, (long long)lp->ia->tw * lp->ia->th, sa.pct_rank[0], sa.pct_rank[1], sa.pct_wlo);
+    quantile_rank(0.98, (long long)lp->ia->tw * lp->ia->th, sa.pct_rank[2], sa.pct_rank[3], sa.pct_whi);
+  }
+  sa.core_depth = in.depth;
+  sa.sh = in.sh;
+  sa.sw = in.sw;
+  sa.d = d;
+  sa.H = H;
+  sa.W = W;
+  sa.xs = xs;
+  sa.ys = ys;
+  sa.sa.p = in.p;
+  sa.sa.W = W;
+  sa.sa.H = H;
+  quantile_rank(in.p.depth_stretch_lo, (long long)W * H, sa.q_rank[0], sa.q_rank[1], sa.q_wlo);
+  quantile_rank(in.p.depth_stretch_hi, (long long)W * H, sa.q_rank[2], sa.q_rank[3], sa.q_whi);
+  for (int j = 0; j < kJobs; ++j) sa.jm[j] = ctx->jm[j];
+  sa.st = ctx->st;
+  sa.fs = ctx->fs;
+  sa.bar = ctx->bar;
+  CK(launch_stats(sa, ctx->stats_blocks, s));
+  ctx->launches += 1;
+  if (ctx->stats_only) return VD3D_OK;
+  launch_shift_fast(d, shift, H, W, ctx->fs, in.p.enable_edge_masking ? 1 : 0, (float)in.p.feather_strength, s);
+  ctx->launches += 1;
+
+  ComposeArgs ca;
+  memset(&ca, 0, sizeof ca);
+  ca.src_u8 = in.src_u8;
+  ca.src_pitch = in.src_pitch;
+  ca.cx0 = in.cx0;
+  ca.cy0 = in.cy0;
+  ca.src_f32 = in.src_f32;
+  ca.shift = shift;
+  ca.xs = xs;
+  ca.ys = ys;
+  ca.H = H;
+  ca.W = W;
+  ca.k = in.p.blur_ksize;
+  ca.feather = feather;
+  ca.grade = in.grade;
+  ca.sat = in.sat;
+  ca.con = in.con;
+  ca.bri = in.bri;
+  ca.left = in.left;
+  ca.right = in.right;
+  if (render_supports(feather, in.p.blur_ksize)) {
+    RenderArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.c = ca;
+    ra.src_rgbx = post.src_rgbx;
+    ra.d = d;
+    ra.feather_strength = (float)in.p.feather_strength;
+    ra.fuse = post.fuse;
+    ra.fs = ctx->fs;
+    ra.sharpen = post.sharpen;
+    ra.kc = post.kc;
+    ra.ke = post.ke;
+    ra.out = post.out;
+    ra.out_w = post.out_w;
+    ra.per_eye_w = post.per_eye_w;
+    {
+      ProfScope ps(ctx, 1);
+      CK(launch_render(ra, s));
+    }
+    ctx->launches += 1;
+  } else {
+    // even / large box sizes: the generic kernels of the exact path (callers never request fuse for these)
+    if (post.src_rgbx) return fail(ctx, VD3D_ERR_STATE, "generic compose needs planar RGB");
+    if (feather) {
+      if ((r = ensure(ctx, ctx->e2, sizeof(float2) * (size_t)W * H))) return r;
+      launch_warp_edges(d, shift, (float2*)ctx->e2.p, H, W, xs, ys, (float)in.p.feather_strength, s);
+      ctx->launches += 1;
+    }
+    ca.e2 = (const float2*)ctx->e2.p;
+    {
+      ProfScope ps(ctx, 1);
+      launch_compose(ca, s);
+    }
+    ctx->launches += 1;
+  }
+  CK(cudaGetLastError());
+  return VD3D_OK;
+}
+
 int begin_frame(vd3d_ctx* ctx) {
-  CK(cudaMemsetAsync(ctx->jobwords, 0, sizeof(uint32_t) * kJobs * kJobWords, ctx->stream));
+  CK(cudaMemsetAsync(ctx->jobwords, 0, sizeof(uint32_t) * (kJobs * kJobWords + kBarWords), ctx->stream));
   CK(cudaMemsetAsync(ctx->fs, 0, sizeof(FrameScalars), ctx->stream));
   return VD3D_OK;
 }
@@ -387,10 +525,12 @@ int ensure_dof_kernels(vd3d_ctx* ctx, double max_sigma, int num_levels) {
     }
   }
   if (all.empty()) all.push_back(1.f);
+  CK(cudaDeviceSynchronize());
   int r = ensure(ctx, ctx->dof_kern, sizeof(float) * all.size());
   if (r) return r;
   CK(cudaMemcpyAsync(ctx->dof_kern.p, all.data(), sizeof(float) * all.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->res_epoch++;
   ctx->dof_sigma_cached = max_sigma;
   ctx->dof_nlevels = num_levels;
   ctx->dof_halo = halo;
@@ -520,6 +660,7 @@ int ensure_area_tabs(vd3d_ctx* ctx, int which, int W, int H, int nw, int nh, Fit
     key[2] = nw;
     key[3] = nh;
     ctx->at_t[which] = T;
+    ctx->res_epoch++;
   }
   const int* ip = (const int*)tab.p;
   f.xofs = ip;
@@ -562,12 +703,12 @@ int plan_fit(vd3d_ctx* ctx, int fmt, int W, int H, int pw, int ph, FitPlan& f, i
     return VD3D_OK;
   }
   if (nw > W || nh > H) {
-    // cv2 switches INTER_AREA to a fixed-point bilinear scheme as soon as one axis grows.  The k_post branch for it is
-    // written against the cv2-pinned oracle but has not been run on a GPU yet: opt-in until it has
+    // cv2 switches INTER_AREA to a fixed-point bilinear scheme as soon as one axis grows (e.g. the hard-coded
+    // 1920x1080 Full-SBS eyes for sources below 1080p, core/render_3d.py:1121).  VD3D_FIT_ENLARGE=0 rejects these.
     static int enlarge = -1;
     if (enlarge < 0) {
       const char* v = getenv("VD3D_FIT_ENLARGE");
-      enlarge = v ? atoi(v) : 0;
+      enlarge = v ? atoi(v) : 1;
     }
     if (!enlarge) return fail(ctx, VD3D_ERR_UNSUPPORTED, "eye fit would enlarge the eye (INTER_AREA upscaling)");
     f.sx = f.sy = 0;
@@ -657,12 +798,13 @@ int vd3d_create(int device, vd3d_ctx** out) {
   }
   if ((e = cudaMalloc(&ctx->st, sizeof(DevState))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&ctx->fs, sizeof(FrameScalars))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&ctx->jobwords, sizeof(uint32_t) * kJobs * kJobWords)) != cudaSuccess)
+  if ((e = cudaMalloc(&ctx->jobwords, sizeof(uint32_t) * (kJobs * kJobWords + kBarWords))) != cudaSuccess)
     return bail("cudaMalloc", e);
+  ctx->bar = ctx->jobwords + kJobs * kJobWords;
   if ((e = cudaMalloc(&ctx->tgs, sizeof(SelTarget) * kJobs * 4)) != cudaSuccess) return bail("cudaMalloc", e);
   cudaMemset(ctx->st, 0, sizeof(DevState));
   cudaMemset(ctx->fs, 0, sizeof(FrameScalars));
-  cudaMemset(ctx->jobwords, 0, sizeof(uint32_t) * kJobs * kJobWords);
+  cudaMemset(ctx->jobwords, 0, sizeof(uint32_t) * (kJobs * kJobWords + kBarWords));
   cudaMemset(ctx->tgs, 0, sizeof(SelTarget) * kJobs * 4);
   for (int j = 0; j < kJobs; ++j) {
     uint32_t* b = ctx->jobwords + (size_t)j * kJobWords;
@@ -676,6 +818,11 @@ int vd3d_create(int device, vd3d_ctx** out) {
   if ((e = cudaMallocHost(&ctx->fs_pinned, sizeof(FrameScalars))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost(&ctx->st_pinned, sizeof(DevState))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = init_kernel_attributes()) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+  if ((e = stats_grid(device, &ctx->stats_blocks)) != cudaSuccess) return bail("k_stats occupancy", e);
+  {
+    const char* v = getenv("VD3D_EXACT");
+    ctx->exact = (v && atoi(v)) ? 1 : 0;
+  }
   *out = ctx;
   return VD3D_OK;
 }
@@ -789,6 +936,20 @@ int vd3d_profile_collect(vd3d_ctx* ctx, int stage, double* total_ms, int* count)
   *count = n;
   return VD3D_OK;
 }
+// 1: the one-kernel-per-op path with correctly rounded transcendentals (bit-for-bit with oracle/dibr.py);
+// 0 (default; env VD3D_EXACT=1 flips the default): persistent stats kernel + fused render kernel
+int vd3d_set_exact(vd3d_ctx* ctx, int enable) {
+  if (!ctx) return VD3D_ERR_ARG;
+  if (ctx->exact != (enable ? 1 : 0)) {
+    cudaStreamSynchronize(ctx->stream);
+    drop_graphs(ctx);
+    ctx->exact = enable ? 1 : 0;
+  }
+  return VD3D_OK;
+}
+int vd3d_get_exact(vd3d_ctx* ctx) { return ctx ? ctx->exact : -1; }
+// 1 while frame graphs are enabled (0 after vd3d_set_graphs(0) or after a failed capture fell back to eager launches)
+int vd3d_graphs_active(vd3d_ctx* ctx) { return ctx ? ctx->use_graphs : -1; }
 int vd3d_set_graphs(vd3d_ctx* ctx, int enable) {
   if (!ctx) return VD3D_ERR_ARG;
   ctx->use_graphs = enable;
@@ -806,8 +967,9 @@ int vd3d_pixel_shift(vd3d_ctx* ctx, const float* rgb, const float* depth, int in
   cudaStream_t s = ctx->stream;
   const int W = width, H = height;
   int r;
+  const bool fastp = !ctx->exact && render_supports(p->enable_feathering ? 1 : 0, p->blur_ksize);
   if ((r = begin_frame(ctx))) return r;
-  launch_set_shifts(ctx->fs, p->fg_shift, p->mg_shift, p->bg_shift, s);
+  if (!fastp) launch_set_shifts(ctx->fs, p->fg_shift, p->mg_shift, p->bg_shift, s);  // k_stats does it itself
   ctx->launches += 2;
   const void *rgb_d, *depth_d;
   if ((r = copy_in(ctx, ctx->in_rgbf, rgb, sizeof(float) * 3 * (size_t)in_h * in_w, mem, s, &rgb_d))) return r;
@@ -844,7 +1006,12 @@ int vd3d_pixel_shift(vd3d_ctx* ctx, const float* rgb, const float* depth, int in
   ci.bri = 0.f;
   ci.left = l_d;
   ci.right = r_d;
-  if ((r = run_core(ctx, ci))) return r;
+  if (fastp) {
+    FastPost post;
+    if ((r = run_core_fast(ctx, ci, nullptr, post))) return r;
+  } else {
+    if ((r = run_core(ctx, ci))) return r;
+  }
   if (mem == VD3D_MEM_HOST) {
     CK(cudaMemcpyAsync(left_bgr, l_d, eye_bytes, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(right_bgr, r_d, eye_bytes, cudaMemcpyDeviceToHost, s));
@@ -928,6 +1095,134 @@ int vd3d_plan_sizes(int src_w, int src_h, const vd3d_render_params* rp, vd3d_siz
   return VD3D_OK;
 }
 
+// the vd3d_shift_params render_sbs_3d hands to pixel_shift_cuda (core/render_3d.py:1284-1331)
+static vd3d_shift_params loop_shift_params(const vd3d_render_params* rp) {
+  vd3d_shift_params sp;
+  memset(&sp, 0, sizeof sp);
+  sp.fg_shift = sp.mg_shift = sp.bg_shift = 0.0;  // taken from FrameScalars (set by k_fin_norm)
+  sp.blur_ksize = rp->blur_ksize;
+  sp.feather_strength = rp->feather_strength;
+  sp.max_pixel_shift_percent = rp->max_pixel_shift_percent;
+  sp.parallax_balance = 0.8;  // never forwarded by render_sbs_3d (core/render_3d.py:1284-1331)
+  sp.zero_parallax_strength = rp->zero_parallax_strength;
+  sp.use_subject_tracking = rp->use_subject_tracking;
+  sp.enable_floating_window = rp->use_floating_window;
+  sp.enable_feathering = rp->enable_feathering;
+  sp.enable_edge_masking = rp->enable_edge_masking;
+  sp.convergence_strength = rp->convergence_strength;
+  sp.enable_dynamic_convergence = rp->enable_dynamic_convergence;
+  sp.depth_pop_gamma = 0.85;  // hard-coded at the call site (1299-1305)
+  sp.depth_pop_mid = 0.50;
+  sp.depth_stretch_lo = 0.05;
+  sp.depth_stretch_hi = 0.95;
+  sp.fg_pop_multiplier = 1.20;
+  sp.bg_push_multiplier = 1.10;
+  sp.subject_lock_strength = 1.00;
+  return sp;
+}
+
+// fast-path core of one loop iteration: k_stats (ingest .. scalar trackers) -> k_shift -> k_render.  *fused tells the
+// caller that bars + sharpen + eye fit + pack already happened inside k_render (out_d is complete).
+static int enqueue_core_fast(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* depth_d, int depth_channels,
+                             int src_h, int src_w, const vd3d_render_params* rp, const vd3d_size_plan& pl,
+                             uint8_t* out_d, bool ident, bool* fused) {
+  int r;
+  const int tw = pl.target_eye_w, th = pl.target_eye_h;
+  const int W = pl.resized_width, H = pl.resized_height;
+  const size_t tpx = (size_t)tw * th;
+  IngestArgs ia;
+  memset(&ia, 0, sizeof ia);
+  ia.frame = frame_d;
+  ia.depth = depth_d;
+  ia.depth_ch = depth_channels;
+  ia.src_w = src_w;
+  ia.src_h = src_h;
+  ia.cx0 = pl.crop_x0;
+  ia.cy0 = pl.crop_y0;
+  ia.cw = pl.crop_w;
+  ia.ch = pl.crop_h;
+  ia.tw = tw;
+  ia.th = th;
+  ia.tdf = (float*)ctx->tdf.p;
+  ia.alpha = 0.5f;
+  ia.one_minus_alpha = (float)(1 - 0.5);
+  ia.st = ctx->st;
+  FastLoop lp;
+  memset(&lp, 0, sizeof lp);
+  lp.ia = &ia;
+  FastPost post;
+  if (!ident) {
+    if ((r = ensure(ctx, ctx->rgb_s, sizeof(float4) * tpx))) return r;
+    lp.rgbx_s = (float4*)ctx->rgb_s.p;
+    post.src_rgbx = lp.rgbx_s;
+    if (W != tw || H != th) {
+      if ((r = ensure(ctx, ctx->frameB, sizeof(float4) * (size_t)W * H))) return r;
+      lp.rgbx = (float4*)ctx->frameB.p;
+      post.src_rgbx = lp.rgbx;
+    }
+  }
+  lp.dn = (float*)(ctx->frame_parity ? ctx->dn1.p : ctx->dn0.p);
+  lp.dn_prev = (const float*)(ctx->frame_parity ? ctx->dn0.p : ctx->dn1.p);
+  LoopArgs la;
+  la.fg = rp->fg_shift;
+  la.mg = rp->mg_shift;
+  la.bg = rp->bg_shift;
+  la.ipd = rp->ipd_factor;
+  la.resized_width = W;
+  la.use_floating_window = rp->use_floating_window;
+  la.use_subject_tracking = rp->use_subject_tracking;
+  la.crop_count = (long long)(th * 3 / 4 - th / 4) * (long long)(tw * 3 / 4 - tw / 4);
+  la.npix = (long long)tpx;
+  la.dyn_min = (float)0.90;
+  la.dyn_span = (float)(1.15 - 0.90);
+  lp.la = &la;
+
+  const size_t eye_bytes = (size_t)W * H * 3;
+  CoreIn ci;
+  memset(&ci, 0, sizeof ci);
+  ci.depth = lp.dn;
+  ci.sh = th;
+  ci.sw = tw;
+  ci.src_u8 = ident ? frame_d : nullptr;
+  ci.src_pitch = src_w;
+  ci.cx0 = pl.crop_x0;
+  ci.cy0 = pl.crop_y0;
+  ci.W = W;
+  ci.H = H;
+  ci.p = loop_shift_params(rp);
+  const bool dof = rp->dof_strength > 0.0;
+  ci.grade = dof ? 0 : 1;
+  ci.sat = (float)rp->color_saturation;
+  ci.con = (float)rp->color_contrast;
+  ci.bri = (float)rp->color_brightness;
+
+  // can k_render finish the frame?  SBS formats whose eye fit is the identity or cv2's integer 2:1 horizontal INTER_AREA
+  *fused = false;
+  if (!ctx->stats_only && !dof && (rp->output_format == VD3D_FMT_HALF_SBS || rp->output_format == VD3D_FMT_FULL_SBS)) {
+    FitPlan fp;
+    if ((r = plan_fit(ctx, rp->output_format, W, H, pl.per_eye_w, pl.per_eye_h, fp))) return r;
+    const bool plain = !fp.xal && !fp.lin && fp.fit_x0 == 0 && fp.fit_y0 == 0 && fp.fit_w == pl.per_eye_w &&
+                       fp.fit_h == pl.per_eye_h && pl.out_width == 2 * pl.per_eye_w && pl.out_height == pl.per_eye_h &&
+                       fp.sy == 1 && pl.per_eye_h == H;
+    if (plain && fp.sx == 1 && pl.per_eye_w == W) post.fuse = 1;
+    if (plain && fp.sx == 2 && pl.per_eye_w * 2 == W) post.fuse = 2;
+  }
+  if (post.fuse) {
+    post.sharpen = 1;
+    sharpen_coeffs(rp->sharpness_factor, post.kc, post.ke);
+    post.out = out_d;
+    post.out_w = pl.out_width;
+    post.per_eye_w = pl.per_eye_w;
+    *fused = true;
+  } else if (!ctx->stats_only) {
+    if ((r = ensure(ctx, ctx->eyeL, eye_bytes))) return r;
+    if ((r = ensure(ctx, ctx->eyeR, eye_bytes))) return r;
+    ci.left = (uint8_t*)ctx->eyeL.p;
+    ci.right = (uint8_t*)ctx->eyeR.p;
+  }
+  return run_core_fast(ctx, ci, &lp, post);
+}
+
 // enqueue one loop iteration on ctx->stream; inputs/outputs are DEVICE pointers
 static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* depth_d, int depth_channels,
                          int src_h, int src_w, const vd3d_render_params* rp, const vd3d_size_plan& pl,
@@ -952,6 +1247,16 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
   if ((r = begin_frame(ctx))) return r;
   ctx->launches += 2;
 
+  const bool fastp = !ctx->exact && render_supports(rp->enable_feathering ? 1 : 0, rp->blur_ksize);
+  bool fused = false;
+  if (fastp) {
+    if ((r = enqueue_core_fast(ctx, frame_d, depth_d, depth_channels, src_h, src_w, rp, pl, out_d, ident, &fused)))
+      return r;
+    if (ctx->stats_only || fused) {
+      ctx->frame_parity ^= 1;
+      return VD3D_OK;
+    }
+  } else {
   // ---- ingest + TemporalDepthFilter
   IngestArgs ia;
   ia.frame = frame_d;
@@ -1032,28 +1337,7 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
   }
   ci.W = W;
   ci.H = H;
-  vd3d_shift_params sp;
-  memset(&sp, 0, sizeof sp);
-  sp.fg_shift = sp.mg_shift = sp.bg_shift = 0.0;  // taken from FrameScalars (set by k_fin_norm)
-  sp.blur_ksize = rp->blur_ksize;
-  sp.feather_strength = rp->feather_strength;
-  sp.max_pixel_shift_percent = rp->max_pixel_shift_percent;
-  sp.parallax_balance = 0.8;  // never forwarded by render_sbs_3d (core/render_3d.py:1284-1331)
-  sp.zero_parallax_strength = rp->zero_parallax_strength;
-  sp.use_subject_tracking = rp->use_subject_tracking;
-  sp.enable_floating_window = rp->use_floating_window;
-  sp.enable_feathering = rp->enable_feathering;
-  sp.enable_edge_masking = rp->enable_edge_masking;
-  sp.convergence_strength = rp->convergence_strength;
-  sp.enable_dynamic_convergence = rp->enable_dynamic_convergence;
-  sp.depth_pop_gamma = 0.85;  // hard-coded at the call site (1299-1305)
-  sp.depth_pop_mid = 0.50;
-  sp.depth_stretch_lo = 0.05;
-  sp.depth_stretch_hi = 0.95;
-  sp.fg_pop_multiplier = 1.20;
-  sp.bg_push_multiplier = 1.10;
-  sp.subject_lock_strength = 1.00;
-  ci.p = sp;
+  ci.p = loop_shift_params(rp);
   bool dof = rp->dof_strength > 0.0;
   ci.grade = dof ? 0 : 1;
   ci.sat = (float)rp->color_saturation;
@@ -1067,6 +1351,10 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
     ctx->frame_parity ^= 1;
     return VD3D_OK;
   }
+  }  // exact path
+  const size_t eye_bytes = (size_t)W * H * 3;
+  const bool dof = rp->dof_strength > 0.0;
+  float* dn = (float*)(ctx->frame_parity ? ctx->dn1.p : ctx->dn0.p);
   const uint8_t* eye_l = (const uint8_t*)ctx->eyeL.p;
   const uint8_t* eye_r = (const uint8_t*)ctx->eyeR.p;
   if (dof) {
@@ -1094,9 +1382,9 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
     }
     da.kern = (const float*)ctx->dof_kern.p;
     da.halo = ctx->dof_halo;
-    da.sat = ci.sat;
-    da.con = ci.con;
-    da.bri = ci.bri;
+    da.sat = (float)rp->color_saturation;
+    da.con = (float)rp->color_contrast;
+    da.bri = (float)rp->color_brightness;
     launch_dof(da, 2, s);
     ctx->launches += 1;
     eye_l = da.dst_l;
@@ -1145,8 +1433,12 @@ static void drop_depth_graphs(vd3d_ctx* ctx) {
 }
 
 static int ensure_depth_clones(vd3d_ctx* ctx, vd3d_depth* parent) {
-  if (ctx->dclone_parent == parent && ctx->dclone[0]) return VD3D_OK;
+  if (ctx->dclone_parent == parent && ctx->dclone[0] && ctx->dclone_wver == vd3d_depth_weights_version(parent))
+    return VD3D_OK;
+  CK(cudaDeviceSynchronize());
   drop_depth_graphs(ctx);
+  drop_graphs(ctx);  // the serial (profiling) path captures the parent engine inside the frame graph
+  ctx->dclone_wver = vd3d_depth_weights_version(parent);
   for (int i = 0; i < kSlots; ++i) {
     if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
     ctx->dclone[i] = nullptr;
@@ -1184,7 +1476,8 @@ static int run_depth_slot(vd3d_ctx* ctx, vd3d_depth* parent, int b, int src_h, i
   if (!g.exec) {
     uint64_t l0 = vd3d_depth_launch_count(e), p0 = vd3d_depth_launch_count(parent);
     if (cudaStreamBeginCapture(ctx->s_depth[b], cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-      cudaGetLastError();
+      fprintf(stderr, "vd3d: CUDA graph capture unavailable (%s); continuing with eager launches\n",
+              cudaGetErrorString(cudaGetLastError()));
       ctx->use_graphs = 0;
       return eager();
     }
@@ -1194,7 +1487,8 @@ static int run_depth_slot(vd3d_ctx* ctx, vd3d_depth* parent, int b, int src_h, i
     uint64_t n = vd3d_depth_launch_count(e) - l0;
     (void)p0;
     if (r != VD3D_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
-      cudaGetLastError();
+      fprintf(stderr, "vd3d: CUDA graph capture failed (r=%d, %s); continuing with eager launches\n", r,
+              cudaGetErrorString(cudaGetLastError()));
       if (graph) cudaGraphDestroy(graph);
       g.exec = nullptr;
       ctx->use_graphs = 0;
@@ -1239,6 +1533,10 @@ static int run_frame_slot(vd3d_ctx* ctx, vd3d_depth* depth, int b, int depth_cha
   };
   bool same = ctx->fg_h == src_h && ctx->fg_w == src_w && ctx->fg_dch == depth_channels && ctx->fg_depth == depth &&
               memcmp(&ctx->fg_rp, rp, sizeof *rp) == 0;
+  if (ctx->fg_epoch != ctx->res_epoch) {  // another entry point moved / rewrote something the graphs bake in
+    drop_graphs(ctx);
+    ctx->fg_epoch = ctx->res_epoch;
+  }
   if (!same) {
     drop_graphs(ctx);
     ctx->fg_h = src_h;
@@ -1256,7 +1554,8 @@ static int run_frame_slot(vd3d_ctx* ctx, vd3d_depth* depth, int b, int depth_cha
   if (!g.exec) {
     uint64_t l0 = ctx->launches, d0 = depth ? vd3d_depth_launch_count(depth) : 0;
     if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-      cudaGetLastError();
+      fprintf(stderr, "vd3d: CUDA graph capture unavailable (%s); continuing with eager launches\n",
+              cudaGetErrorString(cudaGetLastError()));
       ctx->use_graphs = 0;
       return eager();
     }
@@ -1269,7 +1568,8 @@ static int run_frame_slot(vd3d_ctx* ctx, vd3d_depth* depth, int b, int depth_cha
     if (depth) vd3d_depth_add_launches(depth, (uint64_t)0 - nd);
     if (r != VD3D_OK || ce != cudaSuccess || !graph ||
         cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
-      cudaGetLastError();
+      fprintf(stderr, "vd3d: CUDA graph capture failed (r=%d, %s); continuing with eager launches\n", r,
+              cudaGetErrorString(cudaGetLastError()));
       if (graph) cudaGraphDestroy(graph);
       g.exec = nullptr;
       ctx->use_graphs = 0;  // fall back to eager launches for the rest of this ctx
@@ -1411,10 +1711,8 @@ int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_
   }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaStreamSynchronize(ctx->s_d2h));
-  if (!serial) {
-    CK(cudaStreamSynchronize(ctx->s_depth[0]));
-    CK(cudaStreamSynchronize(ctx->s_depth[1]));
-  }
+  if (!serial)
+    for (int b = 0; b < kSlots; ++b) CK(cudaStreamSynchronize(ctx->s_depth[b]));
   return VD3D_OK;
 }
 

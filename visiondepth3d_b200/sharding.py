@@ -17,9 +17,12 @@ def broadcast_state_dict(sd, src=0, device=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return sd
     keys = [k for k, v in sd.items() if torch.is_floating_point(v)]
-    flat = torch.cat([sd[k].reshape(-1).float() for k in keys])
-    if device is not None:
-        flat = flat.to(device)
+    if dist.get_rank() == src:
+        flat = torch.cat([sd[k].reshape(-1).float() for k in keys])
+        if device is not None:
+            flat = flat.to(device)
+    else:  # receivers only need the shapes (their tensors may live on the meta device)
+        flat = torch.empty(sum(sd[k].numel() for k in keys), dtype=torch.float32, device=device or "cpu")
     dist.broadcast(flat, src=src)
     flat = flat.cpu()
     off = 0
