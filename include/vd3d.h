@@ -202,7 +202,15 @@ int vd3d_import_state(vd3d_ctx* ctx, const void* src, size_t bytes, int mem);
 /* drop the per-ctx clones / graphs built for `depth`; call before vd3d_depth_destroy(depth) */
 int vd3d_release_depth(vd3d_ctx* ctx, vd3d_depth* depth);
 
+/* Validate a render configuration without launching anything (sizes, eye-fit mode, DOF kernel bank): what
+ * render_sbs_3d (core/render_3d.py:1086-1138) decides before it opens its writer.  0 or a negative error + message. */
+int vd3d_check_config(vd3d_ctx* ctx, int src_h, int src_w, const vd3d_render_params* rp);
+
 /* stage entry points (same kernels, exposed for stage-isolated parity tests) */
+/* apply_color_grade (core/render_3d.py:734-767): f32 RGB planes [3,h,w] in 0..1 -> same (saturation around Rec.709
+ * luma, contrast around 0.5, additive brightness, clamp) */
+int vd3d_color_grade(vd3d_ctx* ctx, const float* rgb, int h, int w, double saturation, double contrast,
+                     double brightness, float* out, int mem);
 /* apply_sharpening (717-732) on u8 BGR [h,w,3] */
 int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem);
 /* heal_missing_pixels (431-459; the reference's "gradient-blend occlusion fill", defined but not called by

@@ -4,7 +4,8 @@ against fp32 references (numpy matmul, torch conv2d, oracle/depth.py).
 Tolerances: GEMM/conv operands are f16 (10-bit mantissa) with fp32 accumulation, so unit
 kernels are compared with the SAME f16-rounded operands (error = accumulation order only,
 <= 2e-3 relative to the result scale); the full forward is gated at <= 1e-3 max-abs on the
-depth normalised to [0, 1] (north_star tolerance for float intermediates) and <= 1 LSB after
+depth normalised to [0, 1] (north_star tolerance for float intermediates; asserted as 1e-3 in
+test_forward_matches_oracle on a model whose head does not cancel) and <= 1 LSB after
 the reference's min-max -> u8 quantisation (core/render_depth.py:605-611)."""
 import numpy as np
 import pytest
@@ -63,12 +64,43 @@ def test_conv_matches_torch(eng, case):
     assert np.abs(out - ref).max() <= 3e-3 * max(1.0, np.abs(ref).max()), case
 
 
-def _model(name):
+def _model(name, head="positive", stress=False):
+    """Random-init Depth-Anything-V2 (no checkpoints offline) made to behave like a trained one where it matters
+    for a parity gate:
+    * head="positive": the DPT head's last 1x1 conv (32 -> 1) gets non-negative weights.  PyTorch's symmetric init
+      makes that projection cancel to an output range of ~1e-4 of its terms, so a range-normalised error measures
+      the cancellation, not the kernels; trained heads (ReLU features -> positive depth) do not cancel.
+    * stress=True: DINOv2-style statistics -- LayerScale spread over two decades, a few "massive activation"
+      channels (large LayerNorm gains / fc2 biases / pos-embed offsets), so that f16 operand storage sees values
+      far from O(1).
+    """
     import torch
     from transformers import DepthAnythingForDepthEstimation
     from visiondepth3d_b200.depth_weights import hf_config
     torch.manual_seed(0)
-    return DepthAnythingForDepthEstimation(hf_config(name)).eval().state_dict()
+    sd = DepthAnythingForDepthEstimation(hf_config(name)).eval().state_dict()
+    g = torch.Generator().manual_seed(1)
+    if head == "positive":
+        sd["head.conv3.weight"] = sd["head.conv3.weight"].abs() + 0.02
+        sd["head.conv3.bias"] = torch.zeros_like(sd["head.conv3.bias"])
+    if stress:
+        D = sd["backbone.layernorm.weight"].numel()
+        hot = torch.randperm(D, generator=g)[:4]
+        for k in list(sd):
+            if k.endswith("layer_scale1.lambda1") or k.endswith("layer_scale2.lambda1"):
+                sd[k] = torch.exp(torch.empty(D).uniform_(-4.6, 0.7, generator=g))      # 0.01 .. 2
+            if k.endswith("norm1.weight") or k.endswith("norm2.weight"):
+                w = sd[k].clone()
+                w[hot] = 8.0
+                sd[k] = w
+            if k.endswith("mlp.fc2.bias"):
+                b = sd[k].clone()
+                b[hot] = torch.tensor([60.0, -45.0, 30.0, 80.0])
+                sd[k] = b
+        pe = sd["backbone.embeddings.position_embeddings"].clone()
+        pe[..., hot] += 25.0
+        sd["backbone.embeddings.position_embeddings"] = pe
+    return sd
 
 
 def _depth_u8(d):
@@ -79,6 +111,8 @@ def _depth_u8(d):
 
 @pytest.mark.parametrize("name,h,w", [("vits", 70, 98), ("vits", 518, 924), ("vitb", 518, 924), ("vitl", 518, 924)])
 def test_forward_matches_oracle(name, h, w):
+    """predicted_depth <= 1e-3 max-abs of its range (north_star) against the fp32 oracle, <= 1 LSB after the
+    reference's min-max u8 quantisation; every tap / neck feature / fused map <= 2e-3 of its own max."""
     import torch
     from oracle import depth as OD
     from visiondepth3d_b200.depth_engine import DepthEngine
@@ -92,14 +126,55 @@ def test_forward_matches_oracle(name, h, w):
         ref = OD.forward(sd, CONFIGS[name], px).numpy()
     out = e.forward(px.numpy())
     scale = float(ref.max() - ref.min())
+    assert scale > 1e-2 * float(np.abs(ref).max()), "degenerate test model: output range cancels"
     err = np.abs(out - ref).max() / scale
-    # Every intermediate is within ~2 f16 ulp of the fp32 oracle (tools/depth_triage.py); with
-    # RANDOM-INIT weights the head's 32->1 projection cancels to a range of ~1e-4, which inflates
-    # the range-normalised error to ~1.8e-3.  Gate: 3e-3 here, and <= 1 LSB after the min-max u8
-    # quantisation the reference applies before the stereo stage.
-    assert err <= 3e-3, (name, h, w, err)
+    assert err <= 1e-3, (name, h, w, err)
     du = np.abs(_depth_u8(out).astype(int) - _depth_u8(ref).astype(int))
     assert du.max() <= 1
+    e.close()
+
+
+def test_forward_random_head_u8():
+    """The symmetric random head (output range ~1e-4 of its terms): only the u8 handoff is meaningful there."""
+    import torch
+    from oracle import depth as OD
+    from visiondepth3d_b200.depth_engine import DepthEngine
+    from visiondepth3d_b200.depth_weights import CONFIGS
+    sd = _model("vits", head="random")
+    e = DepthEngine("vits", 518, 924)
+    e.load_state_dict(sd)
+    torch.manual_seed(2)
+    px = torch.randn(3, 518, 924)
+    with torch.no_grad():
+        ref = OD.forward(sd, CONFIGS["vits"], px).numpy()
+    out = e.forward(px.numpy())
+    assert np.abs(out - ref).max() / float(ref.max() - ref.min()) <= 3e-3
+    assert np.abs(_depth_u8(out).astype(int) - _depth_u8(ref).astype(int)).max() <= 1
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["vits", "vitb"])
+def test_forward_outlier_channels_no_f16_overflow(name):
+    """DINOv2-like statistics: LayerScale over two decades, four massive-activation channels (|x| ~ 1e2 in the
+    residual stream, LayerNorm gain 8).  The f16 operand stores must neither overflow nor lose the gate."""
+    import torch
+    from oracle import depth as OD
+    from visiondepth3d_b200.depth_engine import DepthEngine
+    from visiondepth3d_b200.depth_weights import CONFIGS
+    sd = _model(name, stress=True)
+    e = DepthEngine(name, 518, 924)
+    e.load_state_dict(sd)
+    torch.manual_seed(3)
+    px = torch.randn(3, 518, 924)
+    with torch.no_grad():
+        ref, parts = OD.forward(sd, CONFIGS[name], px, return_parts=True)
+    ref = ref.numpy()
+    assert float(parts["x"].abs().max()) > 50.0          # the stress really produced outliers
+    out = e.forward(px.numpy())
+    assert np.isfinite(out).all()
+    err = np.abs(out - ref).max() / float(ref.max() - ref.min())
+    assert err <= 2e-3, (name, err)   # outlier channels cost f16 mantissa in the neck's inputs; u8 handoff still exact:
+    assert np.abs(_depth_u8(out).astype(int) - _depth_u8(ref).astype(int)).max() <= 1
     e.close()
 
 
@@ -131,15 +206,20 @@ def test_infer_matches_hf_pipeline_stages():
         dpx = np.abs(px - pv.numpy()) * 0.225 * 255  # in u8 LSB of the resized image
         # float weights here vs ATen's int16 fixed-point uint8 path: >99 % identical, rare 1-2 LSB
         assert dpx.max() <= 2.01 and (dpx > 0.5).mean() <= 0.01, (dpx.max(), (dpx > 0.5).mean())
+        # forward + bicubic resize to the frame + min-max u8 from OUR pixel_values (the rare 1-2 LSB processor
+        # differences above are an input difference, measured separately): north-star gates
         with torch.no_grad():
-            ref = OD.forward(sd, CONFIGS["vits"], pv)
+            ref = OD.forward(sd, CONFIGS["vits"], torch.from_numpy(px.copy()))
             ref = F.interpolate(ref[None, None], size=(h, w), mode="bicubic", align_corners=False)[0, 0].numpy()
         scale = float(ref.max() - ref.min())
-        # the reference arm here starts from HF's pixel_values, ours from its own processor (rare 1-2 LSB
-        # input differences); a random-init model with a ~1e-4 output range amplifies that to ~1 % of range
-        assert np.abs(d32 - ref).max() / scale <= 1e-1
+        assert np.abs(d32 - ref).max() / scale <= 1e-3
         du = np.abs(d8.astype(int) - _depth_u8(ref).astype(int))
-        assert du.max() <= 4 and (du > 1).mean() <= 5e-3, (du.max(), (du > 0).mean())
+        assert du.max() <= 1, (du.max(), (du > 0).mean())
+        # and end to end from HF's pixel_values: bounded by the processor difference
+        with torch.no_grad():
+            ref2 = OD.forward(sd, CONFIGS["vits"], pv)
+            ref2 = F.interpolate(ref2[None, None], size=(h, w), mode="bicubic", align_corners=False)[0, 0].numpy()
+        assert np.abs(d32 - ref2).max() / scale <= 2e-2
     e.close()
 
 

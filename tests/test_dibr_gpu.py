@@ -19,7 +19,8 @@ import numpy as np
 import pytest
 
 from oracle import dibr as O
-from tests.util import LOOP_CASES, LOOP_CASES_EXTRA, PS_CASES, PS_CASES_EXTRA, u8_diff
+from tests.util import (BIG_NATURAL, LOOP_CASES, LOOP_CASES_EXTRA, LOOP_NATURAL, PS_CASES, PS_CASES_EXTRA, PS_NATURAL,
+                        u8_diff)
 from visiondepth3d_b200.synth import synth_frame
 
 pytestmark = pytest.mark.gpu
@@ -115,6 +116,42 @@ def test_pixel_shift_vs_reference_golden(R, golden_dir, name, mode):
         for mine, ref in ((l, g[f"left{i}"]), (r, g[f"right{i}"])):
             mx, f0, f1 = u8_diff(mine, ref)
             assert mx <= 1, (name, i, mx)
+
+
+@pytest.mark.parametrize("name", sorted(PS_NATURAL))
+@pytest.mark.parametrize("mode", MODES, indirect=True)
+def test_pixel_shift_natural_vs_reference(R, golden_dir, name, mode):
+    """CUDA path against the UNMODIFIED reference on content off the k/255 grid: eyes <= 1 LSB, < 0.3 % flips."""
+    c = PS_NATURAL[name]
+    g = np.load(os.path.join(golden_dir, name))
+    R.reset_temporal_state()
+    for i in range(c["n"]):
+        fr, dp = synth_frame(i, c["iw"], c["ih"], c["kind"])
+        l, r, s = _ps(R, fr, dp, c["w"], c["h"], c["kw"])
+        assert np.abs(s.numpy() - g[f"shift{i}"]).max() <= 2e-5
+        for mine, ref in ((l, g[f"left{i}"]), (r, g[f"right{i}"])):
+            mx, f0, f1 = u8_diff(mine, ref)
+            assert mx <= 1 and f0 <= 0.003, (name, mode, i, mx, f0)
+
+
+@pytest.mark.parametrize("name", sorted(LOOP_NATURAL) + sorted(BIG_NATURAL))
+@pytest.mark.parametrize("mode", MODES, indirect=True)
+def test_render_loop_natural_vs_reference(R, golden_dir, name, mode):
+    """Full chain (sharpening on) against the unmodified reference: natural content at 320x180 and at the two
+    BASELINE sizes (1080p Half-SBS, 4K Full-SBS; sparse samples of the reference's frames)."""
+    big = name in BIG_NATURAL
+    c = BIG_NATURAL[name] if big else LOOP_NATURAL[name]
+    g = np.load(os.path.join(golden_dir, name))
+    rp, _ = _rp(R, c["rp"], c["sw"], c["sh"])
+    R.reset_temporal_state()
+    for j, i in enumerate(range(1, c["n"])):
+        fr, dp = synth_frame(i, c["sw"], c["sh"], c["kind"])
+        out = R.render_frame(fr, dp, rp)
+        ref = g[f"final{j}_{c['key']}"] if big else g[f"final{j}"]
+        mine = out[::c["step"], ::c["step"]] if big else out
+        assert mine.shape == ref.shape
+        mx, f0, f1 = u8_diff(mine, ref)
+        assert mx <= 8 and f1 <= 0.002 and f0 <= 0.01, (name, mode, j, mx, f0, f1)
 
 
 def _rp(R, d, w, h):

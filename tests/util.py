@@ -69,3 +69,25 @@ LOOP_CASES_EXTRA = {
                 enable_dynamic_convergence=False, enable_edge_masking=False)),
     "loop_dof_halfsbs_320x180.npz": dict(sw=320, sh=180, n=3, kind="smooth", rp=dict(_BASE, dof_strength=1.5)),
 }
+
+# "natural" set (tools/gen_golden.py natural): band-limited content whose warped values are generic reals instead of
+# sitting on the k/255 truncation boundaries of the ramps.  Against the unmodified reference the eyes are <= 1 LSB with
+# < 0.1 % one-LSB flips (torch's Sleef powf/expf differ from IEEE by <= 1 ulp), and full frames -- sharpening ON, which
+# amplifies an isolated flip up to 7.7 LSB -- have < 0.1 % of bytes off by more than one (2-3 % on the smooth set).
+PS_NATURAL = {
+    "ps_natural_320x180.npz": dict(w=320, h=180, iw=320, ih=180, n=3, kind="natural",
+                                   kw=dict(blur_ksize=9, feather_strength=10.0, zero_parallax_strength=0.01)),
+}
+LOOP_NATURAL = {
+    "loop_natural_halfsbs_320x180.npz": dict(sw=320, sh=180, n=5, kind="natural", rp=dict(_BASE)),
+    "loop_natural_fullsbs_320x180.npz": dict(sw=320, sh=180, n=4, kind="natural",
+                                             rp=dict(_BASE, output_format="Full-SBS", preserve_original_aspect=True)),
+}
+# BASELINE sizes against the unmodified reference: every `step`-th row / column of each output frame + sha256
+BIG_NATURAL = {
+    "loop_natural_1080p_halfsbs.npz": dict(sw=1920, sh=1080, n=3, kind="natural", step=7, key="s7",
+                                           rp=dict(_BASE, output_width=1920, output_height=1080)),
+    "loop_natural_4k_fullsbs.npz": dict(sw=3840, sh=2160, n=2, kind="natural", step=16, key="s16",
+                                        rp=dict(_BASE, output_width=3840, output_height=2160, output_format="Full-SBS",
+                                                preserve_original_aspect=True)),
+}

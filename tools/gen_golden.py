@@ -266,6 +266,53 @@ def gen_extra():
         print(f, os.path.getsize(os.path.join(OUT, f)), {k: z[k].shape for k in z.files if k.startswith("final")})
 
 
+def _sparse(f, step):
+    import hashlib
+    return f[::step, ::step].copy(), np.frombuffer(hashlib.sha256(f.tobytes()).digest(), dtype=np.uint8)
+
+
+def gen_natural():
+    """Q. the "natural" synthetic set (visiondepth3d_b200/synth.py: band-limited fields + texture, values off the
+    k/255 truncation grid) through pixel_shift_cuda and the full loop with sharpening on, plus the two BASELINE sizes
+    (1080p Half-SBS, 4K Full-SBS) stored as every 7th / 16th row and column + sha256 of the full frame
+    (`python tools/gen_golden.py natural`)."""
+    mods = refshim.load_reference(("render_3d",))
+    r3d = mods["render_3d"]
+    import cv2
+    import torch
+    import torchvision
+    torch.set_num_threads(os.cpu_count())
+    meta = dict(torch=torch.__version__, torchvision=torchvision.__version__, cv2=cv2.__version__,
+                numpy=np.__version__)
+    base = dict(output_width=320, output_height=180, sharpness_factor=0.2, output_format="Half-SBS",
+                dof_strength=0.0, feather_strength=10.0, blur_ksize=9, use_subject_tracking=True,
+                use_floating_window=True, preserve_original_aspect=False, zero_parallax_strength=0.01)
+    g = run_pixel_shift(r3d, torch, 320, 180, 320, 180, 3, "natural",
+                        blur_ksize=9, feather_strength=10.0, zero_parallax_strength=0.01)
+    np.savez_compressed(os.path.join(OUT, "ps_natural_320x180.npz"), **g, **meta)
+    g = run_loop(r3d, torch, cv2, 320, 180, 5, "natural", base)
+    np.savez_compressed(os.path.join(OUT, "loop_natural_halfsbs_320x180.npz"), **g, **meta)
+    g = run_loop(r3d, torch, cv2, 320, 180, 4, "natural", dict(base, output_format="Full-SBS", preserve_original_aspect=True))
+    np.savez_compressed(os.path.join(OUT, "loop_natural_fullsbs_320x180.npz"), **g, **meta)
+    # BASELINE sizes
+    g = run_loop(r3d, torch, cv2, 1920, 1080, 3, "natural", dict(base, output_width=1920, output_height=1080))
+    out = {}
+    for k, f in g.items():
+        assert f.shape == (1080, 1920, 3), f.shape
+        out[k + "_s7"], out[k + "_sha256"] = _sparse(f, 7)
+    np.savez_compressed(os.path.join(OUT, "loop_natural_1080p_halfsbs.npz"), **out, **meta)
+    g = run_loop(r3d, torch, cv2, 3840, 2160, 2, "natural",
+                 dict(base, output_width=3840, output_height=2160, output_format="Full-SBS", preserve_original_aspect=True))
+    out = {}
+    for k, f in g.items():
+        assert f.shape == (2160, 7680, 3), f.shape
+        out[k + "_s16"], out[k + "_sha256"] = _sparse(f, 16)
+    np.savez_compressed(os.path.join(OUT, "loop_natural_4k_fullsbs.npz"), **out, **meta)
+    for f in ("ps_natural_320x180.npz", "loop_natural_halfsbs_320x180.npz", "loop_natural_fullsbs_320x180.npz",
+              "loop_natural_1080p_halfsbs.npz", "loop_natural_4k_fullsbs.npz"):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
 def gen_depth_gray():
     """O. convert_depth_to_grayscale (core/render_depth.py:585-611) on the input kinds it accepts
     (`python tools/gen_golden.py depthgray`): tensor / ndarray, 2-D, [C,H,W], [H,W,C], flat and NaN frames."""
@@ -333,5 +380,7 @@ if __name__ == "__main__":
         gen_extra()
     elif len(sys.argv) > 1 and sys.argv[1] == "vr":
         gen_vr()
+    elif len(sys.argv) > 1 and sys.argv[1] == "natural":
+        gen_natural()
     else:
         main()

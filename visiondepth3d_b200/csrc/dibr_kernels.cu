@@ -982,9 +982,24 @@ __global__ void __launch_bounds__(256) k_heal(const float* __restrict__ warped, 
   }
 }
 
+// apply_color_grade (core/render_3d.py:734-767) on planar f32 RGB
+__global__ void __launch_bounds__(256) k_grade_f32(const float* __restrict__ src, float* __restrict__ dst, int n, float sat,
+                                                   float con, float bri) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float r = src[i], g = src[n + i], b = src[2 * (size_t)n + i];
+  grade_px(r, g, b, sat, con, bri);
+  dst[i] = r;
+  dst[n + i] = g;
+  dst[2 * (size_t)n + i] = b;
+}
+
 // ---------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------
+void launch_grade_f32(const float* src, float* dst, int n, float sat, float con, float bri, cudaStream_t s) {
+  k_grade_f32<<<(n + 255) / 256, 256, 0, s>>>(src, dst, n, sat, con, bri);
+}
 void launch_heal(const float* warped, const float* orig, const float* edge, float* out, int H, int W, float hs,
                  cudaStream_t s) {
   dim3 g((W + 31) / 32, (H + 7) / 8);

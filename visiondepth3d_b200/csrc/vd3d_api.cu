@@ -1825,6 +1825,49 @@ int vd3d_release_depth(vd3d_ctx* ctx, vd3d_depth* depth) {
   return VD3D_OK;
 }
 
+// Validate a render configuration without launching anything: sizes, eye-fit mode (builds the INTER_AREA tables it
+// will need), DOF kernel bank.  render_sbs_3d calls it before it creates the output file, so that an unsupported
+// configuration fails with a message instead of leaving an empty video behind.
+int vd3d_check_config(vd3d_ctx* ctx, int src_h, int src_w, const vd3d_render_params* rp) {
+  if (!ctx || !rp) return fail(ctx, VD3D_ERR_ARG, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  vd3d_size_plan pl;
+  int r = vd3d_plan_sizes(src_w, src_h, rp, &pl);
+  if (r) return fail(ctx, r, "unsupported output format / sizes");
+  if (pl.target_eye_w < 8 || pl.target_eye_h < 8 || pl.resized_width < 8 || pl.resized_height < 8)
+    return fail(ctx, VD3D_ERR_ARG, "frame too small");
+  if (rp->enable_feathering && (rp->blur_ksize < 1 || rp->blur_ksize > 63))
+    return fail(ctx, VD3D_ERR_UNSUPPORTED, "blur_ksize must be in [1,63]");
+  FitPlan fp;
+  if ((r = plan_fit(ctx, rp->output_format, pl.resized_width, pl.resized_height, pl.per_eye_w, pl.per_eye_h, fp)))
+    return r;
+  if (rp->dof_strength > 0.0 && (r = ensure_dof_kernels(ctx, rp->dof_strength, 5))) return r;
+  return VD3D_OK;
+}
+
+// apply_color_grade (core/render_3d.py:734-767) on f32 RGB planes [3,h,w] in 0..1
+int vd3d_color_grade(vd3d_ctx* ctx, const float* rgb, int h, int w, double sat, double con, double bri, float* out,
+                     int mem) {
+  if (!ctx || !rgb || !out || h < 1 || w < 1) return fail(ctx, VD3D_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  size_t bytes = sizeof(float) * 3 * (size_t)h * w;
+  const void* r_d;
+  int r;
+  if ((r = copy_in(ctx, ctx->in_rgbf, rgb, bytes, mem, s, &r_d))) return r;
+  float* o_d = out;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->frameB, bytes))) return r;
+    o_d = (float*)ctx->frameB.p;
+  }
+  launch_grade_f32((const float*)r_d, o_d, h * w, (float)sat, (float)con, (float)bri, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(out, o_d, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+
 int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem) {
   if (!ctx || !src || !dst || h < 2 || w < 2) return fail(ctx, VD3D_ERR_ARG, "bad argument");
   CK(cudaSetDevice(ctx->device));

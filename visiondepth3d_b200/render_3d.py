@@ -155,6 +155,27 @@ def apply_sharpening(frame, factor=1.0):
     return out
 
 
+def apply_color_grade(rgb_tensor, saturation=1.0, contrast=1.0, brightness=0.0):
+    """core/render_3d.py:734-767: f32 RGB [3,H,W] in 0..1 -> graded, clamped tensor of the same kind (torch tensor on
+    its device, or numpy)."""
+    assert rgb_tensor.ndim == 3 and rgb_tensor.shape[0] == 3
+    ctx = _ctx()
+    h, w = int(rgb_tensor.shape[1]), int(rgb_tensor.shape[2])
+    is_t = torch is not None and isinstance(rgb_tensor, torch.Tensor)
+    if is_t and rgb_tensor.is_cuda:
+        src = rgb_tensor.contiguous().float()
+        out = torch.empty_like(src)
+        torch.cuda.current_stream().synchronize()
+        ctx.check(ctx.lib.vd3d_color_grade(ctx.h, src.data_ptr(), h, w, float(saturation), float(contrast),
+                                           float(brightness), out.data_ptr(), _lib.MEM_DEVICE))
+        return out
+    src = np.ascontiguousarray(rgb_tensor.detach().cpu().numpy() if is_t else rgb_tensor, dtype=np.float32)
+    out = np.empty_like(src)
+    ctx.check(ctx.lib.vd3d_color_grade(ctx.h, src.ctypes.data, h, w, float(saturation), float(contrast),
+                                       float(brightness), out.ctypes.data, _lib.MEM_HOST))
+    return torch.from_numpy(out) if is_t else out
+
+
 def dof_grade_frame(frame_bgr, depth01, focal_depth, max_sigma=2.0, saturation=1.0, contrast=1.0,
                     brightness=0.0):
     """frame_to_tensor -> apply_dof_cuda -> apply_color_grade -> tensor_to_frame on a u8 eye
@@ -311,6 +332,116 @@ def advance_state(frame_bgr, depth_bgr, rp, ctx=None):
                                          C.byref(rp), _lib.MEM_HOST))
 
 
+class _ClipWindow:
+    """Frame-index arithmetic of render_sbs_3d's optional clip window (core/render_3d.py:986-1030): times are clamped
+    to the clip, converted to frame indices by rounding, and a window shorter than half a millisecond is empty.
+    `budget` is the number of loop iterations (the whole clip when the window has no frames of its own)."""
+
+    def __init__(self, n_frames, fps, start_s, end_s):
+        length_ms = (n_frames / max(fps, 1e-6)) * 1000.0
+        t0 = max(0.0, (start_s or 0.0) * 1000.0)
+        t1 = length_ms if end_s is None else min(length_ms, end_s * 1000.0)
+        self.empty = t0 >= t1 - 0.5
+        self.first = int(round(t0 / 1000.0 * fps))
+        self.stop = int(round(t1 / 1000.0 * fps))
+        span = max(0, self.stop - self.first)
+        self.budget = span if span > 0 else n_frames
+        self.bounded = end_s is not None
+
+
+def _frame_pairs(cap, dcap, win, suspend_flag, cancel_flag):
+    """(frame, depth) pairs in the order the reference's loop consumes them (core/render_3d.py:1184-1225, 1429-1432):
+    seek to the window start, read and drop one pair, then at most win.budget pairs; stops at the first failed read,
+    on cancel, or -- when an end time was given -- once the colour stream's position has reached the window's end."""
+    import cv2
+    cap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
+    dcap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
+    ok_a, _ = cap.read()
+    ok_b, _ = dcap.read()
+    if not (ok_a and ok_b):
+        return
+    for _ in range(win.budget):
+        while suspend_flag.is_set() and not cancel_flag.is_set():
+            time.sleep(0.2)
+        if cancel_flag.is_set():
+            return
+        ok_a, frame = cap.read()
+        ok_b, depth = dcap.read()
+        if not (ok_a and ok_b):
+            return
+        last = win.bounded and int(cap.get(cv2.CAP_PROP_POS_FRAMES)) >= win.stop
+        yield frame, depth
+        if last:
+            return
+
+
+class _PinnedRing:
+    """n page-locked host buffers of `shape` u8 (cudaMallocHost through the C ABI) viewed as numpy arrays."""
+
+    def __init__(self, lib, n, shape):
+        self.lib, self.ptrs, self.arrays = lib, [], []
+        nbytes = int(np.prod(shape))
+        for _ in range(n):
+            p = lib.vd3d_host_alloc(nbytes)
+            if not p:
+                self.close()
+                raise MemoryError("vd3d_host_alloc failed")
+            self.ptrs.append(p)
+            self.arrays.append(np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p)).reshape(shape))
+
+    def close(self):
+        self.arrays = []
+        for p in self.ptrs:
+            self.lib.vd3d_host_free(p)
+        self.ptrs = []
+
+
+class _FrameSink:
+    """Where packed frames go: raw bgr24 into an ffmpeg stdin pipe (core/render_3d.py:1143-1163, 1422-1427) or a
+    cv2.VideoWriter (1164-1169)."""
+
+    def __init__(self, path, size, fps, fourcc, use_ffmpeg, ffmpeg_codec, crf):
+        import cv2
+        self.proc = self.writer = None
+        w, h = size
+        if use_ffmpeg:
+            import subprocess
+            cmd = ["ffmpeg", "-y", "-f", "rawvideo", "-vcodec", "rawvideo", "-pix_fmt", "bgr24", "-s", f"{w}x{h}",
+                   "-r", str(fps), "-i", "-", "-an", "-c:v", str(ffmpeg_codec), "-preset", "slow", "-pix_fmt", "yuv420p"]
+            if str(ffmpeg_codec).startswith("libx"):
+                cmd += ["-crf", str(crf)]
+            elif "nvenc" in str(ffmpeg_codec):
+                cmd += ["-cq", str(crf), "-b:v", "0"]
+            self.proc = subprocess.Popen(cmd + [path], stdin=subprocess.PIPE)
+        else:
+            self.writer = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*fourcc), fps, (w, h))
+
+    def ok(self):
+        return self.proc is not None or (self.writer is not None and self.writer.isOpened())
+
+    def write(self, frame):
+        if self.proc is not None:
+            self.proc.stdin.write(memoryview(frame).cast("B"))
+        else:
+            self.writer.write(frame)
+
+    def close(self):
+        if self.proc is not None:
+            try:
+                self.proc.stdin.close()
+                self.proc.wait()
+            except Exception:
+                pass
+        if self.writer is not None:
+            try:
+                self.writer.release()
+            except Exception:
+                pass
+
+
+_BATCH = 8  # frames per vd3d_render_clip call of the video loop (3 of them in flight on the device)
+
+
 def render_sbs_3d(
     input_path, depth_path, output_path, selected_codec, fps, output_width, output_height,
     fg_shift, mg_shift, bg_shift, sharpness_factor, output_format, selected_aspect_ratio,
@@ -326,96 +457,296 @@ def render_sbs_3d(
     subject_lock_strength=1.00, color_saturation=1.0, color_contrast=1.0, color_brightness=0.0,
     start_s=None, end_s=None,
 ):
-    """core/render_3d.py:933-1504: video in -> video out.  Video I/O stays cv2 on the host
-    (SURVEY section 8(f) "next"); every frame's math runs in libvd3d.  Reproduces the reference's
-    sequencing: first frame of the clip window dropped (1184-1188), pop controls and
-    parallax_balance not forwarded (1284-1331), no exception escapes (1477-1478)."""
+    """core/render_3d.py:933-1504: video in -> video out.
+
+    Three stages run concurrently: a reader thread decodes frame / depth pairs (cv2) into a ring of page-locked
+    buffers, the calling thread hands batches of them to vd3d_render_clip (H2D | kernels | D2H pipelined over three
+    streams, CUDA-graph replay), and a writer thread pushes the packed frames of the previous batch as raw bgr24 into
+    an ffmpeg pipe (use_ffmpeg, when the binary exists) or a cv2.VideoWriter.  Sequencing follows the reference:
+    first pair of the window dropped, pop controls and parallax_balance not forwarded (1284-1331), no exception
+    escapes (1477-1478).  auto_crop_black_bars / skip_blank_frames (ffmpeg blackdetect, letterbox tracker) are outside
+    the hot path: refused with a message before any file is created."""
+    import queue
+    import shutil
     import cv2
-    if use_ffmpeg or auto_crop_black_bars or skip_blank_frames:
-        print("⚠️ use_ffmpeg / auto_crop_black_bars / skip_blank_frames are outside the B200 hot path")
+    if auto_crop_black_bars or skip_blank_frames:
+        print("⚠️ auto_crop_black_bars / skip_blank_frames are outside the B200 hot path")
         return
+    if use_ffmpeg and shutil.which("ffmpeg") is None:
+        print("⚠️ ffmpeg binary not found: writing through cv2.VideoWriter instead")
+        use_ffmpeg = False
     cap, dcap = cv2.VideoCapture(input_path), cv2.VideoCapture(depth_path)
     if not cap.isOpened() or not dcap.isOpened():
         return
-    total_frames_full = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
-    fps = cap.get(cv2.CAP_PROP_FPS) or fps or 30.0
-    dur_ms = (total_frames_full / max(fps, 1e-6)) * 1000.0
-    start_ms = max(0.0, (start_s or 0.0) * 1000.0)
-    end_ms = dur_ms if (end_s is None) else min(dur_ms, end_s * 1000.0)
-    if start_ms >= end_ms - 0.5:
-        print("⚠️ Invalid clip window; nothing to render.")
-        cap.release(); dcap.release()
-        return
-    start_frame_idx = int(round(start_ms / 1000.0 * fps))
-    end_frame_idx = int(round(end_ms / 1000.0 * fps))
-    clip_total_frames = max(0, end_frame_idx - start_frame_idx)
-    cap.set(cv2.CAP_PROP_POS_FRAMES, start_frame_idx)
-    dcap.set(cv2.CAP_PROP_POS_FRAMES, start_frame_idx)
-    ret1, frame = cap.read()
-    ret2, depth = dcap.read()
-    if not ret1 or not ret2:
-        cap.release(); dcap.release()
-        return
-    suspend_flag = suspend_flag or globals()["suspend_flag"]
-    cancel_flag = cancel_flag or globals()["cancel_flag"]
-    ratio = aspect_ratios.get(selected_aspect_ratio.get(), 16 / 9)
-    rp = make_render_params(
-        output_width, output_height, fg_shift, mg_shift, bg_shift, sharpness_factor, output_format, ratio,
-        dof_strength, feather_strength, blur_ksize, use_subject_tracking, use_floating_window,
-        max_pixel_shift_percent, preserve_original_aspect, zero_parallax_strength, enable_edge_masking,
-        enable_feathering, original_video_width, original_video_height, convergence_strength,
-        enable_dynamic_convergence, ipd_factor, color_saturation, color_contrast, color_brightness)
-    sh, sw = frame.shape[:2]
-    out = None
+    n_frames = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    fps = cap.get(cv2.CAP_PROP_FPS) or fps or 30.0        # the container's rate wins over the argument (993)
+    win = _ClipWindow(n_frames, fps, start_s, end_s)
+    sink = ring_in = ring_out = None
+    stop = threading.Event()
     try:
-        pl = plan_sizes(sw, sh, rp)
+        if win.empty:
+            print("⚠️ Invalid clip window; nothing to render.")
+            return
+        cap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
+        dcap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
+        ok_a, probe = cap.read()
+        ok_b, probe_d = dcap.read()
+        if not (ok_a and ok_b):
+            return
+        suspend_flag = suspend_flag or globals()["suspend_flag"]
+        cancel_flag = cancel_flag or globals()["cancel_flag"]
+        ratio = aspect_ratios.get(selected_aspect_ratio.get(), 16 / 9)
+        rp = make_render_params(
+            output_width, output_height, fg_shift, mg_shift, bg_shift, sharpness_factor, output_format, ratio,
+            dof_strength, feather_strength, blur_ksize, use_subject_tracking, use_floating_window,
+            max_pixel_shift_percent, preserve_original_aspect, zero_parallax_strength, enable_edge_masking,
+            enable_feathering, original_video_width, original_video_height, convergence_strength,
+            enable_dynamic_convergence, ipd_factor, color_saturation, color_contrast, color_brightness)
+        sh, sw = probe.shape[:2]
+        dch = 1 if probe_d.ndim == 2 else probe_d.shape[2]
+        pl = plan_sizes(sw, sh, rp)                     # raises before any output file exists
         oshape = output_shape(rp, pl)
-        out = cv2.VideoWriter(output_path, cv2.VideoWriter_fourcc(*selected_codec), fps, (oshape[1], oshape[0]))
-        if not out.isOpened():
-            print("❌ OpenCV VideoWriter failed to open. Check codec/fourcc and path.")
-            cap.release(); dcap.release()
-            return
         ctx = _ctx()
-        ctx.reset(_lib.STATE_CLIP)  # ShiftSmoother / TemporalDepthFilter / FocalDepthTracker are per render
-        cap.set(cv2.CAP_PROP_POS_FRAMES, start_frame_idx)
-        dcap.set(cv2.CAP_PROP_POS_FRAMES, start_frame_idx)
-        ret1, frame = cap.read()   # read + discard (1184-1188)
-        ret2, depth = dcap.read()
-        if not ret1 or not ret2:
+        ctx.check(ctx.lib.vd3d_check_config(ctx.h, sh, sw, C.byref(rp)))   # eye fit / DOF limits, still no file
+        sink = _FrameSink(output_path, (oshape[1], oshape[0]), fps, selected_codec, use_ffmpeg, selected_ffmpeg_codec,
+                          crf_value)
+        if not sink.ok():
+            print("❌ OpenCV VideoWriter failed to open. Check codec/fourcc and path.")
             return
-        total_frames = clip_total_frames if clip_total_frames > 0 else total_frames_full
-        t0 = time.time()
-        for idx in range(total_frames):
-            if cancel_flag.is_set():
+        ctx.reset(_lib.STATE_CLIP)  # ShiftSmoother / TemporalDepthFilter / FocalDepthTracker are per render (1174-1182)
+        ring_in = (_PinnedRing(ctx.lib, 3 * _BATCH, (sh, sw, 3)), _PinnedRing(ctx.lib, 3 * _BATCH, probe_d.shape))
+        ring_out = _PinnedRing(ctx.lib, 2 * _BATCH, oshape)
+        free_in, ready = queue.Queue(), queue.Queue(maxsize=3 * _BATCH)
+        for k in range(3 * _BATCH):
+            free_in.put(k)
+        to_write, free_out = queue.Queue(), queue.Queue()
+        free_out.put(0)
+        free_out.put(1)
+        errors = []
+
+        def reader():
+            try:
+                for frame, depth in _frame_pairs(cap, dcap, win, suspend_flag, cancel_flag):
+                    k = free_in.get()
+                    if stop.is_set():
+                        break
+                    np.copyto(ring_in[0].arrays[k], frame)
+                    np.copyto(ring_in[1].arrays[k], depth)
+                    ready.put(k)
+            except Exception as e:  # surfaced by the main thread
+                errors.append(e)
+            ready.put(None)
+
+        def writer():
+            while True:
+                item = to_write.get()
+                if item is None:
+                    return
+                half, n = item
+                try:
+                    for j in range(n):
+                        sink.write(ring_out.arrays[half * _BATCH + j])
+                except Exception as e:
+                    print(f"❌ FFmpeg write error: {e}" if use_ffmpeg else f"❌ write error: {e}")
+                    errors.append(e)
+                free_out.put(half)
+
+        th_r = threading.Thread(target=reader, daemon=True)
+        th_w = threading.Thread(target=writer, daemon=True)
+        th_r.start()
+        th_w.start()
+        done, t0, eof = 0, time.time(), False
+        while not eof and not errors:
+            slots = []
+            while len(slots) < _BATCH:
+                k = ready.get()
+                if k is None:
+                    eof = True
+                    break
+                slots.append(k)
+            if not slots:
                 break
-            while suspend_flag.is_set() and not cancel_flag.is_set():
-                time.sleep(0.2)
-            if cancel_flag.is_set():
-                break
-            ret1, frame = cap.read()
-            ret2, depth = dcap.read()
-            if not ret1 or not ret2:
-                break
-            final = render_frame(frame, depth, rp, ctx=ctx)
-            out.write(final)
-            if end_s is not None and int(cap.get(cv2.CAP_PROP_POS_FRAMES)) >= end_frame_idx:
-                break
+            half = free_out.get()
+            n = len(slots)
+            fp = (C.c_void_p * n)(*[ring_in[0].ptrs[k] for k in slots])
+            dp = (C.c_void_p * n)(*[ring_in[1].ptrs[k] for k in slots])
+            op = (C.c_void_p * n)(*[ring_out.ptrs[half * _BATCH + j] for j in range(n)])
+            ctx.check(ctx.lib.vd3d_render_clip(ctx.h, n, fp, dp, dch, sh, sw, C.byref(rp), op, _lib.MEM_HOST, None))
+            for k in slots:
+                free_in.put(k)
+            to_write.put((half, n))
+            done += n
+            frac = min(done / max(win.budget, 1), 1.0) * 100.0
             if progress:
-                progress["value"] = (idx / max(total_frames, 1)) * 100.0
+                progress["value"] = frac
                 progress.update()
             if progress_label:
                 el = time.time() - t0
-                progress_label.config(text=f"{(idx / max(total_frames, 1)) * 100.0:.2f}% | "
-                                           f"FPS: {(idx + 1) / max(el, 1e-9):.2f}")
-        if progress:
+                rate = done / max(el, 1e-9)
+                eta = (win.budget - done) / rate if rate > 0 else 0
+                progress_label.config(text=f"{frac:.2f}% | FPS: {rate:.2f} | Elapsed: "
+                                           f"{time.strftime('%H:%M:%S', time.gmtime(el))} | ETA: "
+                                           f"{time.strftime('%H:%M:%S', time.gmtime(max(eta, 0)))}")
+        to_write.put(None)
+        th_w.join()
+        if progress and not cancel_flag.is_set():
             progress["value"] = 100
             progress.update()
     except Exception as e:  # the reference prints and returns None (1477-1478)
         print(f"❌ Render crashed: {e}")
     finally:
-        cap.release(); dcap.release()
-        if out is not None:
-            try:
-                out.release()
-            except Exception:
-                pass
+        stop.set()
+        cap.release()
+        dcap.release()
+        if sink is not None:
+            sink.close()
+        try:
+            if ring_in is not None:
+                _ctx().check(_ctx().lib.vd3d_sync(_ctx().h))
+                ring_in[0].close()
+                ring_in[1].close()
+            if ring_out is not None:
+                ring_out.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------
+# GUI-facing entry points the reference's callers import (VisionDepth3D.py:25-38).  The dialogs themselves are Tk and
+# outside the hot path; the functions keep the reference's call shape so the import list resolves.
+# ---------------------------------------------------------------------------
+# the GUI's encoder vocabulary -> ffmpeg encoder names (interface constants, core/render_3d.py:49-73)
+FFMPEG_CODEC_MAP = {
+    "H.264 / AVC (libx264 - CPU)": "libx264", "H.265 / HEVC (libx265 - CPU)": "libx265",
+    "AV1 (libaom - CPU)": "libaom-av1", "AV1 (SVT - CPU, faster)": "libsvtav1",
+    "MPEG-4 (mp4v - CPU)": "mp4v", "XviD (AVI - CPU)": "XVID", "DivX (AVI - CPU)": "DIVX",
+    "H.264 / AVC (NVENC - NVIDIA GPU)": "h264_nvenc", "H.265 / HEVC (NVENC - NVIDIA GPU)": "hevc_nvenc",
+    "AV1 (NVENC - NVIDIA RTX 40+ GPU)": "av1_nvenc",
+    "H.264 / AVC (AMF - AMD GPU)": "h264_amf", "H.265 / HEVC (AMF - AMD GPU)": "hevc_amf",
+    "AV1 (AMF - AMD RDNA3+)": "av1_amf",
+    "H.264 / AVC (QSV - Intel GPU)": "h264_qsv", "H.265 / HEVC (QSV - Intel GPU)": "hevc_qsv",
+    "VP9 (QSV - Intel GPU)": "vp9_qsv", "AV1 (QSV - Intel ARC / Gen11+)": "av1_qsv",
+}
+original_video_width = None
+original_video_height = None
+
+
+def _val(v):
+    return v.get() if hasattr(v, "get") else v
+
+
+def process_video(
+    input_video_path, selected_depth_map, output_sbs_video_path, selected_codec, fg_shift, mg_shift, bg_shift,
+    sharpness_factor, output_format, selected_aspect_ratio, aspect_ratios, feather_strength, blur_ksize, progress,
+    progress_label, suspend_flag, cancel_flag, use_ffmpeg, selected_ffmpeg_codec, crf_value, use_subject_tracking,
+    use_floating_window, max_pixel_shift, auto_crop_black_bars, parallax_balance, preserve_original_aspect,
+    zero_parallax_strength, enable_edge_masking, enable_feathering, skip_blank_frames, dof_strength,
+    convergence_strength, enable_dynamic_convergence, depth_pop_gamma, depth_pop_mid, depth_stretch_lo,
+    depth_stretch_hi, fg_pop_multiplier, bg_push_multiplier, subject_lock_strength, color_saturation,
+    color_contrast, color_brightness, ipd_value=0.0, start_s=None, end_s=None,
+):
+    """core/render_3d.py:1594-1753: unwrap the GUI variables (anything with .get()), derive the output size from the
+    source video and the format, and run render_sbs_3d for the four SBS-family formats (VR is not dispatched by the
+    reference either).  Errors the reference reports through message boxes are printed."""
+    global original_video_width, original_video_height
+    import cv2
+    src, dep, dst = _val(input_video_path), _val(selected_depth_map), _val(output_sbs_video_path)
+    if not src or not dst or not dep:
+        print("Error: Please select input video, depth map, and output path.")
+        return
+    probe = cv2.VideoCapture(src)
+    width = int(probe.get(cv2.CAP_PROP_FRAME_WIDTH))
+    height = int(probe.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    rate = probe.get(cv2.CAP_PROP_FPS)
+    probe.release()
+    if rate <= 0:
+        print("Error: Unable to retrieve FPS from the input video.")
+        return
+    original_video_width, original_video_height = width, height
+    ratio = aspect_ratios.get(_val(selected_aspect_ratio), 16 / 9)
+    fmt = _val(output_format)
+    if _val(preserve_original_aspect) or fmt == "Half-SBS":
+        out_w, out_h = width, height
+    elif fmt == "Full-SBS":
+        out_w, out_h = width * 2, height
+    elif fmt == "VR":
+        out_w, out_h = 4096, int(4096 / ratio)
+    else:
+        out_w, out_h = width, int(width / ratio)
+    if progress is not None:
+        progress["value"] = 0
+        progress.update()
+    if progress_label is not None:
+        progress_label.config(text="0%")
+    if fmt not in ("Full-SBS", "Half-SBS", "Red-Cyan Anaglyph", "Passive Interlaced"):
+        return
+    codec_name = _val(selected_ffmpeg_codec)
+    render_sbs_3d(
+        src, dep, dst, _val(selected_codec), rate, out_w, out_h, _val(fg_shift), _val(mg_shift), _val(bg_shift),
+        _val(sharpness_factor), fmt, selected_aspect_ratio, aspect_ratios,
+        feather_strength=_val(feather_strength), blur_ksize=_val(blur_ksize), use_ffmpeg=_val(use_ffmpeg),
+        selected_ffmpeg_codec=FFMPEG_CODEC_MAP.get(codec_name, codec_name), crf_value=_val(crf_value),
+        use_subject_tracking=_val(use_subject_tracking), use_floating_window=_val(use_floating_window),
+        max_pixel_shift_percent=_val(max_pixel_shift), progress=progress, progress_label=progress_label,
+        suspend_flag=suspend_flag, cancel_flag=cancel_flag, auto_crop_black_bars=_val(auto_crop_black_bars),
+        parallax_balance=_val(parallax_balance), preserve_original_aspect=_val(preserve_original_aspect),
+        zero_parallax_strength=_val(zero_parallax_strength), enable_edge_masking=_val(enable_edge_masking),
+        enable_feathering=_val(enable_feathering), skip_blank_frames=_val(skip_blank_frames),
+        dof_strength=_val(dof_strength), original_video_width=width, original_video_height=height,
+        convergence_strength=_val(convergence_strength), enable_dynamic_convergence=_val(enable_dynamic_convergence),
+        ipd_factor=ipd_value, depth_pop_gamma=_val(depth_pop_gamma), depth_pop_mid=_val(depth_pop_mid),
+        depth_stretch_lo=_val(depth_stretch_lo), depth_stretch_hi=_val(depth_stretch_hi),
+        fg_pop_multiplier=_val(fg_pop_multiplier), bg_push_multiplier=_val(bg_push_multiplier),
+        subject_lock_strength=_val(subject_lock_strength), color_saturation=_val(color_saturation),
+        color_contrast=_val(color_contrast), color_brightness=_val(color_brightness), start_s=start_s, end_s=end_s)
+
+
+def _dialog(kind, **kw):
+    try:
+        from tkinter import filedialog
+    except Exception as e:  # headless box: the dialogs are GUI-only
+        raise RuntimeError("file dialogs need tkinter (GUI helper, outside the B200 hot path)") from e
+    return getattr(filedialog, kind)(**kw)
+
+
+_VIDEO_TYPES = [("Video files", "*.mp4 *.avi *.mkv")]
+
+
+def select_input_video(input_video_path, video_thumbnail_label, video_specs_label, update_aspect_preview,
+                       original_video_width, original_video_height):
+    """core/render_3d.py:1507-1556 without the thumbnail: pick a file, publish its size / fps to the GUI variables."""
+    import cv2
+    path = _dialog("askopenfilename", filetypes=_VIDEO_TYPES)
+    if not path:
+        return
+    input_video_path.set(path)
+    cap = cv2.VideoCapture(path)
+    if not cap.isOpened():
+        print("Error: Unable to open video file.")
+        return
+    w, h = int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+    rate = cap.get(cv2.CAP_PROP_FPS)
+    cap.release()
+    original_video_width.set(w)
+    original_video_height.set(h)
+    if video_specs_label is not None:
+        video_specs_label.config(text=f"Video Info:\nResolution: {w}x{h}\nFPS: {rate:.2f}")
+    if update_aspect_preview is not None:
+        update_aspect_preview()
+
+
+def select_output_video(output_sbs_video_path):
+    """core/render_3d.py:1568-1578."""
+    output_sbs_video_path.set(_dialog("asksaveasfilename", defaultextension=".mp4",
+                                      filetypes=[("MP4 files", "*.mp4"), ("MKV files", "*.mkv"), ("AVI files", "*.avi")]))
+
+
+def select_depth_map(selected_depth_map, depth_map_label):
+    """core/render_3d.py:1581-1591."""
+    import os
+    path = _dialog("askopenfilename", filetypes=_VIDEO_TYPES)
+    if not path:
+        return
+    selected_depth_map.set(path)
+    if depth_map_label is not None:
+        depth_map_label.config(text=f"Selected Depth Map:\n{os.path.basename(path)}")
