@@ -323,7 +323,9 @@ class GpuArm:
             with torch.device("meta"):
                 sd = DepthAnythingForDepthEstimation(hf_config(wl["model"])).state_dict()
         sd = broadcast_state_dict(sd, src=0, device=self.dev)
-        self.deng = DepthEngine(wl["model"], 518, 924, ctx=self.ctx)
+        from visiondepth3d_b200.depth_engine import processed_size
+        ih, iw = processed_size(wl["w"], wl["h"])     # what the DPT processor picks for this frame shape (518 x 924)
+        self.deng = DepthEngine(wl["model"], ih, iw, ctx=self.ctx)
         self.deng.load_state_dict(sd)
         del sd
         self.rp = render_params(R, wl)

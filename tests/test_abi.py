@@ -132,3 +132,70 @@ def test_create_fails_loudly_without_gpu(lib):
         pytest.skip("GPU present")
     with pytest.raises(_lib.Vd3dError, match="no CPU fallback"):
         _lib.Context(0)
+
+
+def test_callers_import_lists_resolve():
+    """The exact names the reference's callers import from core.render_3d / core.render_depth
+    (VisionDepth3D.py:25-53, core/preview_gui.py:12-21, core/__init__.py:3-19) exist on the drop-ins."""
+    from visiondepth3d_b200.render_3d import (  # noqa: F401  VisionDepth3D.py:25-38
+        render_sbs_3d, format_3d_output, frame_to_tensor, depth_to_tensor, tensor_to_frame, pixel_shift_cuda,
+        generate_anaglyph_3d, apply_sharpening, select_input_video, select_depth_map, select_output_video,
+        process_video)
+    from visiondepth3d_b200.render_depth import (  # noqa: F401  VisionDepth3D.py:41-53
+        ensure_model_downloaded, update_pipeline, open_image, open_video, choose_output_directory, process_image,
+        process_image_folder, process_images_in_folder, process_videos_in_folder, update_progress, cancel_requested)
+    from visiondepth3d_b200.render_3d import (  # noqa: F401  core/preview_gui.py:12-21
+        frame_to_tensor, depth_to_tensor, pixel_shift_cuda, apply_sharpening, tensor_to_frame, pad_to_aspect_ratio,
+        format_3d_output, apply_color_grade)
+    from visiondepth3d_b200.render_3d import aspect_ratios  # noqa: F401  core/__init__.py:3-10
+    from visiondepth3d_b200.render_depth import process_video_folder  # noqa: F401  core/__init__.py:12-19
+    import visiondepth3d_b200.render_depth as RD
+    assert RD.pipe is None and RD.pipe_type is None  # module globals the callers read (core/render_depth.py:34-36)
+    assert RD.ensure_model_downloaded("depth-anything/Depth-Anything-V2-Small-hf") == (None, None)  # no weights offline
+
+
+def test_process_video_unwraps_gui_variables(monkeypatch, tmp_path):
+    """process_video (core/render_3d.py:1594-1753): .get() unwrapping, output size per format, dispatch."""
+    import cv2
+    import numpy as np
+    from visiondepth3d_b200 import render_3d as R
+
+    class V:
+        def __init__(self, v):
+            self.v = v
+
+        def get(self):
+            return self.v
+
+    src = str(tmp_path / "in.avi")
+    wr = cv2.VideoWriter(src, cv2.VideoWriter_fourcc(*"MJPG"), 25.0, (64, 36))
+    for _ in range(3):
+        wr.write(np.zeros((36, 64, 3), np.uint8))
+    wr.release()
+    seen = {}
+    monkeypatch.setattr(R, "render_sbs_3d", lambda *a, **k: seen.update(a=a, k=k))
+
+    class W:
+        def __setitem__(self, k, v):
+            pass
+
+        def update(self):
+            pass
+
+        def config(self, **k):
+            pass
+
+    args = [V(src), V("d.avi"), V("o.mp4"), V("XVID"), V(4.5), V(-1.5), V(-6.0), V(0.2), V("Full-SBS"), V("Default (16:9)"),
+            R.aspect_ratios, V(10.0), V(9), W(), W(), None, None, V(False), V("H.264 / AVC (NVENC - NVIDIA GPU)"), V(23), V(True), V(True),
+            V(0.02), V(False), V(0.8), V(False), V(0.01), V(True), V(True), V(False), V(0.0), V(0.0), V(True), V(0.85), V(0.5),
+            V(0.05), V(0.95), V(1.2), V(1.1), V(1.0), V(1.0), 1.0, V(0.0)]
+    R.process_video(*args, ipd_value=0.9, start_s=1.0, end_s=None)
+    assert seen["a"][:7] == (src, "d.avi", "o.mp4", "XVID", 25.0, 128, 36)
+    assert seen["a"][7:12] == (4.5, -1.5, -6.0, 0.2, "Full-SBS")
+    k = seen["k"]
+    assert k["selected_ffmpeg_codec"] == "h264_nvenc" and k["ipd_factor"] == 0.9 and k["start_s"] == 1.0
+    assert k["original_video_width"] == 64 and k["color_contrast"] == 1.0 and k["max_pixel_shift_percent"] == 0.02
+    seen.clear()
+    args[8] = V("VR")       # not dispatched by the reference either
+    R.process_video(*args)
+    assert not seen

@@ -51,11 +51,98 @@ def test_render_sbs_3d_video_loop(tmp_path):
     # the two half-width eyes differ (there is parallax) and are not black
     half = w // 2
     assert frames[2].mean() > 10 and np.abs(frames[2][:, :half].astype(int) - frames[2][:, half:].astype(int)).mean() > 0.05
-    # unsupported options return early like the reference's error paths (no exception escapes)
-    assert R.render_sbs_3d(rgb, dep, out, "MJPG", 24.0, w, h, 4.5, -1.5, -6.0, 0.2, "Half-SBS",
-                           _Var("Default (16:9)"), R.aspect_ratios, 0.0, use_ffmpeg=True) is None
-    assert R.render_sbs_3d("missing.avi", dep, out, "MJPG", 24.0, w, h, 4.5, -1.5, -6.0, 0.2, "Half-SBS",
+    # content: what reached the writer equals the frame loop run by hand on the decoded inputs (same decoder, state
+    # reset like a fresh render, first pair dropped), bit for bit -- the writer's codec is the only loss
+    expected = _by_hand(R, rgb, dep, w, h)
+    assert len(expected) == n - 1
+    for k, (a, b) in enumerate(zip(frames, expected)):
+        mse = float(((a.astype(np.float64) - b) ** 2).mean())
+        assert 10 * np.log10(255.0 ** 2 / max(mse, 1e-9)) > 30.0, k   # MJPG round trip of the same picture
+    # unsupported options return early like the reference's error paths (no exception escapes, no file left behind)
+    out2 = str(tmp_path / "out2.avi")
+    assert R.render_sbs_3d(rgb, dep, out2, "MJPG", 24.0, w, h, 4.5, -1.5, -6.0, 0.2, "Half-SBS",
+                           _Var("Default (16:9)"), R.aspect_ratios, 0.0, skip_blank_frames=True) is None
+    assert not os.path.exists(out2)
+    assert R.render_sbs_3d("missing.avi", dep, out2, "MJPG", 24.0, w, h, 4.5, -1.5, -6.0, 0.2, "Half-SBS",
                            _Var("Default (16:9)"), R.aspect_ratios, 0.0) is None
+    assert not os.path.exists(out2)
+
+
+def _by_hand(R, rgb, dep, w, h, **kw):
+    import cv2
+    rp = R.make_render_params(w, h, 4.5, -1.5, -6.0, 0.2, kw.get("fmt", "Half-SBS"), 16 / 9, 0.0, 10.0, 9, True, True,
+                              zero_parallax_strength=0.01, preserve_original_aspect=kw.get("preserve", False))
+    R.reset_temporal_state(global_state=False)
+    ca, cb = cv2.VideoCapture(rgb), cv2.VideoCapture(dep)
+    ca.read(), cb.read()
+    outs = []
+    while True:
+        ok1, f = ca.read()
+        ok2, d = cb.read()
+        if not (ok1 and ok2):
+            break
+        outs.append(R.render_frame(f, d, rp))
+    return outs
+
+
+def _write_inputs(tmp_path, w, h, n, kind="natural"):
+    import cv2
+    from visiondepth3d_b200.synth import synth_frame
+    rgb, dep = str(tmp_path / "rgb.avi"), str(tmp_path / "depth.avi")
+    fourcc = cv2.VideoWriter_fourcc(*"MJPG")
+    wr, wd = cv2.VideoWriter(rgb, fourcc, 24.0, (w, h)), cv2.VideoWriter(dep, fourcc, 24.0, (w, h))
+    for i in range(n):
+        f, d = synth_frame(i, w, h, kind)
+        wr.write(f)
+        wd.write(d)
+    wr.release()
+    wd.release()
+    return rgb, dep
+
+
+def test_render_sbs_3d_ffmpeg_pipe_is_exact(tmp_path, monkeypatch):
+    """use_ffmpeg: raw bgr24 frames of out_width x out_height go to the stdin of `ffmpeg ... -f rawvideo -pix_fmt bgr24
+    -s WxH -r fps -i - ...` (core/render_3d.py:1143-1163, 1422-1427).  A stand-in `ffmpeg` on PATH records its argv and
+    stdin: the bytes must equal the frame loop run by hand, and 20 frames cross three pipelined batches."""
+    import stat
+    from visiondepth3d_b200 import render_3d as R
+    w, h, n = 320, 180, 21
+    rgb, dep = _write_inputs(tmp_path, w, h, n)
+    fake = tmp_path / "bin"
+    fake.mkdir()
+    script = fake / "ffmpeg"
+    script.write_text('#!/bin/sh\nfor a in "$@"; do last="$a"; done\necho "$@" > "$last.argv"\ncat > "$last.raw"\n')
+    script.chmod(script.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(fake) + os.pathsep + os.environ.get("PATH", ""))
+    out = str(tmp_path / "out.mp4")
+    R.reset_temporal_state()
+    R.render_sbs_3d(rgb, dep, out, "mp4v", 24.0, w, h, 4.5, -1.5, -6.0, 0.2, "Full-SBS",
+                    _Var("Default (16:9)"), R.aspect_ratios, 0.0, feather_strength=10.0, blur_ksize=9,
+                    use_ffmpeg=True, selected_ffmpeg_codec="libx264", crf_value=19,
+                    use_subject_tracking=True, use_floating_window=True, preserve_original_aspect=True,
+                    suspend_flag=threading.Event(), cancel_flag=threading.Event(), zero_parallax_strength=0.01)
+    argv = open(out + ".argv").read().split()
+    assert argv[:11] == ["-y", "-f", "rawvideo", "-vcodec", "rawvideo", "-pix_fmt", "bgr24", "-s", f"{2 * w}x{h}", "-r", "24.0"]
+    assert "libx264" in argv and argv[argv.index("-crf") + 1] == "19"
+    raw = np.fromfile(out + ".raw", dtype=np.uint8)
+    assert raw.size == (n - 1) * h * 2 * w * 3
+    got = raw.reshape(n - 1, h, 2 * w, 3)
+    R.reset_temporal_state()
+    expected = _by_hand(R, rgb, dep, w, h, fmt="Full-SBS", preserve=True)
+    for k in range(n - 1):
+        assert np.array_equal(got[k], expected[k]), k
+
+
+def test_clip_window_arithmetic():
+    """start_s / end_s -> frame indices exactly as core/render_3d.py:1004-1030 computes them."""
+    from visiondepth3d_b200.render_3d import _ClipWindow
+    wn = _ClipWindow(240, 24.0, None, None)
+    assert (wn.empty, wn.first, wn.stop, wn.budget, wn.bounded) == (False, 0, 240, 240, False)
+    wn = _ClipWindow(240, 24.0, 1.0, 2.5)
+    assert (wn.first, wn.stop, wn.budget, wn.bounded) == (24, 60, 36, True)
+    wn = _ClipWindow(240, 23.976, 0.52, 100.0)      # end clamped to the clip, rounding of the start index
+    assert (wn.first, wn.stop) == (int(round(0.52 * 23.976)), int(round((240 / 23.976) * 23.976)))
+    assert _ClipWindow(240, 24.0, 5.0, 5.0).empty and _ClipWindow(240, 24.0, 11.0, None).empty
 
 
 def test_pipe_protocol():

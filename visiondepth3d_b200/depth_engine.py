@@ -8,6 +8,19 @@ from . import _lib
 from .depth_weights import CONFIGS, prepare
 
 
+def processed_size(width, height, target=518, multiple=14):
+    """(h, w) the DPT image processor resizes a (width, height) image to: keep the aspect ratio, scale the side
+    that is closer to `target`, round both to multiples of 14 (transformers image_processing_dpt.py,
+    get_resize_output_image_size with keep_aspect_ratio=True, ensure_multiple_of=14)."""
+    sh, sw = target / height, target / width
+    if abs(1 - sw) < abs(1 - sh):
+        sh = sw
+    else:
+        sw = sh
+    rnd = lambda v: max(multiple, int(round(v / multiple) * multiple))  # noqa: E731
+    return rnd(sh * height), rnd(sw * width)
+
+
 class DepthConfig(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32), ("taps", C.c_int32 * 4),
                 ("neck", C.c_int32 * 4), ("fusion", C.c_int32), ("image_h", C.c_int32), ("image_w", C.c_int32)]
@@ -93,15 +106,24 @@ class DepthEngine:
         self.check(self.lib.vd3d_depth_forward(self.h, pv.ctypes.data, out.ctypes.data, _lib.MEM_HOST))
         return out
 
-    def infer(self, frame_bgr, invert=False):
-        """BGR u8 [h,w,3] -> (predicted_depth f32 [h,w] resized to the frame, min-max u8 [h,w])."""
+    def infer(self, frame_bgr, invert=False, check_size=True):
+        """BGR u8 [h,w,3] -> (predicted_depth f32 [h,w] resized to the frame, min-max u8 [h,w]).
+        check_size: refuse frames whose DPT processed size differs from the one this engine was built for (the HF
+        processor would pick another keep-aspect /14 size, so the depth would differ from the reference's)."""
         f = np.ascontiguousarray(frame_bgr, dtype=np.uint8)
         h, w = f.shape[:2]
+        if check_size and processed_size(w, h) != (self.image_h, self.image_w):
+            raise ValueError(f"engine built for processed size {(self.image_h, self.image_w)}, a {w}x{h} frame needs "
+                             f"{processed_size(w, h)}")
         d32 = np.empty((h, w), dtype=np.float32)
         d8 = np.empty((h, w), dtype=np.uint8)
         self.check(self.lib.vd3d_depth_infer(self.h, f.ctypes.data, h, w, d32.ctypes.data, d8.ctypes.data,
                                              int(bool(invert))))
         return d32, d8
+
+    def infer_batch(self, frames_bgr, invert=False, check_size=True):
+        """List of same-shape BGR frames -> list of (predicted_depth f32, min-max u8)."""
+        return [self.infer(f, invert=invert, check_size=check_size) for f in frames_bgr]
 
     def get_buffer(self, name, shape, dtype):
         out = np.empty(shape, dtype=dtype)
