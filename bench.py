@@ -47,7 +47,7 @@ WORKLOADS = {
                   dibr_bytes=3 * 1920 * 1080 + 1920 * 1080 + 8 * 960 * 540 + 3 * 1920 * 1080),
     # BASELINE.json configs[2] (per-GPU share of the 1000-frame clip)
     "4k": dict(name="4K synthetic clip, Depth-Anything-V2-Large, Full-SBS (per-GPU share of the 1000-frame clip)",
-               w=3840, h=2160, fmt="Full-SBS", preserve=True, model="vitl", pool=10, frames_per_step=10,
+               w=3840, h=2160, fmt="Full-SBS", preserve=True, model="vitl", pool=12, frames_per_step=12,
                dibr_bytes=18 * 3840 * 2160),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused render kernel from `ncu --set full`
@@ -462,10 +462,12 @@ class GpuArm:
                 "timed_frames": frames, "timed_region_s": ms / 1000.0,
                 "pool_mb": self.in_bytes / 1e6,
                 "stage": "DPT processor + depth forward + min-max u8 handoff in HBM + DIBR frame loop + pack",
-                "launch_mode": "CUDA graph replay; depth forwards of consecutive frames overlap on three streams "
+                "launch_mode": "CUDA graph replay; one batched depth forward per group of depth_batch frames on two "
+                               "alternating engine instances / streams, DIBR frame by frame behind it "
                                "(stage timings in roofline* are taken in a separate serial, eager pass)",
                 "dibr_mode": "exact" if args.exact else "fast",
                 "graphs_active": int(lib.vd3d_graphs_active(ctx.h)),
+                "depth_batch": int(lib.vd3d_get_depth_batch(ctx.h)),
             },
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -269,7 +269,17 @@ int vd3d_depth_infer(vd3d_depth* e, const uint8_t* frame_bgr, int h, int w, floa
                      int invert);
 int vd3d_depth_infer_device(vd3d_depth* e, const uint8_t* frame_bgr_dev, int h, int w, uint8_t* depth_u8_dev,
                             float* depth_f32_dev_or_null, int invert);
-/* copy an internal activation buffer to the host (parity triage: "x", "tap0".., "f0".., "fused3") */
+/* The same for B (1..8) frames of one size with ONE batched forward: the token-wise GEMMs see the stacked token
+ * matrix of all frames (the reference hands the whole list to the HF pipeline too, core/render_depth.py:1113-1119).
+ * Arrays of B pointers; depth_f32 / depth_u8 (or single entries) may be NULL. */
+int vd3d_depth_infer_batch(vd3d_depth* e, int B, const uint8_t* const* frames_bgr, int h, int w, float* const* depth_f32,
+                           uint8_t* const* depth_u8, int invert);
+int vd3d_depth_infer_batch_device(vd3d_depth* e, int B, const uint8_t* const* frames_bgr_dev, int h, int w,
+                                  uint8_t* const* depth_u8_dev, float* const* depth_f32_dev, int invert);
+/* frames per depth forward inside vd3d_render_clip_depth (1..4, default 3; env VD3D_DEPTH_BATCH) */
+int vd3d_set_depth_batch(vd3d_ctx* ctx, int frames);
+int vd3d_get_depth_batch(vd3d_ctx* ctx);
+/* copy an internal activation buffer to the host (parity triage: "x", "tap0.0".., "f0".., "fused3") */
 int vd3d_depth_get_buffer(vd3d_depth* e, const char* name, void* host_out, size_t bytes);
 /* unit-test hooks for the tensor-core kernels */
 int vd3d_gemm_f16(vd3d_depth* e, const void* A_f16, const void* B_f16, int M, int N, int K, float* C_host, int bn);

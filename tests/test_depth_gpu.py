@@ -223,6 +223,24 @@ def test_infer_matches_hf_pipeline_stages():
     e.close()
 
 
+def test_infer_batch_equals_single_frames():
+    """One batched forward (stacked token matrix, attention with grid.y = images * heads) against frame-by-frame
+    inference: rows of a GEMM do not depend on the other rows, so the results are the same bits."""
+    from visiondepth3d_b200.depth_engine import DepthEngine
+    from visiondepth3d_b200.synth import synth_frame
+    sd = _model("vits")
+    e = DepthEngine("vits", 518, 924)
+    e.load_state_dict(sd)
+    frames = [synth_frame(i, 1280, 720, "natural")[0] for i in range(5)]
+    single = [e.infer(f) for f in frames]
+    for nb in (2, 3, 5):
+        batch = e.infer_batch(frames[:nb])
+        for k in range(nb):
+            assert np.array_equal(batch[k][1], single[k][1]), (nb, k)
+            assert np.abs(batch[k][0] - single[k][0]).max() <= 1e-6 * np.abs(single[k][0]).max(), (nb, k)
+    e.close()
+
+
 def test_clip_depth_pipeline_equals_stagewise():
     """vd3d_render_clip_depth (two depth streams + graphs + in-HBM u8 handoff) must equal
     depth inference followed by vd3d_render_frame with that u8 depth, frame by frame."""
@@ -237,7 +255,7 @@ def test_clip_depth_pipeline_equals_stagewise():
     e.load_state_dict(sd)
     rp = R.make_render_params(w, h, 4.5, -1.5, -6.0, 0.2, "Half-SBS", 16 / 9, 0.0, 10.0, 9, True, True,
                               zero_parallax_strength=0.01)
-    frames = [synth_frame(i, w, h, "smooth")[0] for i in range(7)]
+    frames = [synth_frame(i, w, h, "smooth")[0] for i in range(11)]   # 3 + 3 + 3 + 2: two engine instances, a tail batch
     ctx = e.ctx
     ctx.reset()
     ref = []

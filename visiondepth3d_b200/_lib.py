@@ -87,7 +87,8 @@ SYMBOLS = [
     # depth forward (bound in depth_engine.py)
     "vd3d_depth_create", "vd3d_depth_destroy", "vd3d_depth_last_error", "vd3d_depth_launch_count",
     "vd3d_depth_set_tensor", "vd3d_depth_forward", "vd3d_depth_get_buffer", "vd3d_gemm_f16", "vd3d_gemm_bench", "vd3d_conv_f16",
-    "vd3d_depth_infer", "vd3d_depth_infer_device", "vd3d_render_clip_depth", "vd3d_depth_add_launches", "vd3d_depth_clone", "vd3d_release_depth",
+    "vd3d_depth_infer", "vd3d_depth_infer_device", "vd3d_depth_infer_batch", "vd3d_depth_infer_batch_device",
+    "vd3d_set_depth_batch", "vd3d_get_depth_batch", "vd3d_render_clip_depth", "vd3d_depth_add_launches", "vd3d_depth_clone", "vd3d_release_depth",
     "vd3d_depth_profile", "vd3d_depth_profile_collect",
     "vd3d_advance_state", "vd3d_state_bytes", "vd3d_export_state", "vd3d_import_state",
 ]
@@ -138,6 +139,10 @@ def load():
     lib.vd3d_set_graphs.restype = i
     lib.vd3d_set_exact.argtypes = [vp, i]
     lib.vd3d_set_exact.restype = i
+    lib.vd3d_set_depth_batch.argtypes = [vp, i]
+    lib.vd3d_set_depth_batch.restype = i
+    lib.vd3d_get_depth_batch.argtypes = [vp]
+    lib.vd3d_get_depth_batch.restype = i
     lib.vd3d_get_exact.argtypes = [vp]
     lib.vd3d_get_exact.restype = i
     lib.vd3d_graphs_active.argtypes = [vp]

@@ -60,6 +60,7 @@ struct vd3d_depth {
   // optional device timing of one GEMM class (the fc1 launches) for the roofline report
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;
+  int prof_rows = 0;  // rows (tokens of all images of the batch) of the timed fc1 launches
 };
 
 namespace {
@@ -280,7 +281,8 @@ int vd3d_depth_profile_collect(vd3d_depth* e, double* total_ms, int* count, doub
   e->prof_ev.clear();
   *total_ms = t;
   *count = n;
-  if (gflop_per_launch) *gflop_per_launch = 2.0 * e->ntok * (4.0 * e->cfg.hidden) * e->cfg.hidden / 1e9;
+  if (gflop_per_launch)
+    *gflop_per_launch = 2.0 * (e->prof_rows ? e->prof_rows : e->ntok) * (4.0 * e->cfg.hidden) * e->cfg.hidden / 1e9;
   return VD3D_OK;
 }
 
@@ -441,9 +443,19 @@ int vd3d_conv_f16(vd3d_depth* e, const void* in_nhwc, int H, int W, int cin, con
   return VD3D_OK;
 }
 
-// pixel_values: f32 [3, image_h, image_w] (already resized + normalised); depth_out f32 [image_h, image_w]
-int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_out, int mem) {
-  if (!e || !pixel_values || !depth_out) return VD3D_ERR_ARG;
+}  // extern "C"
+
+namespace {
+
+constexpr int kMaxBatch = 8;
+
+// B images through the network in one pass.  The token-wise stages (LayerNorm, QKV / proj / fc1 / fc2 GEMMs) see one
+// matrix of (B-1)*NP + NT rows -- image b owns rows [b*NP, b*NP + NT), NP = NT rounded up to the 128-row tile -- so the
+// GEMMs run at 3-4x the rows of one frame (the reference batches too: core/render_depth.py:1113-1119); attention runs
+// with grid.y = B * heads; patch embedding, taps, neck and head stay per image (their maps are per-image 2-D tensors).
+// px_dev / depth_dev: DEVICE pointers, f32 [3, image_h, image_w] in, f32 [image_h, image_w] out.
+int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const* depth_dev) {
+  if (B < 1 || B > kMaxBatch) return dfail(e, VD3D_ERR_ARG, "batch must be in [1, 8]");
   const vd3d_depth_config& c = e->cfg;
   cudaStream_t s = e->stream;
   const int D = c.hidden, L = c.layers, Hh = c.heads, F = c.fusion;
@@ -453,27 +465,22 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
   int r;
   char nm[96];
   // ---- buffers ----
-  void *px_d, *x, *xn, *q, *k, *vt, *S, *P, *attn, *hb, *ape, *depth_d;
-  if (mem == VD3D_MEM_HOST) {
-    if ((r = get_buf(e, "px", (size_t)3 * IH * IW * 4, &px_d))) return r;
-    DCK(cudaMemcpyAsync(px_d, pixel_values, (size_t)3 * IH * IW * 4, cudaMemcpyHostToDevice, s));
-  } else {
-    px_d = (void*)pixel_values;
-  }
-  if ((r = get_buf(e, "x", (size_t)NP * D * 4, &x))) return r;
-  if ((r = get_buf(e, "xn", (size_t)NP * D * 2, &xn))) return r;
-  if ((r = get_buf(e, "q", (size_t)Hh * NP * 64 * 2, &q))) return r;
-  if ((r = get_buf(e, "k", (size_t)Hh * NP * 64 * 2, &k))) return r;
-  if ((r = get_buf(e, "vt", (size_t)Hh * 64 * NP * 2, &vt))) return r;
+  void *x, *xn, *q, *k, *vt, *S, *P, *attn, *hb, *ape;
+  const int MT = (B - 1) * NP + NT;  // rows of the stacked token matrix
+  if (B > 1 && !e->flash) return dfail(e, VD3D_ERR_UNSUPPORTED, "batched forward needs the fused attention kernel");
+  if ((r = get_buf(e, "x", (size_t)B * NP * D * 4, &x))) return r;
+  if ((r = get_buf(e, "xn", (size_t)B * NP * D * 2, &xn))) return r;
+  if ((r = get_buf(e, "q", (size_t)B * Hh * NP * 64 * 2, &q))) return r;
+  if ((r = get_buf(e, "k", (size_t)B * Hh * NP * 64 * 2, &k))) return r;
+  if ((r = get_buf(e, "vt", (size_t)B * Hh * 64 * NP * 2, &vt))) return r;
   S = P = nullptr;
   if (!e->flash) {
     if ((r = get_buf(e, "S", (size_t)Hh * NP * NP * 4, &S))) return r;
     if ((r = get_buf(e, "P", (size_t)Hh * NP * NP * 2, &P))) return r;
   }
-  if ((r = get_buf(e, "attn", (size_t)NP * D * 2, &attn))) return r;
-  if ((r = get_buf(e, "h", (size_t)NP * 4 * D * 2, &hb))) return r;
+  if ((r = get_buf(e, "attn", (size_t)B * NP * D * 2, &attn))) return r;
+  if ((r = get_buf(e, "h", (size_t)B * NP * 4 * D * 2, &hb))) return r;
   if ((r = get_buf(e, "ape", (size_t)NPATCH * KPE * 2, &ape))) return r;
-  if ((r = get_buf(e, "depth", (size_t)IH * IW * 4, &depth_d))) return r;
 
   // ---- patch embedding + CLS + position embeddings ----
   const __half* pe_w;
@@ -481,17 +488,21 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
   if ((r = W(e, "pe.w", &pe_w, (size_t)D * KPE)) || (r = W(e, "pe.b", &pe_b, D)) || (r = W(e, "cls", &cls, D)) ||
       (r = W(e, "pos", &pos, (size_t)NT * D)))
     return r;
-  launch_patch_im2col((const float*)px_d, IH, IW, ph, pw, (__half*)ape, KPE, s);
-  {
+  for (int b = 0; b < B; ++b) {
+    float* xb = (float*)x + (size_t)b * NP * D;
+    launch_patch_im2col(px_dev[b], IH, IW, ph, pw, (__half*)ape, KPE, s);
     GemmArgs g = base_args(NPATCH, D, KPE, EPI_PATCH);
-    g.out_f32 = (float*)x;
+    g.out_f32 = xb;
     g.bias = pe_b;
     g.pos = pos;
     g.ldc = D;
     if ((r = gemm(e, (const __half*)ape, KPE, pe_w, KPE, g))) return r;
+    launch_set_cls(xb, cls, pos, D, s);
+    e->launches += 2;
+    // rows [NT, NP) of every image but the last take part in the stacked GEMMs: keep them at zero so that they stay
+    // finite from frame to frame (they are never read as keys / values: the attention tensor maps end at NT)
+    if (b + 1 < B) DCK(cudaMemsetAsync(xb + (size_t)NT * D, 0, (size_t)(NP - NT) * D * 4, s));
   }
-  launch_set_cls((float*)x, cls, pos, D, s);
-  e->launches += 2;
 
   // ---- transformer blocks ----
   int tap_idx = 0;
@@ -510,9 +521,9 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
         (r = W(e, nmf("fc2.w"), &wf2, (size_t)4 * D * D)) || (r = W(e, nmf("fc2.b"), &bf2, D)) ||
         (r = W(e, nmf("ls2"), &ls2, D)))
       return r;
-    launch_layernorm((const float*)x, NT, D, g1, b1, (__half*)xn, 0, s);
+    launch_layernorm((const float*)x, MT, D, g1, b1, (__half*)xn, 0, s);
     {
-      GemmArgs g = base_args(NT, 3 * D, D, EPI_QKV);
+      GemmArgs g = base_args(MT, 3 * D, D, EPI_QKV);
       g.bias = bqkv;
       g.q = (__half*)q;
       g.k = (__half*)k;
@@ -526,10 +537,10 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
     if (e->flash) {
       // fused tcgen05 attention: scores stay in TMEM, probabilities in shared memory
       CUtensorMap mq, mk, mv;
-      if ((r = make_map(e, &mq, q, 64, NT, Hh, 64, (uint64_t)NP * 64, 128, 1))) return r;
-      if ((r = make_map(e, &mk, k, 64, NT, Hh, 64, (uint64_t)NP * 64, 128, 1))) return r;
-      if ((r = make_map(e, &mv, vt, NT, 64, Hh, NP, (uint64_t)64 * NP, 64, 1))) return r;
-      cudaError_t ce = launch_attention(mq, mk, mv, NT, D, (__half*)attn, Hh, s);
+      if ((r = make_map(e, &mq, q, 64, NT, B * Hh, 64, (uint64_t)NP * 64, 128, 1))) return r;
+      if ((r = make_map(e, &mk, k, 64, NT, B * Hh, 64, (uint64_t)NP * 64, 128, 1))) return r;
+      if ((r = make_map(e, &mv, vt, NT, 64, B * Hh, NP, (uint64_t)64 * NP, 64, 1))) return r;
+      cudaError_t ce = launch_attention(mq, mk, mv, NT, D, (__half*)attn, Hh, B, NP, s);
       if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(ce));
       e->launches++;
     } else {
@@ -555,16 +566,16 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
       }
     }
     {
-      GemmArgs g = base_args(NT, D, D, EPI_RESID_LS);
+      GemmArgs g = base_args(MT, D, D, EPI_RESID_LS);
       g.out_f32 = (float*)x;
       g.bias = bo;
       g.ls = ls1;
       g.ldc = D;
       if ((r = gemm(e, (const __half*)attn, D, wo, D, g))) return r;
     }
-    launch_layernorm((const float*)x, NT, D, g2, b2, (__half*)xn, 0, s);
+    launch_layernorm((const float*)x, MT, D, g2, b2, (__half*)xn, 0, s);
     {
-      GemmArgs g = base_args(NT, 4 * D, D, EPI_F16);
+      GemmArgs g = base_args(MT, 4 * D, D, EPI_F16);
       g.out_f16 = (__half*)hb;
       g.bias = bf1;
       g.act = 1;
@@ -574,6 +585,7 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0, s);
+        e->prof_rows = MT;
       }
       if ((r = gemm(e, (const __half*)xn, D, wf1, D, g))) return r;
       if (e->prof) {
@@ -583,7 +595,7 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
       }
     }
     {
-      GemmArgs g = base_args(NT, D, 4 * D, EPI_RESID_LS);
+      GemmArgs g = base_args(MT, D, 4 * D, EPI_RESID_LS);
       g.out_f32 = (float*)x;
       g.bias = bf2;
       g.ls = ls2;
@@ -595,16 +607,20 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
       // backbone output: final LayerNorm applied (apply_layernorm=True), CLS dropped by the neck
       const float *ng, *nb;
       if ((r = W(e, "norm.g", &ng, D)) || (r = W(e, "norm.b", &nb, D))) return r;
-      void* tp;
-      snprintf(nm, sizeof nm, "tap%d", tap_idx);
-      if ((r = get_buf(e, nm, (size_t)round_up(NPATCH, 128) * D * 2, &tp))) return r;
-      launch_layernorm((const float*)x, NPATCH, D, ng, nb, (__half*)tp, 1, s);
-      e->launches++;
+      for (int b = 0; b < B; ++b) {
+        void* tp;
+        snprintf(nm, sizeof nm, "tap%d.%d", tap_idx, b);
+        if ((r = get_buf(e, nm, (size_t)round_up(NPATCH, 128) * D * 2, &tp))) return r;
+        launch_layernorm((const float*)x + (size_t)b * NP * D, NPATCH, D, ng, nb, (__half*)tp, 1, s);
+        e->launches++;
+      }
       ++tap_idx;
     }
   }
   if (tap_idx != 4) return dfail(e, VD3D_ERR_ARG, "taps must be increasing layer indices <= layers");
 
+  for (int b = 0; b < B; ++b) {  // neck + head, one image at a time (activation buffers are reused, stream-ordered)
+  void* depth_d = depth_dev[b];
   // ---- neck: reassemble + 3x3 conv to the fusion width ----
   int fh[4], fw[4];
   void* feat[4];
@@ -616,7 +632,8 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
     if ((r = W(e, nm, &pw_, (size_t)CP * D))) return r;
     snprintf(nm, sizeof nm, "r%d.proj.b", i);
     if ((r = W(e, nm, &pb, CP))) return r;
-    void *tp = e->buf[std::string("tap") + char('0' + i)].p, *rp, *rs = nullptr;
+    snprintf(nm, sizeof nm, "tap%d.%d", i, b);
+    void *tp = e->buf[nm].p, *rp, *rs = nullptr;
     snprintf(nm, sizeof nm, "r%d.p", i);
     if ((r = get_buf(e, nm, (size_t)round_up(NPATCH, 128) * CP * 2, &rp))) return r;
     {
@@ -791,13 +808,104 @@ int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_ou
     g2.b3p = b3;
     if ((r = conv(e, (const __half*)h1u, IH, IW, F2, w2, true, g2, 32))) return r;
   }
+  }  // images
   DCK(cudaGetLastError());
+  return VD3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// pixel_values: f32 [3, image_h, image_w] (already resized + normalised); depth_out f32 [image_h, image_w]
+int vd3d_depth_forward(vd3d_depth* e, const float* pixel_values, float* depth_out, int mem) {
+  if (!e || !pixel_values || !depth_out) return VD3D_ERR_ARG;
+  const int IH = e->cfg.image_h, IW = e->cfg.image_w;
+  cudaStream_t s = e->stream;
+  int r;
+  void *px_d = (void*)pixel_values, *depth_d = depth_out;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = get_buf(e, "px", (size_t)3 * IH * IW * 4, &px_d))) return r;
+    if ((r = get_buf(e, "depth", (size_t)IH * IW * 4, &depth_d))) return r;
+    DCK(cudaMemcpyAsync(px_d, pixel_values, (size_t)3 * IH * IW * 4, cudaMemcpyHostToDevice, s));
+  }
+  const float* pxs[1] = {(const float*)px_d};
+  float* ds[1] = {(float*)depth_d};
+  if ((r = forward_core(e, 1, pxs, ds))) return r;
   if (mem == VD3D_MEM_HOST) {
     DCK(cudaMemcpyAsync(depth_out, depth_d, (size_t)IH * IW * 4, cudaMemcpyDeviceToHost, s));
     DCK(cudaStreamSynchronize(s));
-  } else if (depth_out != (float*)depth_d) {
-    DCK(cudaMemcpyAsync(depth_out, depth_d, (size_t)IH * IW * 4, cudaMemcpyDeviceToDevice, s));
   }
+  return VD3D_OK;
+}
+
+// B frames (BGR u8 [h,w,3], DEVICE) -> DPT processor each -> ONE batched forward -> bicubic back + min-max u8 each.
+// depth_u8_dev[b] / depth_f32_dev[b] (either array may be null) receive the results; enqueues on the engine stream.
+int vd3d_depth_infer_batch_device(vd3d_depth* e, int B, const uint8_t* const* frames_bgr_dev, int h, int w,
+                                  uint8_t* const* depth_u8_dev, float* const* depth_f32_dev, int invert) {
+  if (!e || !frames_bgr_dev || B < 1 || B > kMaxBatch || h < 16 || w < 16) return VD3D_ERR_ARG;
+  const int IH = e->cfg.image_h, IW = e->cfg.image_w;
+  cudaStream_t s = e->stream;
+  void *tmp, *rgb, *mm, *up;
+  int r;
+  char nm[32];
+  const float* pxs[kMaxBatch];
+  float* dds[kMaxBatch];
+  if ((r = get_buf(e, "pp.tmp", (size_t)h * IW * 3, &tmp)) || (r = get_buf(e, "pp.rgb", (size_t)IH * IW * 3, &rgb)) ||
+      (r = get_buf(e, "post.up", (size_t)h * w * 4, &up)) || (r = get_buf(e, "post.mm", 64, &mm)))
+    return r;
+  for (int b = 0; b < B; ++b) {
+    void *px, *dd;
+    snprintf(nm, sizeof nm, b ? "px.%d" : "px", b);
+    if ((r = get_buf(e, nm, (size_t)3 * IH * IW * 4, &px))) return r;
+    snprintf(nm, sizeof nm, b ? "depth.%d" : "depth", b);
+    if ((r = get_buf(e, nm, (size_t)IH * IW * 4, &dd))) return r;
+    launch_preprocess(frames_bgr_dev[b], h, w, (uint8_t*)tmp, (uint8_t*)rgb, (float*)px, IH, IW, s);
+    e->launches += 3;
+    pxs[b] = (const float*)px;
+    dds[b] = (float*)dd;
+  }
+  if ((r = forward_core(e, B, pxs, dds))) return r;
+  for (int b = 0; b < B; ++b) {
+    float* upt = (depth_f32_dev && depth_f32_dev[b]) ? depth_f32_dev[b] : (float*)up;
+    uint8_t* u8 = depth_u8_dev ? depth_u8_dev[b] : nullptr;
+    launch_depth_post(dds[b], IH, IW, upt, h, w, (unsigned*)mm, u8, invert, s);
+    e->launches += u8 ? 3 : 2;
+  }
+  DCK(cudaGetLastError());
+  return VD3D_OK;
+}
+
+// host-buffer form of the batch (pipe protocol: the reference hands the whole list to the HF pipeline)
+int vd3d_depth_infer_batch(vd3d_depth* e, int B, const uint8_t* const* frames_bgr, int h, int w, float* const* depth_f32,
+                           uint8_t* const* depth_u8, int invert) {
+  if (!e || !frames_bgr || B < 1 || B > kMaxBatch) return VD3D_ERR_ARG;
+  int r;
+  char nm[32];
+  const uint8_t* fd[kMaxBatch];
+  uint8_t* u8d[kMaxBatch];
+  float* f32d[kMaxBatch];
+  for (int b = 0; b < B; ++b) {
+    void *a, *c, *d;
+    snprintf(nm, sizeof nm, "io.frame.%d", b);
+    if ((r = get_buf(e, nm, (size_t)h * w * 3, &a))) return r;
+    snprintf(nm, sizeof nm, "io.u8.%d", b);
+    if ((r = get_buf(e, nm, (size_t)h * w, &c))) return r;
+    snprintf(nm, sizeof nm, "io.f32.%d", b);
+    if ((r = get_buf(e, nm, (size_t)h * w * 4, &d))) return r;
+    DCK(cudaMemcpyAsync(a, frames_bgr[b], (size_t)h * w * 3, cudaMemcpyHostToDevice, e->stream));
+    fd[b] = (const uint8_t*)a;
+    u8d[b] = (uint8_t*)c;
+    f32d[b] = (float*)d;
+  }
+  if ((r = vd3d_depth_infer_batch_device(e, B, fd, h, w, u8d, f32d, invert))) return r;
+  for (int b = 0; b < B; ++b) {
+    if (depth_f32 && depth_f32[b])
+      DCK(cudaMemcpyAsync(depth_f32[b], f32d[b], (size_t)h * w * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (depth_u8 && depth_u8[b])
+      DCK(cudaMemcpyAsync(depth_u8[b], u8d[b], (size_t)h * w, cudaMemcpyDeviceToHost, e->stream));
+  }
+  DCK(cudaStreamSynchronize(e->stream));
   return VD3D_OK;
 }
 

@@ -418,7 +418,7 @@ static cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, con
 }
 
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, int ntok, int dmodel,
-                             __half* out, int heads, cudaStream_t s) {
+                             __half* out, int heads, int images, int npad, cudaStream_t s) {
   static bool attr_set = false;
   static int two_pass = 0;
   if (!attr_set) {
@@ -433,7 +433,9 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
   a.ntok = ntok;
   a.dmodel = dmodel;
   a.out = out;
-  dim3 grid((ntok + 127) / 128, heads);
+  a.heads = heads;
+  a.npad = npad;
+  dim3 grid((ntok + 127) / 128, heads * images);
   if (two_pass)
     k_umma_attention<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a);
   else

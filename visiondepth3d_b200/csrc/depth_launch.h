@@ -22,9 +22,9 @@ void launch_depth_post(const float* depth, int IH, int IW, float* up, int OH, in
                        int invert, cudaStream_t s);
 void launch_add_relu_f16(const __half* a, const __half* b, __half* sum, __half* sum_relu, size_t n, cudaStream_t s);
 void launch_relu_f16(const __half* in, __half* out, size_t n, cudaStream_t s);
-// fused attention: q,k [h][npad][64] (q pre-scaled), vT [h][64][npad] -> out [ntok, dmodel]
+// fused attention: q,k [image][h][npad][64] (q pre-scaled), vT [image][h][64][npad] -> out [images * npad, dmodel]
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, int ntok, int dmodel,
-                             __half* out, int heads, cudaStream_t s);
+                             __half* out, int heads, int images, int npad, cudaStream_t s);
 // bn in {32, 64, 128}; grid = (ceil(N/bn), m_tiles, batch)
 cudaError_t launch_gemm(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, int m_tiles,
                         int batch, cudaStream_t s);

@@ -47,8 +47,9 @@ struct StatsSmem {
   uint32_t sh64[2][64];
   uint32_t h64[64];
   uint32_t wsum[32];
+  float lut[256];     // i / 255.0f (the IEEE division costs ~10 issue slots; ingest needs 16 per pixel)
   double red[3][32];
-  SelState sel[2];
+  SelState sel[3];
   DevState st;
   FrameScalars fs;
 };
@@ -74,12 +75,38 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch) {
   __syncthreads();
 }
 
-// warp-aggregated histogram increment (all 32 lanes call it)
+// histogram increment, all 32 lanes call it.  Depth planes are smooth, so the lanes of a warp mostly hit one bin: the
+// lanes that share the first participating lane's bin are counted with one ballot and added once; the rest fall back
+// to per-lane atomics (few, and on distinct addresses for noisy content).  Replaces __match_any_sync, whose cost
+// (~32 dependent steps) dominated the streaming phases.
 __device__ __forceinline__ void hist_add(uint32_t* hist, bool on, uint32_t bin) {
-  if (!__any_sync(0xffffffffu, on)) return;
-  unsigned key = on ? bin : 0xFFFFFFFFu;
-  unsigned m = __match_any_sync(0xffffffffu, key);
-  if (on && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(m));
+  const unsigned ballot = __ballot_sync(0xffffffffu, on);
+  if (!ballot) return;
+  const int leader = __ffs(ballot) - 1;
+  const uint32_t b0 = __shfl_sync(0xffffffffu, bin, leader);
+  const bool mine = on && bin == b0;
+  const unsigned grp = __ballot_sync(0xffffffffu, mine);
+  if ((int)(threadIdx.x & 31) == leader) atomicAdd(&hist[b0], (uint32_t)__popc(grp));
+  if (on && !mine) atomicAdd(&hist[bin], 1u);
+}
+
+// idx / d for idx < 2^24 (every plane up to 16.7 Mpx) by a 40-bit reciprocal; plain division beyond
+struct FastDiv {
+  uint32_t d;
+  uint64_t m;
+  bool ok;
+};
+__device__ __forceinline__ FastDiv fast_div(uint32_t d, uint32_t max_idx) {
+  FastDiv f;
+  f.d = d;
+  f.m = ((1ull << 40) / d) + 1ull;
+  f.ok = max_idx < (1u << 24) && d < (1u << 15);
+  return f;
+}
+__device__ __forceinline__ void divmod(const FastDiv& f, int idx, int& q, int& r) {
+  uint32_t qq = f.ok ? (uint32_t)(((uint64_t)(uint32_t)idx * f.m) >> 40) : (uint32_t)idx / f.d;
+  q = (int)qq;
+  r = idx - (int)(qq * f.d);
 }
 
 __device__ __forceinline__ uint32_t key_of(float v01) { return __float_as_uint(v01) & 0x7FFFFFFFu; }
@@ -271,6 +298,7 @@ __device__ void select_pass(const float* plane, int W, int H, const SelState* qa
                             const JobMem* jb, const int* crop) {
   if (qa) {
     const int n = W * H;
+    const FastDiv fdw = fast_div((uint32_t)W, (uint32_t)n);
     for (int base = blockIdx.x * (NT * UNR); base < n; base += gridDim.x * (NT * UNR)) {
       float v[UNR];
 #pragma unroll
@@ -288,7 +316,8 @@ __device__ void select_pass(const float* plane, int W, int H, const SelState* qa
         else
           pass3_add(*qa, *ja, inb, key);
         if (qb) {
-          int y = idx / W, x = idx - y * W;
+          int y, x;
+          divmod(fdw, idx, y, x);
           bool on = inb && in_region(crop, y, x) && subj_keep(v[u]);
           if (PASS == 2)
             pass2_add(*qb, *jb, on, key);
@@ -300,12 +329,14 @@ __device__ void select_pass(const float* plane, int W, int H, const SelState* qa
   } else if (qb) {
     const int rw = crop[1] - crop[0], rh = crop[3] - crop[2];
     const int n = rw * rh;
+    const FastDiv fdr = fast_div((uint32_t)rw, (uint32_t)n);
     for (int base = blockIdx.x * (NT * UNR); base < n; base += gridDim.x * (NT * UNR)) {
       float v[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         int idx = base + u * NT + threadIdx.x;
-        int y = idx / rw, x = idx - y * rw;
+        int y, x;
+        divmod(fdr, idx, y, x);
         v[u] = idx < n ? clamp01(__ldcg(plane + (size_t)(crop[2] + y) * W + crop[0] + x)) : 0.f;
       }
 #pragma unroll
@@ -338,6 +369,14 @@ __device__ __forceinline__ float subject_of(StatsSmem& S, const SelState& q, con
   return subject_core(q.count, S.h64, __uint_as_float(q.bits[0]));
 }
 
+// depth_to_tensor on one source pixel (cv2 BGR2GRAY fixed point, then / 255 through the table)
+__device__ __forceinline__ float depth_lut01(const float* lut, const uint8_t* __restrict__ p, int ch, int pitch_px, int y,
+                                             int x) {
+  const uint8_t* q = p + ((size_t)y * pitch_px + x) * ch;
+  int g = (ch == 1) ? (int)q[0] : ((q[0] * 3735 + q[1] * 19235 + q[2] * 9798 + (1 << 14)) >> 15);
+  return lut[g];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // k_stats
 // ---------------------------------------------------------------------------------------------------------------
@@ -351,11 +390,13 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
 
   // ---- private copy of the temporal state; FrameScalars start from zero like begin_frame() does
   if (tid == 0) S.st = *a.st;
+  if (tid < 256) S.lut[tid] = (float)tid / 255.0f;
   for (int i = tid; i < (int)(sizeof(FrameScalars) / 4); i += NT) reinterpret_cast<uint32_t*>(&S.fs)[i] = 0u;
   __syncthreads();
   if (tid == 0) {
     S.sel[0].nt = 4;
     S.sel[1].nt = 1;
+    S.sel[2].nt = 1;
     if (!a.loop) {
       S.fs.fg = a.sa.p.fg_shift;
       S.fs.mg = a.sa.p.mg_shift;
@@ -364,16 +405,17 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
   }
   __syncthreads();
 
+  const int crop_n[4] = {a.ia.tw / 5, a.ia.tw * 4 / 5, a.ia.th / 5, a.ia.th * 4 / 5};  // loop mode only
   if (a.loop) {
     const int tw = a.ia.tw, th = a.ia.th;
     const int ntp = tw * th;
-    const int crop_n[4] = {tw / 5, tw * 4 / 5, th / 5, th * 4 / 5};
     // ================= ingest + TemporalDepthFilter + pass 1 of q(.02/.98) =================
     zero_pass1(S);
     {
       const IngestArgs& ia = a.ia;
       const bool ident = (ia.tw == ia.cw && ia.th == ia.ch);
       const int tdf_init = S.st.tdf_init;
+      const FastDiv fdt = fast_div((uint32_t)tw, (uint32_t)ntp);
       for (int base = blockIdx.x * (NT * UNR); base < ntp; base += gridDim.x * (NT * UNR)) {
 #pragma unroll 1
         for (int u = 0; u < UNR; ++u) {
@@ -381,18 +423,19 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
           bool inb = idx < ntp;
           float nv = 0.f;
           if (inb) {
-            int y = idx / tw, x = idx - y * tw;
+            int y, x;
+            divmod(fdt, idx, y, x);
             float cur;
             RsAxis ax, ay;
             if (ident && !a.rgbx_s) {
-              cur = depth_src01(ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + y, ia.cx0 + x);
+              cur = depth_lut01(S.lut, ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + y, ia.cx0 + x);
             } else {
               ax = rs_axis(x, ia.cw, ia.tw);
               ay = rs_axis(y, ia.ch, ia.th);
-              float v00 = depth_src01(ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + ay.i0, ia.cx0 + ax.i0);
-              float v01 = depth_src01(ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + ay.i0, ia.cx0 + ax.i1);
-              float v10 = depth_src01(ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + ay.i1, ia.cx0 + ax.i0);
-              float v11 = depth_src01(ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + ay.i1, ia.cx0 + ax.i1);
+              float v00 = depth_lut01(S.lut, ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + ay.i0, ia.cx0 + ax.i0);
+              float v01 = depth_lut01(S.lut, ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + ay.i0, ia.cx0 + ax.i1);
+              float v10 = depth_lut01(S.lut, ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + ay.i1, ia.cx0 + ax.i0);
+              float v11 = depth_lut01(S.lut, ia.depth, ia.depth_ch, ia.src_w, ia.cy0 + ay.i1, ia.cx0 + ax.i1);
               cur = rs_combine(v00, v01, v10, v11, ax, ay);
             }
             float prev = tdf_init ? __ldcg(ia.tdf + idx) : cur;
@@ -403,10 +446,10 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
 #pragma unroll
               for (int ch = 0; ch < 3; ++ch) {  // ch: 0=R 1=G 2=B ; source is BGR
                 const uint8_t* f = ia.frame + (2 - ch);
-                float v00 = (float)f[((size_t)(ia.cy0 + ay.i0) * ia.src_w + ia.cx0 + ax.i0) * 3] / 255.0f;
-                float v01 = (float)f[((size_t)(ia.cy0 + ay.i0) * ia.src_w + ia.cx0 + ax.i1) * 3] / 255.0f;
-                float v10 = (float)f[((size_t)(ia.cy0 + ay.i1) * ia.src_w + ia.cx0 + ax.i0) * 3] / 255.0f;
-                float v11 = (float)f[((size_t)(ia.cy0 + ay.i1) * ia.src_w + ia.cx0 + ax.i1) * 3] / 255.0f;
+                float v00 = S.lut[f[((size_t)(ia.cy0 + ay.i0) * ia.src_w + ia.cx0 + ax.i0) * 3]];
+                float v01 = S.lut[f[((size_t)(ia.cy0 + ay.i0) * ia.src_w + ia.cx0 + ax.i1) * 3]];
+                float v10 = S.lut[f[((size_t)(ia.cy0 + ay.i1) * ia.src_w + ia.cx0 + ax.i0) * 3]];
+                float v11 = S.lut[f[((size_t)(ia.cy0 + ay.i1) * ia.src_w + ia.cx0 + ax.i1) * 3]];
                 c[ch] = rs_combine(v00, v01, v10, v11, ax, ay);
               }
               a.rgbx_s[idx] = make_float4(c[0], c[1], c[2], 0.f);
@@ -427,8 +470,10 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
     select_pass<2>(a.ia.tdf, tw, th, &S.sel[0], &a.jm[0], nullptr, nullptr, nullptr);
     if (a.rgbx) {
       const int n = W * H;
+      const FastDiv fdw = fast_div((uint32_t)W, (uint32_t)n);
       for (int idx = blockIdx.x * NT + tid; idx < n; idx += gridDim.x * NT) {
-        int y = idx / W, x = idx - y * W;
+        int y, x;
+        divmod(fdw, idx, y, x);
         RsAxis ax = rs_axis(x, tw, W), ay = rs_axis(y, th, H);
         const float4* r0 = a.rgbx_s + (size_t)ay.i0 * tw;
         const float4* r1 = a.rgbx_s + (size_t)ay.i1 * tw;
@@ -458,6 +503,7 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
       const float n_lo = S.fs.n_lo, n_den = S.fs.n_den;
       const int have_prev = S.st.have_prev_depth;
       double s = 0, s2 = 0, mad = 0;
+      const FastDiv fdt = fast_div((uint32_t)tw, (uint32_t)ntp);
       for (int base = blockIdx.x * (NT * UNR); base < ntp; base += gridDim.x * (NT * UNR)) {
         float tv[UNR], pv[UNR];
 #pragma unroll
@@ -470,7 +516,8 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
         for (int u = 0; u < UNR; ++u) {
           int idx = base + u * NT + tid;
           bool inb = idx < ntp;
-          int y = idx / tw, x = idx - y * tw;
+          int y, x;
+          divmod(fdt, idx, y, x);
           float d = clamp01(tv[u]);
           float v = pct_flat ? d : clamp01((d - n_lo) / n_den);
           if (inb) {
@@ -507,36 +554,24 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
     flush_pass1(S, 0, a.jm[1], true);
     grid_barrier(a.bar, epoch);
 
-    // ================= subject estimate of the normalised plane: passes 2, 3 =================
-    after_pass1(S, S.sel[1], a.jm[1], true);
-    select_pass<2>(a.dn, tw, th, nullptr, nullptr, &S.sel[1], &a.jm[1], crop_n);
-    grid_barrier(a.bar, epoch);
-    after_pass2(S, S.sel[1], a.jm[1]);
-    select_pass<3>(a.dn, tw, th, nullptr, nullptr, &S.sel[1], &a.jm[1], crop_n);
-    grid_barrier(a.bar, epoch);
-    after_pass3(S, S.sel[1], a.jm[1]);
-    {
-      float sd = subject_of(S, S.sel[1], a.jm[1]);
-      if (tid == 0) {
-        S.fs.sum = __ldcg(&a.fs->sum);
-        S.fs.sumsq = __ldcg(&a.fs->sumsq);
-        S.fs.mad_sum = __ldcg(&a.fs->mad_sum);
-        fin_norm_core(sd, a.la, &S.st, &S.fs);
-      }
-      __syncthreads();
-    }
+    // ===== subject estimate of the normalised plane, pass 2 -- shares its phase with d0 below: d0 only needs dn,
+    // ===== not the scalars of fin_norm, so the two selects interleave and two grid barriers disappear
+    after_pass1(S, S.sel[2], a.jm[1], true);
+    select_pass<2>(a.dn, a.ia.tw, a.ia.th, nullptr, nullptr, &S.sel[2], &a.jm[1], crop_n);
   }
 
   // ================= d0 = clamp01(enhance_curvature(resize(depth))) + pass 1 of q(.05/.95) and of the subject =====
   zero_pass1(S);
   {
     const int n = W * H;
+    const FastDiv fdw = fast_div((uint32_t)W, (uint32_t)n);
     for (int base = blockIdx.x * (NT * UNR); base < n; base += gridDim.x * (NT * UNR)) {
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         int idx = base + u * NT + tid;
         bool inb = idx < n;
-        int y = idx / W, x = idx - y * W;
+        int y, x;
+        divmod(fdw, idx, y, x);
         float v = 0.f;
         if (inb) {
           float d = ldcg_bilinear(a.core_depth, a.sh, a.sw, H, W, y, x);
@@ -560,12 +595,27 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
   flush_pass1(S, 1, a.jm[3], true);
   grid_barrier(a.bar, epoch);
 
+  if (a.loop) {  // subject estimate of the normalised plane, pass 3
+    after_pass2(S, S.sel[2], a.jm[1]);
+    select_pass<3>(a.dn, a.ia.tw, a.ia.th, nullptr, nullptr, &S.sel[2], &a.jm[1], crop_n);
+  }
   if (tid < 4) S.sel[0].rank[tid] = a.q_rank[tid];
   __syncthreads();
   after_pass1(S, S.sel[0], a.jm[2], false);
   after_pass1(S, S.sel[1], a.jm[3], true);
   select_pass<2>(a.d, W, H, &S.sel[0], &a.jm[2], &S.sel[1], &a.jm[3], crop_d);
   grid_barrier(a.bar, epoch);
+  if (a.loop) {  // ShiftSmoother / dynamic scale / FocalDepthTracker / bars: the scalars of the loop level
+    after_pass3(S, S.sel[2], a.jm[1]);
+    float sd = subject_of(S, S.sel[2], a.jm[1]);
+    if (tid == 0) {
+      S.fs.sum = __ldcg(&a.fs->sum);
+      S.fs.sumsq = __ldcg(&a.fs->sumsq);
+      S.fs.mad_sum = __ldcg(&a.fs->mad_sum);
+      fin_norm_core(sd, a.la, &S.st, &S.fs);
+    }
+    __syncthreads();
+  }
   after_pass2(S, S.sel[0], a.jm[2]);
   after_pass2(S, S.sel[1], a.jm[3]);
   select_pass<3>(a.d, W, H, &S.sel[0], &a.jm[2], &S.sel[1], &a.jm[3], crop_d);
@@ -588,6 +638,7 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
     const int st_flat = S.fs.st_flat;
     const float st_lo = S.fs.st_lo, st_den = S.fs.st_den, st_subj = S.fs.st_subj;
     const float mid = (float)a.sa.p.depth_pop_mid, gamma = (float)a.sa.p.depth_pop_gamma;
+    const FastDiv fdw = fast_div((uint32_t)W, (uint32_t)n);
     for (int base = blockIdx.x * (NT * UNR); base < n; base += gridDim.x * (NT * UNR)) {
       float dv[UNR];
 #pragma unroll
@@ -599,7 +650,8 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
       for (int u = 0; u < UNR; ++u) {
         int idx = base + u * NT + tid;
         bool inb = idx < n;
-        int y = idx / W, x = idx - y * W;
+        int y, x;
+        divmod(fdw, idx, y, x);
         float v = dv[u];
         float ds = st_flat ? v : clamp01((v - st_lo) / st_den);
         float centered = (ds - st_subj) + mid;
@@ -607,6 +659,7 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
         float ax = fabsf(xr);
         // |x|^gamma = 2^(gamma*log2|x|) on the SFU: <= ~3e-7 relative (exact path: fp64 pow, one rounding)
         float pw = (ax > 0.f) ? exp2f(gamma * __log2f(ax)) : (gamma == 0.f ? 1.f : 0.f);
+        if (a.dbg & 1) pw = (float)pow((double)ax, (double)gamma);
         float sg = (xr > 0.f) ? 1.f : ((xr < 0.f) ? -1.f : 0.f);
         float o = clamp01((sg * pw) + mid);
         if (inb) a.d[idx] = o;
@@ -791,6 +844,17 @@ __global__ void __launch_bounds__(RT) k_render(RenderArgs a) {
         }
         bl = s.x / kk;
         br = s.y / kk;
+        if (a.dbg & 4) {  // triage: the reference's row-major K x K order straight from the edge tile
+          float al = 0.f, ar = 0.f;
+          for (int dy = 0; dy < K; ++dy)
+            for (int dx = 0; dx < K; ++dx) {
+              float2 v = bufE[(ty + dy) * EX + tx + dx];
+              al = al + v.x;
+              ar = ar + v.y;
+            }
+          bl = al / kk;
+          br = ar / kk;
+        }
       }
       float sv = __ldg(shift + (size_t)gy * W + gx);
       float xv = __ldg(xs + gx), yv = __ldg(ys + gy);

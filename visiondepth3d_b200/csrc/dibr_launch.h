@@ -162,6 +162,7 @@ struct StatsArgs {
   DevState* st;
   FrameScalars* fs;  // zeroed by the host before the launch (the centre / motion sums accumulate into it)
   unsigned* bar;     // grid barrier counter, zeroed by the host before the launch
+  int dbg;           // triage bits (env VD3D_FAST_DEBUG): 1 = correctly rounded pow in the shaping phase
 };
 
 struct RenderArgs {
@@ -175,6 +176,7 @@ struct RenderArgs {
   float kc, ke;
   uint8_t* out;
   int out_w, per_eye_w;    // packed row length in pixels; width of one eye in the packed frame
+  int dbg;                 // triage bits (env VD3D_FAST_DEBUG): 4 = row-major K*K box sum instead of the separable one
 };
 
 bool render_supports(int feather, int k);

@@ -23,7 +23,9 @@ namespace vd3d {
 struct AttnArgs {
   int ntok;     // valid tokens (queries == keys)
   int dmodel;   // row stride of the output (elements)
-  __half* out;  // [ntok, dmodel], head h writes columns [64h, 64h+64)
+  __half* out;  // [images * npad, dmodel], head h of image i writes rows i*npad + token, columns [64h, 64h+64)
+  int heads;    // blockIdx.y = image * heads + head (the tensor maps' third coordinate)
+  int npad;     // rows per image in `out`
 };
 
 constexpr bool kAttnPolyExp = false;  // true: a third of the softmax exponentials on the FMA pipe (umma::ex2_poly) -- measured 2 % SLOWER (profiles/r01_ncu_full_final.md)
@@ -62,7 +64,7 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   float* xch = (float*)(bars + 64);  // [2][128] row max / row sum exchange between the two half-row threads
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qblk = blockIdx.x, h = blockIdx.y;
+  const int qblk = blockIdx.x, zq = blockIdx.y, h = zq % g.heads, img = zq / g.heads;
   const int T = (g.ntok + 127) / 128;  // key tiles
 
   if (warp == 0 && lane == 0) {
@@ -99,21 +101,21 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       umma::mbar_expect_tx(umma::smem_u32(q_full), 16384);
-      umma::tma_load_3d(umma::smem_u32(sQ), &tmQ, umma::smem_u32(q_full), 0, qblk * 128, h);
+      umma::tma_load_3d(umma::smem_u32(sQ), &tmQ, umma::smem_u32(q_full), 0, qblk * 128, zq);
       int kiter = 0;
       for (int pass = 0; pass < 2; ++pass) {
         for (int t = 0; t < T; ++t, ++kiter) {
           const int ks = kiter % kAttnKS;
           umma::mbar_wait(umma::smem_u32(&k_empty[ks]), ((kiter / kAttnKS) & 1) ^ 1);
           umma::mbar_expect_tx(umma::smem_u32(&k_full[ks]), 16384);
-          umma::tma_load_3d(umma::smem_u32(sK + ks * 16384), &tmK, umma::smem_u32(&k_full[ks]), 0, t * 128, h);
+          umma::tma_load_3d(umma::smem_u32(sK + ks * 16384), &tmK, umma::smem_u32(&k_full[ks]), 0, t * 128, zq);
           if (pass == 1) {
             const int vs = t % kAttnVS;
             umma::mbar_wait(umma::smem_u32(&v_empty[vs]), ((t / kAttnVS) & 1) ^ 1);
             umma::mbar_expect_tx(umma::smem_u32(&v_full[vs]), 16384);
             const uint32_t dst = umma::smem_u32(sV + vs * 16384);
-            umma::tma_load_3d(dst, &tmV, umma::smem_u32(&v_full[vs]), t * 128, 0, h);
-            umma::tma_load_3d(dst + 8192, &tmV, umma::smem_u32(&v_full[vs]), t * 128 + 64, 0, h);
+            umma::tma_load_3d(dst, &tmV, umma::smem_u32(&v_full[vs]), t * 128, 0, zq);
+            umma::tma_load_3d(dst + 8192, &tmV, umma::smem_u32(&v_full[vs]), t * 128 + 64, 0, zq);
           }
         }
       }
@@ -267,7 +269,7 @@ k_umma_attention(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t v[32];
       umma::tmem_ld_32x32(tmem_O + lane_off + (uint32_t)(half * 32), v);
       if (m < g.ntok) {
-        uint4* dst = (uint4*)(g.out + (size_t)m * g.dmodel + h * 64 + half * 32);
+        uint4* dst = (uint4*)(g.out + ((size_t)img * g.npad + m) * g.dmodel + h * 64 + half * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
@@ -323,7 +325,7 @@ k_umma_attention_1p(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   float* xch = (float*)(bars + 64);  // [2 buffers][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qblk = blockIdx.x, h = blockIdx.y;
+  const int qblk = blockIdx.x, zq = blockIdx.y, h = zq % g.heads, img = zq / g.heads;
   const int T = (g.ntok + 127) / 128;
 
   if (warp == 0 && lane == 0) {
@@ -356,17 +358,17 @@ k_umma_attention_1p(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       umma::mbar_expect_tx(umma::smem_u32(q_full), 16384);
-      umma::tma_load_3d(umma::smem_u32(sQ), &tmQ, umma::smem_u32(q_full), 0, qblk * 128, h);
+      umma::tma_load_3d(umma::smem_u32(sQ), &tmQ, umma::smem_u32(q_full), 0, qblk * 128, zq);
       for (int t = 0; t < T; ++t) {
         const int ks = t % kAttnKS, vs = t % kAttnVS;
         umma::mbar_wait(umma::smem_u32(&k_empty[ks]), ((t / kAttnKS) & 1) ^ 1);
         umma::mbar_expect_tx(umma::smem_u32(&k_full[ks]), 16384);
-        umma::tma_load_3d(umma::smem_u32(sK + ks * 16384), &tmK, umma::smem_u32(&k_full[ks]), 0, t * 128, h);
+        umma::tma_load_3d(umma::smem_u32(sK + ks * 16384), &tmK, umma::smem_u32(&k_full[ks]), 0, t * 128, zq);
         umma::mbar_wait(umma::smem_u32(&v_empty[vs]), ((t / kAttnVS) & 1) ^ 1);
         umma::mbar_expect_tx(umma::smem_u32(&v_full[vs]), 16384);
         const uint32_t dst = umma::smem_u32(sV + vs * 16384);
-        umma::tma_load_3d(dst, &tmV, umma::smem_u32(&v_full[vs]), t * 128, 0, h);
-        umma::tma_load_3d(dst + 8192, &tmV, umma::smem_u32(&v_full[vs]), t * 128 + 64, 0, h);
+        umma::tma_load_3d(dst, &tmV, umma::smem_u32(&v_full[vs]), t * 128, 0, zq);
+        umma::tma_load_3d(dst + 8192, &tmV, umma::smem_u32(&v_full[vs]), t * 128 + 64, 0, zq);
       }
     }
   } else if (warp == 1) {
@@ -521,7 +523,7 @@ k_umma_attention_1p(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t v[32];
       umma::tmem_ld_32x32(tmem_O + lane_off + (uint32_t)(half * 32), v);
       if (m < g.ntok) {
-        uint4* dst = (uint4*)(g.out + (size_t)m * g.dmodel + h * 64 + half * 32);
+        uint4* dst = (uint4*)(g.out + ((size_t)img * g.npad + m) * g.dmodel + h * 64 + half * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);

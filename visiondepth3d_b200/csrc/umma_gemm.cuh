@@ -443,8 +443,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& g, const uin
       const int which = n0 / g.dmodel;
       const int rem = n0 - which * g.dmodel;
       const int h = rem >> 6, d0 = rem & 63;
+      // batched forward: row m = image * npad + token; q, k are [image][head][npad][64], vT [image][head][64][npad]
+      const int img = m / g.npad, tok = m - img * g.npad;
+      const size_t zh = (size_t)img * g.heads + h;
       if (which < 2) {
-        __half* dst = (which == 0 ? g.q : g.k) + ((size_t)h * g.npad + m) * 64 + d0;
+        __half* dst = (which == 0 ? g.q : g.k) + (zh * g.npad + tok) * 64 + d0;
         const float sc = which == 0 ? g.qscale : 1.0f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[j] *= sc;
@@ -454,7 +457,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& g, const uin
         umma::pack16(a, 16, false, u);
         umma::stg_v8(dst + 16, u);
       } else {
-        __half* dst = g.vt + ((size_t)h * 64 + d0) * g.npad + m;  // transposed: lanes -> consecutive m
+        __half* dst = g.vt + (zh * 64 + d0) * g.npad + tok;  // transposed: lanes -> consecutive tokens
 #pragma unroll
         for (int j = 0; j < 32; ++j) dst[(size_t)j * g.npad] = __float2half_rn(a[j]);
       }

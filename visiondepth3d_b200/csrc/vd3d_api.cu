@@ -23,7 +23,9 @@ struct Buf {
   size_t cap = 0;
 };
 
-constexpr int kSlots = 3;  // frames in flight (staging buffers, depth streams)
+constexpr int kSlots = 8;    // staging slots: two depth batches of up to kMaxDepthBatch frames in flight
+constexpr int kClones = 2;   // depth engine instances (own activation buffers / stream), alternating per batch
+constexpr int kMaxDepthBatch = 4;
 constexpr int kJobs = 5;  // pct, subj(norm), quantile(d0), subj(d0), subj(shaped)
 constexpr size_t kJobWords = 4096 + 4 * 4096 + 4 * 64 + 64 + 64;  // + count (padded)
 constexpr size_t kBarWords = 64;
@@ -43,6 +45,8 @@ struct vd3d_ctx {
   // bumped whenever a device resource that captured graphs bake in moves or changes content (ensure() reallocations,
   // linspace axes, INTER_AREA tables, DOF kernel bank); run_frame_slot drops stale graphs
   uint64_t res_epoch = 0, fg_epoch = 0;
+  int fast_dbg = 0;           // env VD3D_FAST_DEBUG: triage bits of the fast path (1 exact pow, 2 exact k_shift, 4 row-major box sum)
+  int prof_depth_frames = 0;  // frames covered by the stage-2 (depth) samples since the last collect
   uint64_t dclone_wver = 0;
   unsigned* bar = nullptr;  // grid barrier counter of k_stats (inside jobwords: zeroed by begin_frame)
 
@@ -84,15 +88,16 @@ struct vd3d_ctx {
   void* fg_depth = nullptr;
   // depth stage of the depth+stereo clip: two engine clones (shared weights) on two streams so the
   // depth forwards of consecutive frames overlap each other and the DIBR kernels of the previous frame
-  vd3d_depth* dclone[kSlots] = {};
+  vd3d_depth* dclone[kClones] = {};
   vd3d_depth* dclone_parent = nullptr;
-  cudaStream_t s_depth[kSlots] = {};
-  cudaEvent_t ev_depth[kSlots] = {};
-  struct DepthGraph {
+  cudaStream_t s_depth[kClones] = {};
+  cudaEvent_t ev_depth[kClones] = {};
+  struct DepthGraph {  // one graph per (engine instance, frames in the batch)
     cudaGraphExec_t exec = nullptr;
     uint64_t n = 0;
-  } dg[kSlots];
+  } dg[kClones][kMaxDepthBatch + 1];
   int dg_warm = 0, dg_h = 0, dg_w = 0;
+  int depth_batch = 3;  // frames per depth forward in vd3d_render_clip_depth (env VD3D_DEPTH_BATCH, 1..4)
   // dof kernel cache
   double dof_sigma_cached = -1.0;
   int dof_nlevels = 0, dof_ksize[8] = {0}, dof_koff[8] = {0}, dof_halo = 0;
@@ -396,10 +401,14 @@ int run_core_fast(vd3d_ctx* ctx, const CoreIn& in, const FastLoop* lp, const Fas
   sa.st = ctx->st;
   sa.fs = ctx->fs;
   sa.bar = ctx->bar;
+  sa.dbg = ctx->fast_dbg;
   CK(launch_stats(sa, ctx->stats_blocks, s));
   ctx->launches += 1;
   if (ctx->stats_only) return VD3D_OK;
-  launch_shift_fast(d, shift, H, W, ctx->fs, in.p.enable_edge_masking ? 1 : 0, (float)in.p.feather_strength, s);
+  if (ctx->fast_dbg & 2)
+    launch_shift(d, shift, H, W, ctx->fs, in.p.enable_edge_masking ? 1 : 0, (float)in.p.feather_strength, s);
+  else
+    launch_shift_fast(d, shift, H, W, ctx->fs, in.p.enable_edge_masking ? 1 : 0, (float)in.p.feather_strength, s);
   ctx->launches += 1;
 
   ComposeArgs ca;
@@ -437,6 +446,7 @@ int run_core_fast(vd3d_ctx* ctx, const CoreIn& in, const FastLoop* lp, const Fas
     ra.out = post.out;
     ra.out_w = post.out_w;
     ra.per_eye_w = post.per_eye_w;
+    ra.dbg = ctx->fast_dbg;
     {
       ProfScope ps(ctx, 1);
       CK(launch_render(ra, s));
@@ -822,6 +832,10 @@ int vd3d_create(int device, vd3d_ctx** out) {
   {
     const char* v = getenv("VD3D_EXACT");
     ctx->exact = (v && atoi(v)) ? 1 : 0;
+    if ((v = getenv("VD3D_DEPTH_BATCH"))) ctx->depth_batch = atoi(v);
+    if ((v = getenv("VD3D_FAST_DEBUG"))) ctx->fast_dbg = atoi(v);
+    if (ctx->depth_batch < 1) ctx->depth_batch = 1;
+    if (ctx->depth_batch > kMaxDepthBatch) ctx->depth_batch = kMaxDepthBatch;
   }
   *out = ctx;
   return VD3D_OK;
@@ -844,7 +858,7 @@ void vd3d_destroy(vd3d_ctx* ctx) {
   }
   drop_graphs(ctx);
   drop_depth_graphs(ctx);
-  for (int i = 0; i < kSlots; ++i) {
+  for (int i = 0; i < kClones; ++i) {
     if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
     if (ctx->s_depth[i]) cudaStreamDestroy(ctx->s_depth[i]);
     if (ctx->ev_depth[i]) cudaEventDestroy(ctx->ev_depth[i]);
@@ -934,6 +948,10 @@ int vd3d_profile_collect(vd3d_ctx* ctx, int stage, double* total_ms, int* count)
   v.clear();
   *total_ms = t;
   *count = n;
+  if (stage == 2) {  // depth samples cover whole batches: report frames so that total / count is per frame
+    if (ctx->prof_depth_frames > 0) *count = ctx->prof_depth_frames;
+    ctx->prof_depth_frames = 0;
+  }
   return VD3D_OK;
 }
 // 1: the one-kernel-per-op path with correctly rounded transcendentals (bit-for-bit with oracle/dibr.py);
@@ -1202,8 +1220,7 @@ static int enqueue_core_fast(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_
     FitPlan fp;
     if ((r = plan_fit(ctx, rp->output_format, W, H, pl.per_eye_w, pl.per_eye_h, fp))) return r;
     const bool plain = !fp.xal && !fp.lin && fp.fit_x0 == 0 && fp.fit_y0 == 0 && fp.fit_w == pl.per_eye_w &&
-                       fp.fit_h == pl.per_eye_h && pl.out_width == 2 * pl.per_eye_w && pl.out_height == pl.per_eye_h &&
-                       fp.sy == 1 && pl.per_eye_h == H;
+                       fp.fit_h == pl.per_eye_h && fp.sy == 1 && pl.per_eye_h == H;
     if (plain && fp.sx == 1 && pl.per_eye_w == W) post.fuse = 1;
     if (plain && fp.sx == 2 && pl.per_eye_w * 2 == W) post.fuse = 2;
   }
@@ -1211,7 +1228,7 @@ static int enqueue_core_fast(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_
     post.sharpen = 1;
     sharpen_coeffs(rp->sharpness_factor, post.kc, post.ke);
     post.out = out_d;
-    post.out_w = pl.out_width;
+    post.out_w = 2 * pl.per_eye_w;
     post.per_eye_w = pl.per_eye_w;
     *fused = true;
   } else if (!ctx->stats_only) {
@@ -1410,8 +1427,8 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
     pa.out_w = pl.per_eye_w;
     pa.out_h = pl.per_eye_h;
   } else {
-    pa.out_w = pl.out_width;
-    pa.out_h = pl.out_height;
+    pa.out_w = 2 * pl.per_eye_w;  // hstack of the fitted eyes
+    pa.out_h = pl.per_eye_h;
   }
   launch_post(pa, s);
   ctx->launches += 1;
@@ -1423,12 +1440,16 @@ static int enqueue_frame(vd3d_ctx* ctx, const uint8_t* frame_d, const uint8_t* d
 extern "C" uint64_t vd3d_depth_launch_count(vd3d_depth* e);
 extern "C" void vd3d_depth_add_launches(vd3d_depth* e, uint64_t n);
 
+extern "C" int vd3d_depth_infer_batch_device(vd3d_depth* e, int B, const uint8_t* const* frames_bgr_dev, int h, int w,
+                                             uint8_t* const* depth_u8_dev, float* const* depth_f32_dev, int invert);
+
 static void drop_depth_graphs(vd3d_ctx* ctx) {
-  for (int i = 0; i < kSlots; ++i)
-    if (ctx->dg[i].exec) {
-      cudaGraphExecDestroy(ctx->dg[i].exec);
-      ctx->dg[i].exec = nullptr;
-    }
+  for (int i = 0; i < kClones; ++i)
+    for (int j = 0; j <= kMaxDepthBatch; ++j)
+      if (ctx->dg[i][j].exec) {
+        cudaGraphExecDestroy(ctx->dg[i][j].exec);
+        ctx->dg[i][j].exec = nullptr;
+      }
   ctx->dg_warm = 0;
 }
 
@@ -1437,9 +1458,9 @@ static int ensure_depth_clones(vd3d_ctx* ctx, vd3d_depth* parent) {
     return VD3D_OK;
   CK(cudaDeviceSynchronize());
   drop_depth_graphs(ctx);
-  drop_graphs(ctx);  // the serial (profiling) path captures the parent engine inside the frame graph
+  drop_graphs(ctx);
   ctx->dclone_wver = vd3d_depth_weights_version(parent);
-  for (int i = 0; i < kSlots; ++i) {
+  for (int i = 0; i < kClones; ++i) {
     if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
     ctx->dclone[i] = nullptr;
     if (!ctx->s_depth[i]) CK(cudaStreamCreateWithFlags(&ctx->s_depth[i], cudaStreamNonBlocking));
@@ -1451,11 +1472,16 @@ static int ensure_depth_clones(vd3d_ctx* ctx, vd3d_depth* parent) {
   return VD3D_OK;
 }
 
-// depth inference of staging slot b on its own stream (graph-replayed after two eager frames)
-static int run_depth_slot(vd3d_ctx* ctx, vd3d_depth* parent, int b, int src_h, int src_w) {
-  vd3d_depth* e = ctx->dclone[b];
-  const uint8_t* f_d = (const uint8_t*)ctx->in_frame[b].p;
-  uint8_t* d_d = (uint8_t*)ctx->in_depth[b].p;
+// depth inference of one batch (staging slots slot0 .. slot0+nb-1) on engine instance c and its stream; one batched
+// forward for the nb frames, graph-replayed once the configuration has been seen a few times
+static int run_depth_group(vd3d_ctx* ctx, vd3d_depth* parent, int c, int slot0, int nb, int src_h, int src_w) {
+  vd3d_depth* e = ctx->dclone[c];
+  const uint8_t* f_d[kMaxDepthBatch];
+  uint8_t* d_d[kMaxDepthBatch];
+  for (int j = 0; j < nb; ++j) {
+    f_d[j] = (const uint8_t*)ctx->in_frame[slot0 + j].p;
+    d_d[j] = (uint8_t*)ctx->in_depth[slot0 + j].p;
+  }
   if (ctx->dg_h != src_h || ctx->dg_w != src_w) {
     drop_depth_graphs(ctx);
     ctx->dg_h = src_h;
@@ -1463,29 +1489,28 @@ static int run_depth_slot(vd3d_ctx* ctx, vd3d_depth* parent, int b, int src_h, i
   }
   auto eager = [&]() -> int {
     uint64_t l0 = vd3d_depth_launch_count(e);
-    int r = vd3d_depth_infer_device(e, f_d, src_h, src_w, d_d, nullptr, 0);
+    int r = vd3d_depth_infer_batch_device(e, nb, f_d, src_h, src_w, d_d, nullptr, 0);
     if (r) ctx->err = std::string("depth engine: ") + vd3d_depth_last_error(e);
     vd3d_depth_add_launches(parent, vd3d_depth_launch_count(e) - l0);
     return r;
   };
-  if (!ctx->use_graphs || ctx->dg_warm < kSlots) {
+  if (!ctx->use_graphs || ctx->dg_warm < 2 * kClones) {  // workspaces of both instances are allocated eagerly first
     ctx->dg_warm++;
     return eager();
   }
-  vd3d_ctx::DepthGraph& g = ctx->dg[b];
+  vd3d_ctx::DepthGraph& g = ctx->dg[c][nb];
   if (!g.exec) {
-    uint64_t l0 = vd3d_depth_launch_count(e), p0 = vd3d_depth_launch_count(parent);
-    if (cudaStreamBeginCapture(ctx->s_depth[b], cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    uint64_t l0 = vd3d_depth_launch_count(e);
+    if (cudaStreamBeginCapture(ctx->s_depth[c], cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       fprintf(stderr, "vd3d: CUDA graph capture unavailable (%s); continuing with eager launches\n",
               cudaGetErrorString(cudaGetLastError()));
       ctx->use_graphs = 0;
       return eager();
     }
-    int r = vd3d_depth_infer_device(e, f_d, src_h, src_w, d_d, nullptr, 0);
+    int r = vd3d_depth_infer_batch_device(e, nb, f_d, src_h, src_w, d_d, nullptr, 0);
     cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(ctx->s_depth[b], &graph);
+    cudaError_t ce = cudaStreamEndCapture(ctx->s_depth[c], &graph);
     uint64_t n = vd3d_depth_launch_count(e) - l0;
-    (void)p0;
     if (r != VD3D_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
       fprintf(stderr, "vd3d: CUDA graph capture failed (r=%d, %s); continuing with eager launches\n", r,
               cudaGetErrorString(cudaGetLastError()));
@@ -1497,7 +1522,7 @@ static int run_depth_slot(vd3d_ctx* ctx, vd3d_depth* parent, int b, int src_h, i
     cudaGraphDestroy(graph);
     g.n = n;
   }
-  CK(cudaGraphLaunch(g.exec, ctx->s_depth[b]));
+  CK(cudaGraphLaunch(g.exec, ctx->s_depth[c]));
   vd3d_depth_add_launches(parent, g.n);
   return VD3D_OK;
 }
@@ -1545,7 +1570,7 @@ static int run_frame_slot(vd3d_ctx* ctx, vd3d_depth* depth, int b, int depth_cha
     ctx->fg_depth = depth;
     ctx->fg_rp = *rp;
   }
-  if (!ctx->use_graphs || ctx->prof || ctx->fg_warm < kSlots) {
+  if (!ctx->use_graphs || ctx->prof || ctx->fg_warm < 3) {
     ctx->fg_warm++;
     return eager();
   }
@@ -1586,10 +1611,15 @@ static int run_frame_slot(vd3d_ctx* ctx, vd3d_depth* depth, int b, int depth_cha
   return VD3D_OK;
 }
 
+// the packed frame format_3d_output produces (core/render_3d.py:837-860): SBS / VR = hstack of the two fitted eyes,
+// i.e. 2 * per_eye_w wide -- for an odd preserve-aspect Half-SBS width that is one less than `out_width`, the size the
+// reference opens its writer with (1099-1103)
+static int packed_w(const vd3d_render_params* rp, const vd3d_size_plan& pl) {
+  if (rp->output_format == VD3D_FMT_ANAGLYPH || rp->output_format == VD3D_FMT_INTERLACED) return pl.per_eye_w;
+  return 2 * pl.per_eye_w;
+}
 static size_t out_bytes(const vd3d_render_params* rp, const vd3d_size_plan& pl) {
-  if (rp->output_format == VD3D_FMT_ANAGLYPH || rp->output_format == VD3D_FMT_INTERLACED)
-    return (size_t)pl.per_eye_w * pl.per_eye_h * 3;
-  return (size_t)pl.out_width * pl.out_height * 3;
+  return (size_t)packed_w(rp, pl) * pl.per_eye_h * 3;
 }
 
 int vd3d_render_frame(vd3d_ctx* ctx, const uint8_t* frame_bgr, const uint8_t* depth, int depth_channels,
@@ -1679,42 +1709,80 @@ int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_
     if ((r = ensure(ctx, ctx->in_depth[b], db))) return r;
     if ((r = ensure(ctx, ctx->out_dev[b], ob))) return r;
   }
-  const bool serial = ctx->prof != 0;  // stage timing wants one stream; otherwise depth runs on its own streams
+  // Frames travel in groups of `depth_batch`: one batched depth forward per group on one of two engine instances
+  // (group g+1's forward overlaps the neck / head tail of group g and the DIBR kernels of group g's frames), then the
+  // DIBR loop body frame by frame on the main stream (sequential temporal state), D2H behind it.
+  const bool serial = ctx->prof != 0;  // stage timing wants everything on one stream
+  const int B = ctx->depth_batch;
   if (!serial && (r = ensure_depth_clones(ctx, depth))) return r;
-  for (int i = 0; i < n; ++i) {
-    int b = i % kSlots;
-    // ---- stage the frame into slot b (free once DIBR of frame i-2 has finished) ----
-    if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[b], 0));
-    CK(cudaMemcpyAsync(ctx->in_frame[b].p, frames[i], fb,
-                       mem == VD3D_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->s_h2d));
-    CK(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
-    if (serial) {
-      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
-      if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
-      if ((r = run_frame_slot(ctx, depth, b, 1, src_h, src_w, rp, pl))) return r;
-    } else {
-      // ---- depth of frame i on stream b: overlaps depth(i-1) and DIBR(i-1) ----
-      CK(cudaStreamWaitEvent(ctx->s_depth[b], ctx->ev_h2d[b], 0));
-      if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->s_depth[b], ctx->ev_done[b], 0));  // in_depth[b] consumed
-      if ((r = run_depth_slot(ctx, depth, b, src_h, src_w))) return r;
-      CK(cudaEventRecord(ctx->ev_depth[b], ctx->s_depth[b]));
-      // ---- DIBR loop body on the main stream (sequential temporal state) ----
-      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_depth[b], 0));
-      if (i >= kSlots) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));        // out_dev[b] drained
-      if ((r = run_frame_slot(ctx, nullptr, b, 1, src_h, src_w, rp, pl))) return r;
+  const cudaMemcpyKind kin = mem == VD3D_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind kout = mem == VD3D_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  int group = 0;
+  for (int i0 = 0; i0 < n; i0 += B, ++group) {
+    const int nb = (n - i0) < B ? (n - i0) : B;
+    const int c = group % kClones;
+    const int slot0 = c * kMaxDepthBatch;
+    const bool reuse = group >= kClones;  // these slots have been used before in this call
+    // ---- stage the frames of the group (a slot is free once the DIBR pass that read it has finished) ----
+    for (int j = 0; j < nb; ++j) {
+      const int sl = slot0 + j;
+      if (reuse) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[sl], 0));
+      CK(cudaMemcpyAsync(ctx->in_frame[sl].p, frames[i0 + j], fb, kin, ctx->s_h2d));
+      CK(cudaEventRecord(ctx->ev_h2d[sl], ctx->s_h2d));
     }
-    CK(cudaEventRecord(ctx->ev_done[b], ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[b], 0));
-    CK(cudaMemcpyAsync(outs[i], ctx->out_dev[b].p, ob,
-                       mem == VD3D_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CK(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+    if (serial) {
+      for (int j = 0; j < nb; ++j) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot0 + j], 0));
+      {
+        ProfScope ps(ctx, 2);  // one sample per batch: vd3d_profile_collect divides by the frames it covered
+        const uint8_t* f_d[kMaxDepthBatch];
+        uint8_t* d_d[kMaxDepthBatch];
+        for (int j = 0; j < nb; ++j) {
+          f_d[j] = (const uint8_t*)ctx->in_frame[slot0 + j].p;
+          d_d[j] = (uint8_t*)ctx->in_depth[slot0 + j].p;
+        }
+        if ((r = vd3d_depth_infer_batch_device(depth, nb, f_d, src_h, src_w, d_d, nullptr, 0))) {
+          ctx->err = std::string("depth engine: ") + vd3d_depth_last_error(depth);
+          return r;
+        }
+        ctx->prof_depth_frames += nb;
+      }
+    } else {
+      cudaStream_t sd = ctx->s_depth[c];
+      for (int j = 0; j < nb; ++j) {
+        CK(cudaStreamWaitEvent(sd, ctx->ev_h2d[slot0 + j], 0));
+        if (reuse) CK(cudaStreamWaitEvent(sd, ctx->ev_done[slot0 + j], 0));  // in_depth[slot] consumed
+      }
+      if ((r = run_depth_group(ctx, depth, c, slot0, nb, src_h, src_w))) return r;
+      CK(cudaEventRecord(ctx->ev_depth[c], sd));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_depth[c], 0));
+    }
+    // ---- DIBR loop body of the group's frames on the main stream ----
+    for (int j = 0; j < nb; ++j) {
+      const int sl = slot0 + j;
+      if (reuse) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[sl], 0));  // out_dev[slot] drained
+      if ((r = run_frame_slot(ctx, nullptr, sl, 1, src_h, src_w, rp, pl))) return r;
+      CK(cudaEventRecord(ctx->ev_done[sl], ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[sl], 0));
+      CK(cudaMemcpyAsync(outs[i0 + j], ctx->out_dev[sl].p, ob, kout, ctx->s_d2h));
+      CK(cudaEventRecord(ctx->ev_d2h[sl], ctx->s_d2h));
+    }
   }
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaStreamSynchronize(ctx->s_d2h));
   if (!serial)
-    for (int b = 0; b < kSlots; ++b) CK(cudaStreamSynchronize(ctx->s_depth[b]));
+    for (int b = 0; b < kClones; ++b) CK(cudaStreamSynchronize(ctx->s_depth[b]));
   return VD3D_OK;
 }
+
+int vd3d_set_depth_batch(vd3d_ctx* ctx, int frames) {
+  if (!ctx || frames < 1 || frames > kMaxDepthBatch) return fail(ctx, VD3D_ERR_ARG, "depth batch must be in [1, 4]");
+  if (frames != ctx->depth_batch) {
+    CK(cudaDeviceSynchronize());
+    ctx->depth_batch = frames;
+  }
+  return VD3D_OK;
+}
+int vd3d_get_depth_batch(vd3d_ctx* ctx) { return ctx ? ctx->depth_batch : -1; }
 
 // ---- exact frame sharding: advance / export / import the temporal state ----------
 // One loop iteration without rendering: updates TemporalDepthFilter, DepthPercentileEMA, ShiftSmoother,
@@ -1814,7 +1882,7 @@ int vd3d_release_depth(vd3d_ctx* ctx, vd3d_depth* depth) {
     cudaStreamSynchronize(ctx->stream);
     drop_depth_graphs(ctx);
     drop_graphs(ctx);
-    for (int i = 0; i < kSlots; ++i) {
+    for (int i = 0; i < kClones; ++i) {
       if (ctx->s_depth[i]) cudaStreamSynchronize(ctx->s_depth[i]);
       if (ctx->dclone[i]) vd3d_depth_destroy(ctx->dclone[i]);
       ctx->dclone[i] = nullptr;

@@ -54,6 +54,8 @@ def _bind(lib):
     lib.vd3d_depth_infer.restype = i
     lib.vd3d_depth_infer_device.argtypes = [vp, vp, i, i, vp, vp, i]
     lib.vd3d_depth_infer_device.restype = i
+    lib.vd3d_depth_infer_batch.argtypes = [vp, i, C.POINTER(vp), i, i, C.POINTER(vp), C.POINTER(vp), i]
+    lib.vd3d_depth_infer_batch.restype = i
     lib.vd3d_depth_profile.argtypes = [vp, i]
     lib.vd3d_depth_profile.restype = i
     lib.vd3d_depth_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i), C.POINTER(C.c_double)]
@@ -122,8 +124,29 @@ class DepthEngine:
         return d32, d8
 
     def infer_batch(self, frames_bgr, invert=False, check_size=True):
-        """List of same-shape BGR frames -> list of (predicted_depth f32, min-max u8)."""
-        return [self.infer(f, invert=invert, check_size=check_size) for f in frames_bgr]
+        """List of same-shape BGR frames -> list of (predicted_depth f32, min-max u8), up to 8 frames per batched
+        forward (the token-wise GEMMs run on the stacked token matrix of the batch)."""
+        frames = [np.ascontiguousarray(f, dtype=np.uint8) for f in frames_bgr]
+        if not frames:
+            return []
+        h, w = frames[0].shape[:2]
+        if any(f.shape[:2] != (h, w) for f in frames):
+            raise ValueError("infer_batch needs frames of one shape")
+        if check_size and processed_size(w, h) != (self.image_h, self.image_w):
+            raise ValueError(f"engine built for processed size {(self.image_h, self.image_w)}, a {w}x{h} frame needs "
+                             f"{processed_size(w, h)}")
+        out = []
+        for i0 in range(0, len(frames), 8):
+            chunk = frames[i0:i0 + 8]
+            n = len(chunk)
+            d32 = [np.empty((h, w), dtype=np.float32) for _ in range(n)]
+            d8 = [np.empty((h, w), dtype=np.uint8) for _ in range(n)]
+            fp = (C.c_void_p * n)(*[f.ctypes.data for f in chunk])
+            p32 = (C.c_void_p * n)(*[a.ctypes.data for a in d32])
+            p8 = (C.c_void_p * n)(*[a.ctypes.data for a in d8])
+            self.check(self.lib.vd3d_depth_infer_batch(self.h, n, fp, h, w, p32, p8, int(bool(invert))))
+            out += list(zip(d32, d8))
+        return out
 
     def get_buffer(self, name, shape, dtype):
         out = np.empty(shape, dtype=dtype)

@@ -300,9 +300,12 @@ def plan_sizes(src_w, src_h, rp):
 
 
 def output_shape(rp, pl):
+    """Shape of the packed frame (format_3d_output, core/render_3d.py:837-860): anaglyph / interlaced are one eye wide,
+    the SBS family is the hstack of the two fitted eyes (2 * per_eye_w: one less than plan.out_width for an odd
+    preserve-aspect Half-SBS width)."""
     if rp.output_format in (_lib.FMT["Red-Cyan Anaglyph"], _lib.FMT["Passive Interlaced"]):
         return (pl.per_eye_h, pl.per_eye_w, 3)
-    return (pl.out_height, pl.out_width, 3)
+    return (pl.per_eye_h, 2 * pl.per_eye_w, 3)
 
 
 def render_frame(frame_bgr, depth_bgr, rp, want_info=False, ctx=None):
