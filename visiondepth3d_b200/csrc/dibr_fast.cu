@@ -844,17 +844,6 @@ __global__ void __launch_bounds__(RT) k_render(RenderArgs a) {
         }
         bl = s.x / kk;
         br = s.y / kk;
-        if (a.dbg & 4) {  // triage: the reference's row-major K x K order straight from the edge tile
-          float al = 0.f, ar = 0.f;
-          for (int dy = 0; dy < K; ++dy)
-            for (int dx = 0; dx < K; ++dx) {
-              float2 v = bufE[(ty + dy) * EX + tx + dx];
-              al = al + v.x;
-              ar = ar + v.y;
-            }
-          bl = al / kk;
-          br = ar / kk;
-        }
       }
       float sv = __ldg(shift + (size_t)gy * W + gx);
       float xv = __ldg(xs + gx), yv = __ldg(ys + gy);

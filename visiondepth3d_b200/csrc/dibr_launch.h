@@ -176,7 +176,6 @@ struct RenderArgs {
   float kc, ke;
   uint8_t* out;
   int out_w, per_eye_w;    // packed row length in pixels; width of one eye in the packed frame
-  int dbg;                 // triage bits (env VD3D_FAST_DEBUG): 4 = row-major K*K box sum instead of the separable one
 };
 
 bool render_supports(int feather, int k);

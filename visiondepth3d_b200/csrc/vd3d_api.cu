@@ -45,7 +45,7 @@ struct vd3d_ctx {
   // bumped whenever a device resource that captured graphs bake in moves or changes content (ensure() reallocations,
   // linspace axes, INTER_AREA tables, DOF kernel bank); run_frame_slot drops stale graphs
   uint64_t res_epoch = 0, fg_epoch = 0;
-  int fast_dbg = 0;           // env VD3D_FAST_DEBUG: triage bits of the fast path (1 exact pow, 2 exact k_shift, 4 row-major box sum)
+  int fast_dbg = 0;           // env VD3D_FAST_DEBUG: triage bits of the fast path (1 exact pow, 2 exact k_shift)
   int prof_depth_frames = 0;  // frames covered by the stage-2 (depth) samples since the last collect
   uint64_t dclone_wver = 0;
   unsigned* bar = nullptr;  // grid barrier counter of k_stats (inside jobwords: zeroed by begin_frame)
@@ -446,7 +446,6 @@ int run_core_fast(vd3d_ctx* ctx, const CoreIn& in, const FastLoop* lp, const Fas
     ra.out = post.out;
     ra.out_w = post.out_w;
     ra.per_eye_w = post.per_eye_w;
-    ra.dbg = ctx->fast_dbg;
     {
       ProfScope ps(ctx, 1);
       CK(launch_render(ra, s));
