@@ -366,6 +366,94 @@ class GpuArm:
         self.ctx.check(self.lib.vd3d_render_clip(self.ctx.h, self.B, a, d, 3, wl["h"], wl["w"], C.byref(self.rp), c,
                                                  _lib.MEM_DEVICE, None))
 
+    def step_dibr_host(self):
+        idx, wl, _lib = self._idx(), self.wl, self._lib
+        if not hasattr(self, "d_host"):
+            self.d_host = [t.cpu().pin_memory() for t in self.d_dev]
+        a, d, c = self.ptr_array(self.f_host, idx), self.ptr_array(self.d_host, idx), self.ptr_array(self.o_host, idx)
+        self.ctx.check(self.lib.vd3d_render_clip(self.ctx.h, self.B, a, d, 3, wl["h"], wl["w"], C.byref(self.rp), c,
+                                                 _lib.MEM_HOST, None))
+
+    def python_surface(self, n_frames):
+        """render_sbs_3d -- the call a user of the reference makes -- on an in-memory source and a counting sink
+        (cv2.VideoCapture / the writer patched out, as tools/gen_golden.py does), so that the number is the drop-in's
+        reader thread + pinned ring + batched vd3d_render_clip pipeline and not a codec's."""
+        import cv2
+        from visiondepth3d_b200 import render_3d as R
+        wl = self.wl
+        pool_f = [t.numpy() for t in self.f_host]
+        pool_d = [t.cpu().numpy() for t in self.d_dev]
+        P = len(pool_f)
+
+        class Cap:
+            def __init__(self, which):
+                self.src, self.pos = (pool_f if which == "rgb" else pool_d), 0
+
+            def isOpened(self):
+                return True
+
+            def get(self, prop):
+                if prop == cv2.CAP_PROP_FRAME_COUNT:
+                    return float(n_frames + 1)
+                if prop == cv2.CAP_PROP_FPS:
+                    return 24.0
+                if prop == cv2.CAP_PROP_POS_FRAMES:
+                    return float(self.pos)
+                return 0.0
+
+            def set(self, prop, v):
+                if prop == cv2.CAP_PROP_POS_FRAMES:
+                    self.pos = int(v)
+                return True
+
+            def read(self):
+                if self.pos > n_frames:
+                    return False, None
+                self.pos += 1
+                return True, self.src[self.pos % P]
+
+            def release(self):
+                pass
+
+        class Sink:
+            count = 0
+
+            def __init__(self, *a, **k):
+                pass
+
+            def ok(self):
+                return True
+
+            def write(self, frame):
+                Sink.count += 1
+
+            def close(self):
+                pass
+
+        class Var:
+            def get(self):
+                return "Default (16:9)"
+
+        real_cap, real_sink = cv2.VideoCapture, R._FrameSink
+        cv2.VideoCapture, R._FrameSink = Cap, Sink
+        R._lib._default_ctx[self.dev.index] = self.ctx
+        try:
+            def go():
+                Sink.count = 0
+                t0 = time.perf_counter()
+                R.render_sbs_3d("rgb", "depth", "out.mp4", "mp4v", 24.0, wl["w"], wl["h"], COMMON["fg"], COMMON["mg"],
+                                COMMON["bg"], COMMON["sharp"], wl["fmt"], Var(), R.aspect_ratios, COMMON["dof"],
+                                feather_strength=COMMON["feather"], blur_ksize=COMMON["ksize"],
+                                use_subject_tracking=COMMON["tracking"], use_floating_window=COMMON["floating"],
+                                preserve_original_aspect=wl["preserve"], zero_parallax_strength=COMMON["zps"],
+                                suspend_flag=threading.Event(), cancel_flag=threading.Event())
+                return Sink.count / (time.perf_counter() - t0), Sink.count
+            go()                       # warm-up (workspaces, graphs)
+            fps, n = go()
+        finally:
+            cv2.VideoCapture, R._FrameSink = real_cap, real_sink
+        return fps, n
+
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
@@ -415,6 +503,15 @@ class GpuArm:
         dsteps = max(4, min(args.steps, 10))
         dms, _ = self.timed(self.step_dibr, dsteps, 3)
         dibr_fps = dsteps * B / (dms / 1000.0)          # per GPU
+        # ---------------- DIBR stage through host buffers, and through the Python drop-in surface (rank 0, N = 1) -----
+        py_fps = py_n = dibr_host_fps = None
+        if world == 1:
+            _, hs = self.timed(self.step_dibr_host, dsteps, 3)
+            dibr_host_fps = dsteps * B / hs
+            try:
+                py_fps, py_n = self.python_surface(dsteps * B)
+            except Exception as e:  # informational arm: never take the bench line down
+                py_fps, py_n = None, str(e)
         # ---------------- per-stage device timing (CUDA events around the stages; serial eager launches) ----------
         lib.vd3d_profile(ctx.h, 1)
         lib.vd3d_depth_profile(deng.h, 1)
@@ -492,6 +589,12 @@ class GpuArm:
             "dibr_only": {"what": "DIBR stage back to back on device-resident u8 depth (vd3d_render_clip, graph replay)",
                           "frames_per_s_per_gpu": dibr_fps, "achieved": tput_gbs, "peak": hbm_peak, "unit": "GB/s",
                           "frac": tput_gbs / hbm_peak, "ms_per_frame": 1000.0 / dibr_fps},
+            "python_surface": {"what": "render_sbs_3d (drop-in call surface: reader thread -> pinned ring -> batched "
+                                       "vd3d_render_clip -> writer thread) on an in-memory source / counting sink, given depth "
+                                       "frames (no depth engine on this path), against the same stage through the C ABI on "
+                                       "pinned host buffers", "frames_per_s": py_fps, "frames": py_n,
+                               "c_abi_host_buffers_frames_per_s": dibr_host_fps,
+                               "ratio": (py_fps / dibr_host_fps) if (py_fps and dibr_host_fps) else None},
         }
         return line
 
@@ -544,7 +647,7 @@ def main():
         del a4
         if rank == 0:
             keep = ("value", "unit", "ms_per_step", "config", "run", "clocks", "e2e", "gpu_launches", "roofline",
-                    "roofline_depth_stage", "roofline_dibr_render", "roofline_dibr_stage", "dibr_only")
+                    "roofline_depth_stage", "roofline_dibr_render", "roofline_dibr_stage", "dibr_only", "python_surface")
             line["arm_4k"] = {k: l4[k] for k in keep}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

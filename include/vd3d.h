@@ -211,6 +211,9 @@ int vd3d_check_config(vd3d_ctx* ctx, int src_h, int src_w, const vd3d_render_par
  * luma, contrast around 0.5, additive brightness, clamp) */
 int vd3d_color_grade(vd3d_ctx* ctx, const float* rgb, int h, int w, double saturation, double contrast,
                      double brightness, float* out, int mem);
+/* cv2.resize(u8 plane [h,w], (ow,oh), interpolation=cv2.INTER_CUBIC): the resize the depth writer applies to the u8
+ * depth (core/render_depth.py:1917, 193): float32 bicubic (A = -0.75), round half to even */
+int vd3d_resize_cubic_u8(vd3d_ctx* ctx, const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, int mem);
 /* apply_sharpening (717-732) on u8 BGR [h,w,3] */
 int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem);
 /* heal_missing_pixels (431-459; the reference's "gradient-blend occlusion fill", defined but not called by

@@ -947,3 +947,39 @@ def render_frame(gs: GlobalState, cs: ClipState, frame_bgr: np.ndarray, depth_bg
         return final, dict(left=left, right=right, focal=focal, dyn=dyn, stable_zero=stable,
                            bar=bar, depth_norm=dn)
     return final
+
+
+def _cubic_axis(ssize, dsize):
+    """cv2.resize(INTER_CUBIC) source taps and Catmull-Rom-like weights (A = -0.75) of one axis, float32 like cv2's
+    interpolateCubic (imgproc/src/resize.cpp); border taps are clamped."""
+    scale = ssize / dsize
+    d = np.arange(dsize)
+    fx = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    sx = np.floor(fx).astype(np.int64)
+    x = (fx - sx.astype(np.float32)).astype(np.float32)
+    A, one = np.float32(-0.75), np.float32(1)
+    x1, xm = x + one, one - x
+    c0 = ((A * x1 - np.float32(5) * A) * x1 + np.float32(8) * A) * x1 - np.float32(4) * A
+    c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+    c2 = ((A + np.float32(2)) * xm - (A + np.float32(3))) * xm * xm + one
+    c3 = one - c0 - c1 - c2
+    ofs = np.clip(sx[:, None] - 1 + np.arange(4)[None], 0, ssize - 1)
+    return ofs, np.stack([c0, c1, c2, c3], 1).astype(np.float32)
+
+
+def resize_cubic_u8(img: np.ndarray, ow: int, oh: int) -> np.ndarray:
+    """cv2.resize(u8 [h, w], (ow, oh), interpolation=cv2.INTER_CUBIC) as the depth writer applies it
+    (core/render_depth.py:1917, 193).  The installed cv2 (4.13 with Intel IPP) evaluates the bicubic in float32:
+    rows first, then columns, round half to even.  Pinned against cv2 at <= 1 LSB with < 1e-4 of the pixels off
+    (tests/test_oracle_golden.py); cv2's own non-IPP fixed-point path differs from its IPP path by 1 LSB on 3-5 %."""
+    h, w = img.shape
+    if (h, w) == (oh, ow):
+        return img.copy()
+    xo, xa = _cubic_axis(w, ow)
+    yo, ya = _cubic_axis(h, oh)
+    S = img.astype(np.float32)
+    R = S[yo]                                   # [oh, 4, w]
+    V = ((R[:, 0] * ya[:, 0, None] + R[:, 1] * ya[:, 1, None]) + R[:, 2] * ya[:, 2, None]) + R[:, 3] * ya[:, 3, None]
+    C = V[:, xo]                                # [oh, ow, 4]
+    Hh = ((C[..., 0] * xa[None, :, 0] + C[..., 1] * xa[None, :, 1]) + C[..., 2] * xa[None, :, 2]) + C[..., 3] * xa[None, :, 3]
+    return np.clip(np.rint(Hh), 0, 255).astype(np.uint8)

@@ -61,6 +61,20 @@ def _tol(mode, kind="noise"):
     return (2e-5, 2e-5, 0.01, 0.05, 0.012, 16)
 
 
+def _ps(R, fr, dp, w, h, kw, infos=None):
+    ft, dt = O.bgr_to_rgb01(fr), O.depth_bgr_to_01(dp)
+    return R.pixel_shift_cuda(ft, dt, w, h, kw.get("fg", 4.5), kw.get("mg", -1.5), kw.get("bg", -6.0),
+                              _info=infos, **{k: v for k, v in kw.items() if k not in ("fg", "mg", "bg")})
+
+
+def _oracle_kw(kw):
+    m = dict(kw)
+    for a, b in (("fg", "fg_shift"), ("mg", "mg_shift"), ("bg", "bg_shift")):
+        if a in m:
+            m[b] = m.pop(a)
+    return m
+
+
 SIZES = [(320, 180, 320, 180), (157, 93, 157, 93), (320, 180, 160, 90), (256, 144, 100, 60), (64, 40, 64, 40)]
 PARAMS = [
     dict(blur_ksize=9, feather_strength=10.0, zero_parallax_strength=0.01),

@@ -165,3 +165,61 @@ def test_pipe_protocol():
     assert np.array_equal(RD.depth_u8_from_frame(fr), g)  # GPU min-max u8 == host helper on the same depth
     res2 = pipe([imgs[0]], inference_size=(320, 180))
     assert tuple(res2[0]["predicted_depth"].shape) == (180, 320)
+
+
+def test_loader_entry_points_and_depth_video(tmp_path, monkeypatch):
+    """ensure_model_downloaded / update_pipeline on a local HF-format checkpoint folder (core/render_depth.py:728-829,
+    973-1140), then the depth-video writer in the reference's handoff format (XVID BGR .mkv + .letterbox.json,
+    1736-1763, 1894-1935) feeding render_sbs_3d."""
+    import cv2
+    import json
+    import torch
+    from safetensors.torch import save_file
+    from transformers import DepthAnythingForDepthEstimation
+    from visiondepth3d_b200 import render_3d as R
+    from visiondepth3d_b200 import render_depth as RD
+    from visiondepth3d_b200.depth_weights import hf_config
+    # a checkpoint folder laid out like the reference's cache: weights/<org>_<name>/model.safetensors
+    torch.manual_seed(0)
+    sd = DepthAnythingForDepthEstimation(hf_config("vits")).eval().state_dict()
+    wdir = tmp_path / "weights"
+    ck = wdir / "depth-anything_Depth-Anything-V2-Small-hf"
+    ck.mkdir(parents=True)
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(ck / "model.safetensors"))
+    monkeypatch.setattr(RD, "local_model_dir", str(wdir))
+    got, meta = RD.ensure_model_downloaded("depth-anything/Depth-Anything-V2-Small-hf")
+    assert meta["arch"] == "vits" and set(got) == set(sd)
+    assert RD.ensure_model_downloaded("depth-anything/Depth-Anything-V2-Base-hf") == (None, None)
+
+    class Label:
+        text = ""
+
+        def config(self, text=""):
+            Label.text = text
+
+    t = RD.update_pipeline(_Var("Depth Anything V2 Small"), Label(), _Var("Original"), None)
+    t.join(timeout=600)
+    assert RD.pipe is RD.hf_batch_safe_pipe and RD.pipe_type == "hf" and Label.text.startswith("✅")
+    # depth video in the reference's format
+    w, h, n = 320, 180, 7
+    rgb, _ = _write_inputs(tmp_path, w, h, n)
+    dpath = str(tmp_path / "clip_depth.mkv")
+    assert RD.depth_video_from_video(rgb, dpath, batch_size=3) == n
+    side = json.load(open(str(tmp_path / "clip_depth.letterbox.json")))
+    assert side == {"top": 0, "bottom": 0, "orig_w": w, "orig_h": h} == RD.read_letterbox_sidecar(dpath)
+    cap = cv2.VideoCapture(dpath)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) == w and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n
+    ok, d0 = cap.read()
+    cap.release()
+    assert ok and d0.shape == (h, w, 3) and d0.std() > 1.0
+    # ... and it is what render_sbs_3d's depth_path expects
+    out = str(tmp_path / "sbs.avi")
+    R.render_sbs_3d(rgb, dpath, out, "MJPG", 24.0, w, h, 4.5, -1.5, -6.0, 0.2, "Half-SBS", _Var("Default (16:9)"),
+                    R.aspect_ratios, 0.0, feather_strength=10.0, blur_ksize=9, use_subject_tracking=True,
+                    use_floating_window=True, suspend_flag=threading.Event(), cancel_flag=threading.Event())
+    cap = cv2.VideoCapture(out)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n - 1
+    cap.release()
+    # inference_size path: PIL bicubic in, cv2-INTER_CUBIC-equivalent resize of the u8 depth back out
+    d2 = str(tmp_path / "clip_depth_small.mkv")
+    assert RD.depth_video_from_video(rgb, d2, inference_size=(224, 126), batch_size=4, max_frames=4) == 4

@@ -73,3 +73,18 @@ def test_vr_loop_vs_oracle_and_golden(R, golden_dir):
         assert mx <= 12 and f1 <= 0.03, (j, mx, f0, f1)
     l = np.full((1600, 1440, 3), 7, dtype=np.uint8)
     assert np.array_equal(R.format_3d_output(l, l + 1, "VR"), np.hstack((l, l + 1)))
+
+
+def test_resize_cubic_u8_matches_oracle():
+    """vd3d_resize_cubic_u8 (the depth writer's cv2 INTER_CUBIC) against the cv2-pinned oracle: same float32
+    arithmetic, exact."""
+    from visiondepth3d_b200 import render_depth as RD
+    rng = np.random.default_rng(9)
+    for (w, h, ow, oh) in ((924, 518, 1920, 1080), (100, 70, 133, 91), (640, 360, 320, 180), (37, 23, 80, 50), (64, 48, 64, 48)):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(RD.resize_cubic_u8(img, ow, oh), O.resize_cubic_u8(img, ow, oh)), (w, h, ow, oh)
+    d = rng.random((70, 100)).astype(np.float32)
+    u = RD._normalize_to_u8(d, (133, 91), invert=True)
+    lo, hi = np.percentile(d, 1.0), np.percentile(d, 99.0)
+    ref = 255 - (np.clip((d - lo) / (hi - lo), 0.0, 1.0) * 255.0).astype(np.uint8)
+    assert np.array_equal(u, O.resize_cubic_u8(ref, 133, 91))

@@ -982,6 +982,53 @@ __global__ void __launch_bounds__(256) k_heal(const float* __restrict__ warped, 
   }
 }
 
+// cv2.resize(u8 plane, INTER_CUBIC) (core/render_depth.py:1917): float32 bicubic, A = -0.75, rows then columns,
+// round half to even -- the arithmetic of oracle.resize_cubic_u8 (pinned to the installed cv2 / IPP)
+struct CubicTap {
+  int o[4];
+  float c[4];
+};
+__device__ __forceinline__ CubicTap cubic_tap(int d, int ssize, int dsize) {
+  CubicTap t;
+  const double scale = (double)ssize / (double)dsize;
+  float fx = (float)(((double)d + 0.5) * scale - 0.5);
+  float fl = floorf(fx);
+  int sx = (int)fl;
+  float x = fx - fl;
+  const float A = -0.75f;
+  float x1 = x + 1.0f, xm = 1.0f - x;
+  t.c[0] = ((((A * x1) - (5.0f * A)) * x1) + (8.0f * A)) * x1 - (4.0f * A);
+  t.c[1] = ((((A + 2.0f) * x) - (A + 3.0f)) * x) * x + 1.0f;
+  t.c[2] = ((((A + 2.0f) * xm) - (A + 3.0f)) * xm) * xm + 1.0f;
+  t.c[3] = ((1.0f - t.c[0]) - t.c[1]) - t.c[2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t.o[k] = min(max(sx - 1 + k, 0), ssize - 1);
+  return t;
+}
+__global__ void __launch_bounds__(256) k_resize_cubic_u8(const uint8_t* __restrict__ src, int h, int w,
+                                                         uint8_t* __restrict__ dst, int oh, int ow) {
+  int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= ow || y >= oh) return;
+  CubicTap tx = cubic_tap(x, w, ow), ty = cubic_tap(y, h, oh);
+  float col[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // rows first: the value of column tx.o[k] at output row y
+    const int xc = tx.o[k];
+    float v = (float)src[(size_t)ty.o[0] * w + xc] * ty.c[0];
+    v = v + ((float)src[(size_t)ty.o[1] * w + xc] * ty.c[1]);
+    v = v + ((float)src[(size_t)ty.o[2] * w + xc] * ty.c[2]);
+    v = v + ((float)src[(size_t)ty.o[3] * w + xc] * ty.c[3]);
+    col[k] = v;
+  }
+  float r = (((col[0] * tx.c[0]) + (col[1] * tx.c[1])) + (col[2] * tx.c[2])) + (col[3] * tx.c[3]);
+  dst[(size_t)y * ow + x] = rhe_u8(r);
+}
+void launch_resize_cubic_u8(const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, cudaStream_t s) {
+  dim3 g((ow + 31) / 32, (oh + 7) / 8);
+  k_resize_cubic_u8<<<g, 256, 0, s>>>(src, h, w, dst, oh, ow);
+}
+
 // apply_color_grade (core/render_3d.py:734-767) on planar f32 RGB
 __global__ void __launch_bounds__(256) k_grade_f32(const float* __restrict__ src, float* __restrict__ dst, int n, float sat,
                                                    float con, float bri) {

@@ -1912,6 +1912,30 @@ int vd3d_check_config(vd3d_ctx* ctx, int src_h, int src_w, const vd3d_render_par
   return VD3D_OK;
 }
 
+// cv2.resize(u8 [h,w], (ow,oh), INTER_CUBIC): the resize of the depth writer (core/render_depth.py:1917, 193)
+int vd3d_resize_cubic_u8(vd3d_ctx* ctx, const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, int mem) {
+  if (!ctx || !src || !dst || h < 1 || w < 1 || oh < 1 || ow < 1) return fail(ctx, VD3D_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const void* s_d;
+  int r;
+  if ((r = copy_in(ctx, ctx->eyeL, src, (size_t)h * w, mem, s, &s_d))) return r;
+  uint8_t* o_d = dst;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->out_dev[0], (size_t)oh * ow))) return r;
+    o_d = (uint8_t*)ctx->out_dev[0].p;
+  }
+  if (h == oh && w == ow)
+    CK(cudaMemcpyAsync(o_d, s_d, (size_t)h * w, cudaMemcpyDeviceToDevice, s));  // cv2.resize copies on equal sizes
+  else
+    launch_resize_cubic_u8((const uint8_t*)s_d, h, w, o_d, oh, ow, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(dst, o_d, (size_t)oh * ow, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+
 // apply_color_grade (core/render_3d.py:734-767) on f32 RGB planes [3,h,w] in 0..1
 int vd3d_color_grade(vd3d_ctx* ctx, const float* rgb, int h, int w, double sat, double con, double bri, float* out,
                      int mem) {

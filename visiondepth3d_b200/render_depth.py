@@ -186,12 +186,24 @@ def convert_depth_to_grayscale(depth):
     return ((plane - lo) / (hi - lo + 1e-6) * 255).astype(np.uint8)
 
 
+def resize_cubic_u8(plane, width, height):
+    """cv2.resize(u8 plane, (width, height), interpolation=cv2.INTER_CUBIC) on the GPU (vd3d_resize_cubic_u8): the
+    resize the reference's depth writer applies to the u8 depth (core/render_depth.py:1917, 193)."""
+    from . import _lib
+    ctx = _lib.default_context(0)
+    src = np.ascontiguousarray(plane, dtype=np.uint8)
+    assert src.ndim == 2
+    out = np.empty((int(height), int(width)), dtype=np.uint8)
+    ctx.check(ctx.lib.vd3d_resize_cubic_u8(ctx.h, src.ctypes.data, src.shape[0], src.shape[1], out.ctypes.data,
+                                           int(height), int(width), _lib.MEM_HOST))
+    return out
+
+
 def _normalize_to_u8(depth_f, out_size, invert=False, pclip=(1.0, 99.0)):
     """core/render_depth.py:173-194 (the ndarray / tiled-depth front end): non-finite values -> 0, clip to the
     [p1, p99] percentiles (np.percentile, linear), fall back to min-max when they coincide and to flat 128 when the
-    frame is flat, truncate to u8, optional inversion, cv2 INTER_CUBIC resize to out_size = (W, H).  Host helper:
-    the HF tensor path of the hot loop never takes it (1907-1917)."""
-    import cv2
+    frame is flat, truncate to u8, optional inversion, INTER_CUBIC resize to out_size = (W, H) on the GPU.  The
+    percentile front end is a host helper: the HF tensor path of the hot loop never takes it (1907-1917)."""
     d = np.asarray(depth_f, dtype=np.float32)
     if not np.isfinite(d).all():
         d = np.nan_to_num(d, nan=0.0, posinf=0.0, neginf=0.0)
@@ -206,7 +218,7 @@ def _normalize_to_u8(depth_f, out_size, invert=False, pclip=(1.0, 99.0)):
             u8 = np.full_like(d, 128, dtype=np.uint8)
     if invert:
         u8 = 255 - u8
-    return cv2.resize(u8, out_size, interpolation=cv2.INTER_CUBIC)
+    return resize_cubic_u8(u8, out_size[0], out_size[1])
 
 
 # ---------------------------------------------------------------------------
@@ -357,7 +369,7 @@ def depth_video_from_video(input_path, output_path, invert=False, inference_size
                 d8 = convert_depth_to_grayscale(res["predicted_depth"])
                 if invert:
                     d8 = 255 - d8
-                d8 = cv2.resize(d8, (W, H), interpolation=cv2.INTER_CUBIC)
+                d8 = resize_cubic_u8(d8, W, H)
                 out.write(cv2.cvtColor(d8, cv2.COLOR_GRAY2BGR))
                 n += 1
         batch.clear()
