@@ -509,7 +509,7 @@ class GpuArm:
             _, hs = self.timed(self.step_dibr_host, dsteps, 3)
             dibr_host_fps = dsteps * B / hs
             try:
-                py_fps, py_n = self.python_surface(dsteps * B)
+                py_fps, py_n = self.python_surface(max(300, dsteps * B))   # long enough to amortise the pinned-ring set-up
             except Exception as e:  # informational arm: never take the bench line down
                 py_fps, py_n = None, str(e)
         # ---------------- per-stage device timing (CUDA events around the stages; serial eager launches) ----------

@@ -60,7 +60,7 @@ struct vd3d_depth {
   // optional device timing of one GEMM class (the fc1 launches) for the roofline report
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;
-  int prof_rows = 0;  // rows (tokens of all images of the batch) of the timed fc1 launches
+  long long prof_rows = 0;  // rows (tokens of all images of the batch) summed over the timed fc1 launches
 };
 
 namespace {
@@ -281,8 +281,9 @@ int vd3d_depth_profile_collect(vd3d_depth* e, double* total_ms, int* count, doub
   e->prof_ev.clear();
   *total_ms = t;
   *count = n;
-  if (gflop_per_launch)
-    *gflop_per_launch = 2.0 * (e->prof_rows ? e->prof_rows : e->ntok) * (4.0 * e->cfg.hidden) * e->cfg.hidden / 1e9;
+  if (gflop_per_launch)  // average over the timed launches (batches of different sizes have different row counts)
+    *gflop_per_launch = 2.0 * (n ? (double)e->prof_rows / n : (double)e->ntok) * (4.0 * e->cfg.hidden) * e->cfg.hidden / 1e9;
+  e->prof_rows = 0;
   return VD3D_OK;
 }
 
@@ -585,7 +586,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0, s);
-        e->prof_rows = MT;
+        e->prof_rows += MT;
       }
       if ((r = gemm(e, (const __half*)xn, D, wf1, D, g))) return r;
       if (e->prof) {

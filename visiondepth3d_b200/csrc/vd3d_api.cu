@@ -97,7 +97,7 @@ struct vd3d_ctx {
     uint64_t n = 0;
   } dg[kClones][kMaxDepthBatch + 1];
   int dg_warm = 0, dg_h = 0, dg_w = 0;
-  int depth_batch = 3;  // frames per depth forward in vd3d_render_clip_depth (env VD3D_DEPTH_BATCH, 1..4)
+  int depth_batch = 4;  // frames per depth forward in vd3d_render_clip_depth (env VD3D_DEPTH_BATCH, 1..4)
   // dof kernel cache
   double dof_sigma_cached = -1.0;
   int dof_nlevels = 0, dof_ksize[8] = {0}, dof_koff[8] = {0}, dof_halo = 0;
