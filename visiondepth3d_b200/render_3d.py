@@ -352,32 +352,6 @@ class _ClipWindow:
         self.bounded = end_s is not None
 
 
-def _frame_pairs(cap, dcap, win, suspend_flag, cancel_flag):
-    """(frame, depth) pairs in the order the reference's loop consumes them (core/render_3d.py:1184-1225, 1429-1432):
-    seek to the window start, read and drop one pair, then at most win.budget pairs; stops at the first failed read,
-    on cancel, or -- when an end time was given -- once the colour stream's position has reached the window's end."""
-    import cv2
-    cap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
-    dcap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
-    ok_a, _ = cap.read()
-    ok_b, _ = dcap.read()
-    if not (ok_a and ok_b):
-        return
-    for _ in range(win.budget):
-        while suspend_flag.is_set() and not cancel_flag.is_set():
-            time.sleep(0.2)
-        if cancel_flag.is_set():
-            return
-        ok_a, frame = cap.read()
-        ok_b, depth = dcap.read()
-        if not (ok_a and ok_b):
-            return
-        last = win.bounded and int(cap.get(cv2.CAP_PROP_POS_FRAMES)) >= win.stop
-        yield frame, depth
-        if last:
-            return
-
-
 class _PinnedRing:
     """n page-locked host buffers of `shape` u8 (cudaMallocHost through the C ABI) viewed as numpy arrays."""
 
@@ -462,8 +436,8 @@ def render_sbs_3d(
 ):
     """core/render_3d.py:933-1504: video in -> video out.
 
-    Three stages run concurrently: a reader thread decodes frame / depth pairs (cv2) into a ring of page-locked
-    buffers, the calling thread hands batches of them to vd3d_render_clip (H2D | kernels | D2H pipelined over three
+    Three stages run concurrently: reader threads decode the colour and the depth stream in parallel (cv2) into a
+    ring of page-locked buffers, the calling thread hands batches of them to vd3d_render_clip (H2D | kernels | D2H pipelined over three
     streams, CUDA-graph replay), and a writer thread pushes the packed frames of the previous batch as raw bgr24 into
     an ffmpeg pipe (use_ffmpeg, when the binary exists) or a cv2.VideoWriter.  Sequencing follows the reference:
     first pair of the window dropped, pop controls and parallax_balance not forwarded (1284-1331), no exception
@@ -484,8 +458,9 @@ def render_sbs_3d(
     n_frames = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
     fps = cap.get(cv2.CAP_PROP_FPS) or fps or 30.0        # the container's rate wins over the argument (993)
     win = _ClipWindow(n_frames, fps, start_s, end_s)
-    sink = ring_in = ring_out = None
+    sink = ring_in = ring_out = free_in = None
     stop = threading.Event()
+    threads = []
     try:
         if win.empty:
             print("⚠️ Invalid clip window; nothing to render.")
@@ -527,17 +502,52 @@ def render_sbs_3d(
         free_out.put(1)
         errors = []
 
+        # the colour and the depth stream are decoded (cv2 releases the GIL) and copied into the pinned ring by one
+        # worker thread each; `reader` sequences them exactly like the reference's loop consumes pairs
+        jobs = (queue.Queue(), queue.Queue())
+        done = (queue.Queue(), queue.Queue())
+
+        def stream_worker(which, src):
+            while True:
+                k = jobs[which].get()
+                if k is None:
+                    return
+                try:
+                    ok, img = src.read()
+                    if ok and k >= 0:
+                        np.copyto(ring_in[which].arrays[k], img)
+                except Exception as e:
+                    errors.append(e)
+                    ok = False
+                done[which].put(bool(ok))
+
+        def read_pair(k):
+            jobs[0].put(k)
+            jobs[1].put(k)
+            ok_a, ok_b = done[0].get(), done[1].get()
+            return ok_a and ok_b
+
         def reader():
             try:
-                for frame, depth in _frame_pairs(cap, dcap, win, suspend_flag, cancel_flag):
-                    k = free_in.get()
-                    if stop.is_set():
-                        break
-                    np.copyto(ring_in[0].arrays[k], frame)
-                    np.copyto(ring_in[1].arrays[k], depth)
-                    ready.put(k)
+                cap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
+                dcap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
+                if read_pair(-1):                       # the first pair of the window is read and dropped (1184-1188)
+                    for _ in range(win.budget):
+                        while suspend_flag.is_set() and not cancel_flag.is_set():
+                            time.sleep(0.2)
+                        if cancel_flag.is_set():
+                            break
+                        k = free_in.get()
+                        if stop.is_set() or not read_pair(k):
+                            break
+                        last = win.bounded and int(cap.get(cv2.CAP_PROP_POS_FRAMES)) >= win.stop
+                        ready.put(k)
+                        if last:
+                            break
             except Exception as e:  # surfaced by the main thread
                 errors.append(e)
+            jobs[0].put(None)
+            jobs[1].put(None)
             ready.put(None)
 
         def writer():
@@ -556,7 +566,10 @@ def render_sbs_3d(
 
         th_r = threading.Thread(target=reader, daemon=True)
         th_w = threading.Thread(target=writer, daemon=True)
-        th_r.start()
+        threads += [threading.Thread(target=stream_worker, args=(which, src), daemon=True)
+                    for which, src in enumerate((cap, dcap))] + [th_r]
+        for t in threads:
+            t.start()
         th_w.start()
         done, t0, eof = 0, time.time(), False
         while not eof and not errors:
@@ -599,6 +612,10 @@ def render_sbs_3d(
         print(f"❌ Render crashed: {e}")
     finally:
         stop.set()
+        if free_in is not None:
+            free_in.put(-1)   # wake a reader that waits for a free slot
+        for t in threads:     # nobody may still be inside cap.read() / the pinned ring when they go away
+            t.join(timeout=5.0)
         cap.release()
         dcap.release()
         if sink is not None:

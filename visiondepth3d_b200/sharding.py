@@ -33,14 +33,19 @@ def broadcast_state_dict(sd, src=0, device=None):
     return sd
 
 
-def render_chunk_exact(ctx, frames, depths, rp, render_frame, advance_state, rank=None, world=None):
+def render_chunk_exact(ctx, frames, depths, rp, render_frame, advance_state, rank=None, world=None,
+                        reset_global=False):
     """Exact frame-sharded rendering of one clip.
 
     Every rank holds the whole list of (frame, depth) pairs or at least its own chunk.  Rank r
     (1) receives the temporal state after frame start-1 from rank r-1, (2) advances it over its own
     chunk without rendering and forwards it to rank r+1 -- this short scalar/plane chain is the only
     sequential part -- then (3) re-imports its start state and renders its chunk.  The result is
-    bit-identical to one GPU rendering the clip sequentially.
+    bit-identical to one GPU rendering the clip sequentially.  Like render_sbs_3d, rank 0 starts from fresh per-render
+    state but KEEPS the module-singleton trackers (DepthPercentileEMA, ConvergenceEMA, FloatingWindowTracker,
+    FloatingBarEaser persist across renders in the reference, core/render_3d.py:284-285,500,511) unless reset_global.
+    The chain is sequential: rank r starts rendering after ranks 0..r-1 have advanced over their chunks
+    (N_frames x t(k_stats) in total); see DESIGN.md section 7 for what that costs.
     Returns (start, stop, [rendered frames of the chunk])."""
     import numpy as np
     rank = dist.get_rank() if rank is None else rank
@@ -54,9 +59,14 @@ def render_chunk_exact(ctx, frames, depths, rp, render_frame, advance_state, ran
         start_state = blob.numpy().copy()
         ctx.import_state(start_state)
     else:
-        ctx.reset()
+        try:
+            ctx.reset(3 if reset_global else 2)   # STATE_GLOBAL | STATE_CLIP, or the per-render state only
+        except TypeError:                         # contexts without the split (host-logic tests)
+            ctx.reset()
         start_state = None
     if rank + 1 < world:
+        if start_state is None:
+            rank0_state = ctx.export_state()      # what rank 0 returns to after its advance pass (singletons included)
         for i in range(start, stop):
             advance_state(frames[i], depths[i], rp, ctx=ctx)
         end_state = torch.from_numpy(np.ascontiguousarray(ctx.export_state()))
@@ -65,6 +75,6 @@ def render_chunk_exact(ctx, frames, depths, rp, render_frame, advance_state, ran
         if start_state is not None:
             ctx.import_state(start_state)
         else:
-            ctx.reset()
+            ctx.import_state(rank0_state)
     outs = [render_frame(frames[i], depths[i], rp, ctx=ctx) for i in range(start, stop)]
     return start, stop, outs

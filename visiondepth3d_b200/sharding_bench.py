@@ -32,7 +32,7 @@ class ExactShard:
         lib.vd3d_depth_infer_batch_device.argtypes = [vp, i, C.POINTER(vp), i, i, C.POINTER(vp), C.POINTER(vp), i]
         lib.vd3d_depth_infer_batch_device.restype = i
 
-    def depth_chunk(self, frames_dev, batch=3):
+    def depth_chunk(self, frames_dev, batch=4):
         """u8 depth [h, w] per frame, device resident (one batched forward per `batch` frames)."""
         torch, lib = self.torch, self.ctx.lib
         depths = [torch.empty((self.h, self.w), dtype=torch.uint8, device=self.dev) for _ in frames_dev]
@@ -64,9 +64,11 @@ class ExactShard:
             dist.recv(start, src=self.rank - 1)
             self._import(start)
         else:
-            ctx.reset()
+            ctx.reset(self._lib.STATE_CLIP)   # a fresh render; the module-singleton trackers persist like the reference's
         if self.rank + 1 < self.world:
             t0 = time.perf_counter()
+            if start is None:
+                start0 = self._export()
             for f, d in zip(frames_dev, depths_dev):
                 ctx.check(lib.vd3d_advance_state(ctx.h, f.data_ptr(), d.data_ptr(), 1, self.h, self.w, C.byref(self.rp),
                                                  _lib.MEM_DEVICE))
@@ -74,10 +76,7 @@ class ExactShard:
             dist.send(torch.tensor([end.numel()], dtype=torch.int64, device=self.dev), dst=self.rank + 1)
             dist.send(end, dst=self.rank + 1)
             t_chain = time.perf_counter() - t0
-            if start is not None:
-                self._import(start)
-            else:
-                ctx.reset()
+            self._import(start if start is not None else start0)
         n = len(frames_dev)
         ctx.check(lib.vd3d_render_clip(ctx.h, n, _ptrs(frames_dev), _ptrs(depths_dev), 1, self.h, self.w,
                                        C.byref(self.rp), _ptrs(outs_dev), _lib.MEM_DEVICE, None))
