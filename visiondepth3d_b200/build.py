@@ -46,10 +46,12 @@ def build(verbose=False, force=False):
             subprocess.check_call(cmd)
         objs.append(obj)
     if force or _stale(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        tmp = LIB + ".tmp"  # link next to the target, then rename: a concurrent reader never sees a half-written library
+        cmd = [nvcc] + ARCH + ["-shared", "-o", tmp] + objs + ["-lcudart"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+        os.replace(tmp, LIB)
     return LIB
 
 
