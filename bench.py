@@ -173,7 +173,8 @@ def _dibr_workers():
 
 def _dibr_chunk(job):
     """Worker: render one chunk with its own temporal state; returns (seconds for the timed frames, frames)."""
-    wl, frames_idx, depths = job
+    wl, frames_idx, depths, common = job
+    COMMON.update(common)   # spawned workers re-import this module: carry the parent's parameters over
     from oracle import dibr as O
     from visiondepth3d_b200.synth import synth_frame
     gs, cs, rp = O.GlobalState(), O.ClipState(), oracle_params(wl)
@@ -229,8 +230,9 @@ class CpuPort:
         t_depth = time.perf_counter() - t0
         n_depth = W * per
         if self.pool is None:
-            self.pool = mp.get_context("fork").Pool(W)
-        res = self.pool.map(_dibr_chunk, [(self.wl, ch, dp) for ch, dp in zip(idx, depths)])
+            # spawn, not fork: the parent may hold a CUDA context, OpenMP pools and helper threads (fork-unsafe)
+            self.pool = mp.get_context("spawn").Pool(W)
+        res = self.pool.map_async(_dibr_chunk, [(self.wl, ch, dp, dict(COMMON)) for ch, dp in zip(idx, depths)]).get(timeout=600)
         t_dibr = max(r[0] for r in res)          # chunks run concurrently: the slowest one is the stage time
         n = sum(r[1] for r in res)
         # per-frame cost = depth (all threads, one frame at a time) + DIBR (W chunks in parallel)

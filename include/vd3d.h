@@ -214,6 +214,12 @@ int vd3d_color_grade(vd3d_ctx* ctx, const float* rgb, int h, int w, double satur
 /* cv2.resize(u8 plane [h,w], (ow,oh), interpolation=cv2.INTER_CUBIC): the resize the depth writer applies to the u8
  * depth (core/render_depth.py:1917, 193): float32 bicubic (A = -0.75), round half to even */
 int vd3d_resize_cubic_u8(vd3d_ctx* ctx, const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, int mem);
+/* the same on interleaved u8 [h,w,ch] (ch <= 4): run_esrgan's INTER_CUBIC chain on BGR frames
+ * (core/merged_pipeline.py:262-266) */
+int vd3d_resize_cubic(vd3d_ctx* ctx, const uint8_t* src, int h, int w, int ch, uint8_t* dst, int oh, int ow, int mem);
+/* cv2.addWeighted(a, alpha, b, beta, 0) on n u8 values: blend_images (core/merged_pipeline.py:233-238) */
+int vd3d_add_weighted(vd3d_ctx* ctx, const uint8_t* a, double alpha, const uint8_t* b, double beta, size_t n, uint8_t* dst,
+                      int mem);
 /* apply_sharpening (717-732) on u8 BGR [h,w,3] */
 int vd3d_sharpen(vd3d_ctx* ctx, const uint8_t* src, int h, int w, double factor, uint8_t* dst, int mem);
 /* heal_missing_pixels (431-459; the reference's "gradient-blend occlusion fill", defined but not called by
@@ -282,6 +288,14 @@ int vd3d_depth_infer_batch_device(vd3d_depth* e, int B, const uint8_t* const* fr
 /* frames per depth forward inside vd3d_render_clip_depth (1..4, default 4; env VD3D_DEPTH_BATCH) */
 int vd3d_set_depth_batch(vd3d_ctx* ctx, int frames);
 int vd3d_get_depth_batch(vd3d_ctx* ctx);
+/* ---- Real-ESRGAN upscale stage (core/merged_pipeline.py:221-267) --------------------------------
+ * The reference runs an ONNX export of xinntao/Real-ESRGAN's SRVGGNetCompact (realesr-general-x4v3: 32 body convs;
+ * realesr-animevideov3: 16) through ONNXRuntime.  vd3d_sr_create returns an engine container (weights by name through
+ * vd3d_depth_set_tensor: "sr.c{i}.w" f16 [Cout, 9*64], "sr.c{i}.b" f32, "sr.a{i}" f32 PReLU slopes; destroy with
+ * vd3d_depth_destroy).  vd3d_sr_forward: BGR u8 [h,w,3] -> BGR u8 [4h,4w,3] = preprocess_esr -> network (tcgen05
+ * implicit-GEMM convs, f16 activations, fp32 accumulate, fp32 last layer) -> PixelShuffle + input -> postprocess_esr. */
+int vd3d_sr_create(void* cuda_stream, vd3d_depth** out);
+int vd3d_sr_forward(vd3d_depth* e, const uint8_t* frame_bgr, int h, int w, int num_conv, uint8_t* out_bgr, int mem);
 /* copy an internal activation buffer to the host (parity triage: "x", "tap0.0".., "f0".., "fused3") */
 int vd3d_depth_get_buffer(vd3d_depth* e, const char* name, void* host_out, size_t bytes);
 /* unit-test hooks for the tensor-core kernels */

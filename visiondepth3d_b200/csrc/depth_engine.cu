@@ -910,6 +910,83 @@ int vd3d_depth_infer_batch(vd3d_depth* e, int B, const uint8_t* const* frames_bg
   return VD3D_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Real-ESRGAN upscale stage (core/merged_pipeline.py:240-267; the network is the ONNX export of xinntao/Real-ESRGAN's
+// SRVGGNetCompact: conv3x3(3->64)+PReLU, num_conv x [conv3x3(64->64)+PReLU], conv3x3(64->48), PixelShuffle(4), + nearest
+// x4 of the input).  Every conv is the tcgen05 implicit GEMM of the depth neck (f16 NHWC activations, fp32 accumulate);
+// the last one keeps fp32.  The engine object is the depth engine's container (named weights + buffers).
+int vd3d_sr_create(void* stream, vd3d_depth** out) {
+  if (!out) return VD3D_ERR_ARG;
+  *out = nullptr;
+  if (!load_encode()) return VD3D_ERR_CUDA;
+  vd3d_depth* e = new vd3d_depth();
+  memset(&e->cfg, 0, sizeof e->cfg);
+  e->stream = (cudaStream_t)stream;
+  *out = e;
+  return VD3D_OK;
+}
+
+// frame BGR u8 [h,w,3] -> BGR u8 [4h,4w,3] (preprocess_esr -> network -> postprocess_esr).  Weights: "sr.c{i}.w" f16
+// [Cout, 9*64] (tap-major, input channels padded to 64), "sr.c{i}.b" f32 [Cout], "sr.a{i}" f32 [64] (PReLU slopes),
+// i = 0 .. num_conv+1.
+int vd3d_sr_forward(vd3d_depth* e, const uint8_t* frame_bgr, int h, int w, int num_conv, uint8_t* out_bgr, int mem) {
+  if (!e || !frame_bgr || !out_bgr || h < 8 || w < 8 || num_conv < 1 || num_conv > 64) return VD3D_ERR_ARG;
+  cudaStream_t s = e->stream;
+  const size_t npix = (size_t)h * w;
+  void *fd = (void*)frame_bgr, *od = out_bgr, *x0, *x1, *cvo;
+  int r;
+  char nm[32];
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = get_buf(e, "sr.in", npix * 3, &fd)) || (r = get_buf(e, "sr.outu8", npix * 48, &od))) return r;
+    DCK(cudaMemcpyAsync(fd, frame_bgr, npix * 3, cudaMemcpyHostToDevice, s));
+  }
+  if ((r = get_buf(e, "sr.x0", npix * 64 * 2, &x0)) || (r = get_buf(e, "sr.x1", npix * 64 * 2, &x1)) ||
+      (r = get_buf(e, "sr.cv", npix * 48 * 4, &cvo)))
+    return r;
+  launch_sr_in((const uint8_t*)fd, (__half*)x0, (int)npix, s);
+  e->launches++;
+  __half *cur = (__half*)x0, *nxt = (__half*)x1;
+  for (int i = 0; i <= num_conv + 1; ++i) {
+    const bool last = (i == num_conv + 1);
+    const int cout = last ? 48 : 64;
+    const __half* wt;
+    const float *bias, *slope = nullptr;
+    snprintf(nm, sizeof nm, "sr.c%d.w", i);
+    if ((r = W(e, nm, &wt, (size_t)cout * 9 * 64))) return r;
+    snprintf(nm, sizeof nm, "sr.c%d.b", i);
+    if ((r = W(e, nm, &bias, cout))) return r;
+    if (!last) {
+      snprintf(nm, sizeof nm, "sr.a%d", i);
+      if ((r = W(e, nm, &slope, 64))) return r;
+    }
+    GemmArgs g = base_args(0, cout, 0, last ? EPI_F32 : EPI_F16);
+    g.bias = bias;
+    if (last) {
+      g.out_f32 = (float*)cvo;
+      g.ldc = 48;
+    } else {
+      g.out_f16 = nxt;
+      g.ldc = 64;
+      g.act = 3;
+      g.ls = slope;
+    }
+    if ((r = conv(e, cur, h, w, 64, wt, true, g, last ? 32 : 64))) return r;
+    if (!last) {
+      __half* t = cur;
+      cur = nxt;
+      nxt = t;
+    }
+  }
+  launch_sr_out((const float*)cvo, 48, (const uint8_t*)fd, (uint8_t*)od, h, w, s);
+  e->launches++;
+  DCK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) {
+    DCK(cudaMemcpyAsync(out_bgr, od, npix * 48, cudaMemcpyDeviceToHost, s));
+    DCK(cudaStreamSynchronize(s));
+  }
+  return VD3D_OK;
+}
+
 // frame (BGR u8 [h,w,3], DEVICE) -> processor -> forward -> bicubic back to (h,w) -> min-max u8 [h,w]
 // (hf pipeline + convert_depth_to_grayscale, core/render_depth.py:1113-1119,605-611,1907-1917).
 // Enqueues on the engine stream without synchronising; depth_f32_or_null receives the resized

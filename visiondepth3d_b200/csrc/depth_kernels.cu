@@ -398,6 +398,51 @@ void launch_upsample_ac(const __half* in, int H, int W, int C, __half* out, int 
   size_t total = (size_t)OH * OW * (C / 8);
   k_upsample_ac<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, H, W, C, out, OH, OW);
 }
+// ---------------------------------------------------------------------------
+// Real-ESRGAN stage (SRVGGNetCompact): input / output ends of the conv stack
+// preprocess_esr (core/merged_pipeline.py:221-225): BGR u8 -> RGB / 255, here as the first 3 of 64 f16 channels (NHWC)
+__global__ void __launch_bounds__(256) k_sr_in(const uint8_t* __restrict__ bgr, __half* __restrict__ x, int npix) {
+  int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= npix) return;
+  const uint8_t* q = bgr + (size_t)i * 3;
+  uint4 z = make_uint4(0, 0, 0, 0);
+  uint4* dst = (uint4*)(x + (size_t)i * 64);
+  __align__(16) __half h4[8];
+  h4[0] = __float2half_rn((float)q[2] / 255.0f);
+  h4[1] = __float2half_rn((float)q[1] / 255.0f);
+  h4[2] = __float2half_rn((float)q[0] / 255.0f);
+#pragma unroll
+  for (int k = 3; k < 8; ++k) h4[k] = __float2half_rn(0.f);
+  dst[0] = *(uint4*)h4;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) dst[k] = z;
+}
+// PixelShuffle(4) + nearest x4 of the input + postprocess_esr (227-231): out[c, 4y+i, 4x+j] = conv[c*16 + i*4 + j, y, x] +
+// in[c, y, x]; clip to [0,1], x255, truncate, RGB -> BGR.  One thread per output pixel.
+__global__ void __launch_bounds__(256) k_sr_out(const float* __restrict__ conv, int ldc, const uint8_t* __restrict__ bgr,
+                                                uint8_t* __restrict__ out, int h, int w) {
+  int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (X >= 4 * w || Y >= 4 * h) return;
+  const int y = Y >> 2, x = X >> 2, sub = (Y & 3) * 4 + (X & 3);
+  const float* cv = conv + ((size_t)y * w + x) * ldc + sub;
+  const uint8_t* q = bgr + ((size_t)y * w + x) * 3;
+  uint8_t* o = out + ((size_t)Y * 4 * w + X) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {  // c: 0 = R, 1 = G, 2 = B
+    float v = cv[c * 16] + ((float)q[2 - c] / 255.0f);
+    v = fminf(fmaxf(v, 0.f), 1.f) * 255.0f;
+    o[2 - c] = (uint8_t)(int)v;
+  }
+}
+void launch_sr_in(const uint8_t* bgr, __half* x, int npix, cudaStream_t s) {
+  k_sr_in<<<(npix + 255) / 256, 256, 0, s>>>(bgr, x, npix);
+}
+void launch_sr_out(const float* conv, int ldc, const uint8_t* bgr, uint8_t* out, int h, int w, cudaStream_t s) {
+  dim3 g((4 * w + 31) / 32, (4 * h + 7) / 8);
+  k_sr_out<<<g, 256, 0, s>>>(conv, ldc, bgr, out, h, w);
+}
+
 void launch_relu_f16(const __half* in, __half* out, size_t n, cudaStream_t s) {
   size_t n8 = n / 8;
   k_relu_f16<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(in, out, n8);

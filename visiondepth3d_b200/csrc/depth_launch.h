@@ -22,6 +22,9 @@ void launch_depth_post(const float* depth, int IH, int IW, float* up, int OH, in
                        int invert, cudaStream_t s);
 void launch_add_relu_f16(const __half* a, const __half* b, __half* sum, __half* sum_relu, size_t n, cudaStream_t s);
 void launch_relu_f16(const __half* in, __half* out, size_t n, cudaStream_t s);
+// Real-ESRGAN stage: BGR u8 -> 64-channel f16 NHWC (RGB/255 in channels 0..2); pixel-shuffle + base + clip + u8 BGR
+void launch_sr_in(const uint8_t* bgr, __half* x, int npix, cudaStream_t s);
+void launch_sr_out(const float* conv, int ldc, const uint8_t* bgr, uint8_t* out, int h, int w, cudaStream_t s);
 // fused attention: q,k [image][h][npad][64] (q pre-scaled), vT [image][h][64][npad] -> out [images * npad, dmodel]
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, int ntok, int dmodel,
                              __half* out, int heads, int images, int npad, cudaStream_t s);

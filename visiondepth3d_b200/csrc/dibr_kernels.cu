@@ -1005,28 +1005,45 @@ __device__ __forceinline__ CubicTap cubic_tap(int d, int ssize, int dsize) {
   for (int k = 0; k < 4; ++k) t.o[k] = min(max(sx - 1 + k, 0), ssize - 1);
   return t;
 }
-__global__ void __launch_bounds__(256) k_resize_cubic_u8(const uint8_t* __restrict__ src, int h, int w,
+__global__ void __launch_bounds__(256) k_resize_cubic_u8(const uint8_t* __restrict__ src, int h, int w, int ch,
                                                          uint8_t* __restrict__ dst, int oh, int ow) {
   int x = blockIdx.x * 32 + (threadIdx.x & 31);
   int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= ow || y >= oh) return;
   CubicTap tx = cubic_tap(x, w, ow), ty = cubic_tap(y, h, oh);
-  float col[4];
+  for (int c = 0; c < ch; ++c) {
+    float col[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {  // rows first: the value of column tx.o[k] at output row y
-    const int xc = tx.o[k];
-    float v = (float)src[(size_t)ty.o[0] * w + xc] * ty.c[0];
-    v = v + ((float)src[(size_t)ty.o[1] * w + xc] * ty.c[1]);
-    v = v + ((float)src[(size_t)ty.o[2] * w + xc] * ty.c[2]);
-    v = v + ((float)src[(size_t)ty.o[3] * w + xc] * ty.c[3]);
-    col[k] = v;
+    for (int k = 0; k < 4; ++k) {  // rows first: the value of column tx.o[k] at output row y
+      const int xc = tx.o[k];
+      float v = (float)src[((size_t)ty.o[0] * w + xc) * ch + c] * ty.c[0];
+      v = v + ((float)src[((size_t)ty.o[1] * w + xc) * ch + c] * ty.c[1]);
+      v = v + ((float)src[((size_t)ty.o[2] * w + xc) * ch + c] * ty.c[2]);
+      v = v + ((float)src[((size_t)ty.o[3] * w + xc) * ch + c] * ty.c[3]);
+      col[k] = v;
+    }
+    float r = (((col[0] * tx.c[0]) + (col[1] * tx.c[1])) + (col[2] * tx.c[2])) + (col[3] * tx.c[3]);
+    dst[((size_t)y * ow + x) * ch + c] = rhe_u8(r);
   }
-  float r = (((col[0] * tx.c[0]) + (col[1] * tx.c[1])) + (col[2] * tx.c[2])) + (col[3] * tx.c[3]);
-  dst[(size_t)y * ow + x] = rhe_u8(r);
 }
-void launch_resize_cubic_u8(const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, cudaStream_t s) {
+void launch_resize_cubic_u8(const uint8_t* src, int h, int w, int ch, uint8_t* dst, int oh, int ow, cudaStream_t s) {
   dim3 g((ow + 31) / 32, (oh + 7) / 8);
-  k_resize_cubic_u8<<<g, 256, 0, s>>>(src, h, w, dst, oh, ow);
+  k_resize_cubic_u8<<<g, 256, 0, s>>>(src, h, w, ch, dst, oh, ow);
+}
+
+// cv2.addWeighted(a, alpha, b, beta, 0) on u8 (blend_images, core/merged_pipeline.py:233-238): cv2 4.13 evaluates
+// fma(a, alpha, fl(b * beta)) in float32, rounds half to even, saturates (oracle/sr.py, pinned exact against cv2)
+__global__ void __launch_bounds__(256) k_add_weighted(const uint8_t* __restrict__ a, float alpha,
+                                                      const uint8_t* __restrict__ b, float beta, uint8_t* __restrict__ dst,
+                                                      size_t n) {
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float t = (float)b[i] * beta;
+  dst[i] = rhe_u8(__fmaf_rn((float)a[i], alpha, t));
+}
+void launch_add_weighted(const uint8_t* a, float alpha, const uint8_t* b, float beta, uint8_t* dst, size_t n,
+                         cudaStream_t s) {
+  k_add_weighted<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, alpha, b, beta, dst, n);
 }
 
 // apply_color_grade (core/render_3d.py:734-767) on planar f32 RGB

@@ -126,7 +126,9 @@ void launch_compose(const ComposeArgs& a, cudaStream_t s);
 void launch_dof(const DofArgs& a, int eyes, cudaStream_t s);
 void launch_post(const PostArgs& a, cudaStream_t s);
 void launch_grade_f32(const float* src, float* dst, int n, float sat, float con, float bri, cudaStream_t s);
-void launch_resize_cubic_u8(const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, cudaStream_t s);
+void launch_resize_cubic_u8(const uint8_t* src, int h, int w, int ch, uint8_t* dst, int oh, int ow, cudaStream_t s);
+void launch_add_weighted(const uint8_t* a, float alpha, const uint8_t* b, float beta, uint8_t* dst, size_t n,
+                         cudaStream_t s);
 void launch_heal(const float* warped, const float* orig, const float* edge, float* out, int H, int W, float hs,
                  cudaStream_t s);
 

@@ -37,7 +37,7 @@ struct GemmArgs {
   int M, N, K;            // logical sizes (K = total reduction length)
   int nt, mt, nz;         // tile counts along N, M and batch (filled by launch_gemm)
   int epi;
-  int act;                // 0 none, 1 GELU(erf), 2 ReLU
+  int act;                // 0 none, 1 GELU(erf), 2 ReLU, 3 PReLU (slopes in ls)
   // conv mode (implicit GEMM over a (C, W, H) activation map)
   int conv;               // 0 = plain GEMM, 1 = 3x3 pad 1, 2 = 1x1 over the same map
   int cin;                // channels per tap (multiple of 64)
@@ -371,6 +371,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmArgs& g, const uin
       } else if (g.act == 2) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.f);
+      } else if (g.act == 3) {  // PReLU, per-channel slopes in g.ls (SRVGGNetCompact)
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) a[j] = a[j] > 0.f ? a[j] : a[j] * __ldg(g.ls + n0 + j);
       }
       if (vec) {
         uint32_t u[8];

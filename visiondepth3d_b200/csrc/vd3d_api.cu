@@ -1912,26 +1912,52 @@ int vd3d_check_config(vd3d_ctx* ctx, int src_h, int src_w, const vd3d_render_par
   return VD3D_OK;
 }
 
-// cv2.resize(u8 [h,w], (ow,oh), INTER_CUBIC): the resize of the depth writer (core/render_depth.py:1917, 193)
-int vd3d_resize_cubic_u8(vd3d_ctx* ctx, const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, int mem) {
-  if (!ctx || !src || !dst || h < 1 || w < 1 || oh < 1 || ow < 1) return fail(ctx, VD3D_ERR_ARG, "bad argument");
+// cv2.resize(u8 [h,w,ch], (ow,oh), INTER_CUBIC): the resize of the depth writer (core/render_depth.py:1917, 193; ch = 1)
+// and of run_esrgan's resize chain (core/merged_pipeline.py:262-266; ch = 3)
+int vd3d_resize_cubic(vd3d_ctx* ctx, const uint8_t* src, int h, int w, int ch, uint8_t* dst, int oh, int ow, int mem) {
+  if (!ctx || !src || !dst || h < 1 || w < 1 || oh < 1 || ow < 1 || ch < 1 || ch > 4) return fail(ctx, VD3D_ERR_ARG, "bad argument");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   const void* s_d;
   int r;
-  if ((r = copy_in(ctx, ctx->eyeL, src, (size_t)h * w, mem, s, &s_d))) return r;
+  if ((r = copy_in(ctx, ctx->eyeL, src, (size_t)h * w * ch, mem, s, &s_d))) return r;
   uint8_t* o_d = dst;
   if (mem == VD3D_MEM_HOST) {
-    if ((r = ensure(ctx, ctx->out_dev[0], (size_t)oh * ow))) return r;
+    if ((r = ensure(ctx, ctx->out_dev[0], (size_t)oh * ow * ch))) return r;
     o_d = (uint8_t*)ctx->out_dev[0].p;
   }
   if (h == oh && w == ow)
-    CK(cudaMemcpyAsync(o_d, s_d, (size_t)h * w, cudaMemcpyDeviceToDevice, s));  // cv2.resize copies on equal sizes
+    CK(cudaMemcpyAsync(o_d, s_d, (size_t)h * w * ch, cudaMemcpyDeviceToDevice, s));  // cv2.resize copies on equal sizes
   else
-    launch_resize_cubic_u8((const uint8_t*)s_d, h, w, o_d, oh, ow, s);
+    launch_resize_cubic_u8((const uint8_t*)s_d, h, w, ch, o_d, oh, ow, s);
   ctx->launches += 1;
   CK(cudaGetLastError());
-  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(dst, o_d, (size_t)oh * ow, cudaMemcpyDeviceToHost, s));
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(dst, o_d, (size_t)oh * ow * ch, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return VD3D_OK;
+}
+int vd3d_resize_cubic_u8(vd3d_ctx* ctx, const uint8_t* src, int h, int w, uint8_t* dst, int oh, int ow, int mem) {
+  return vd3d_resize_cubic(ctx, src, h, w, 1, dst, oh, ow, mem);
+}
+
+// cv2.addWeighted(a, alpha, b, 1 - alpha... any beta, 0) on n bytes (blend_images, core/merged_pipeline.py:233-238)
+int vd3d_add_weighted(vd3d_ctx* ctx, const uint8_t* a, double alpha, const uint8_t* b, double beta, size_t n, uint8_t* dst,
+                      int mem) {
+  if (!ctx || !a || !b || !dst || !n) return fail(ctx, VD3D_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const void *a_d, *b_d;
+  int r;
+  if ((r = copy_in(ctx, ctx->eyeL, a, n, mem, s, &a_d)) || (r = copy_in(ctx, ctx->eyeR, b, n, mem, s, &b_d))) return r;
+  uint8_t* o_d = dst;
+  if (mem == VD3D_MEM_HOST) {
+    if ((r = ensure(ctx, ctx->out_dev[0], n))) return r;
+    o_d = (uint8_t*)ctx->out_dev[0].p;
+  }
+  launch_add_weighted((const uint8_t*)a_d, (float)alpha, (const uint8_t*)b_d, (float)beta, o_d, n, s);
+  ctx->launches += 1;
+  CK(cudaGetLastError());
+  if (mem == VD3D_MEM_HOST) CK(cudaMemcpyAsync(dst, o_d, n, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   return VD3D_OK;
 }
