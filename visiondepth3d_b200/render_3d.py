@@ -504,12 +504,12 @@ def render_sbs_3d(
 
         # the colour and the depth stream are decoded (cv2 releases the GIL) and copied into the pinned ring by one
         # worker thread each; `reader` sequences them exactly like the reference's loop consumes pairs
-        jobs = (queue.Queue(), queue.Queue())
-        done = (queue.Queue(), queue.Queue())
+        q_jobs = (queue.Queue(), queue.Queue())
+        q_done = (queue.Queue(), queue.Queue())
 
         def stream_worker(which, src):
             while True:
-                k = jobs[which].get()
+                k = q_jobs[which].get()
                 if k is None:
                     return
                 try:
@@ -519,12 +519,15 @@ def render_sbs_3d(
                 except Exception as e:
                     errors.append(e)
                     ok = False
-                done[which].put(bool(ok))
+                q_done[which].put(bool(ok))
 
         def read_pair(k):
-            jobs[0].put(k)
-            jobs[1].put(k)
-            ok_a, ok_b = done[0].get(), done[1].get()
+            q_jobs[0].put(k)
+            q_jobs[1].put(k)
+            try:   # a decoder that stalls for a minute is treated like a failed read (the reference would block forever)
+                ok_a, ok_b = q_done[0].get(timeout=60), q_done[1].get(timeout=60)
+            except queue.Empty:
+                return False
             return ok_a and ok_b
 
         def reader():
@@ -546,8 +549,8 @@ def render_sbs_3d(
                             break
             except Exception as e:  # surfaced by the main thread
                 errors.append(e)
-            jobs[0].put(None)
-            jobs[1].put(None)
+            q_jobs[0].put(None)
+            q_jobs[1].put(None)
             ready.put(None)
 
         def writer():
@@ -571,11 +574,11 @@ def render_sbs_3d(
         for t in threads:
             t.start()
         th_w.start()
-        done, t0, eof = 0, time.time(), False
+        n_done, t0, eof = 0, time.time(), False
         while not eof and not errors:
             slots = []
             while len(slots) < _BATCH:
-                k = ready.get()
+                k = ready.get(timeout=180)
                 if k is None:
                     eof = True
                     break
@@ -591,15 +594,15 @@ def render_sbs_3d(
             for k in slots:
                 free_in.put(k)
             to_write.put((half, n))
-            done += n
-            frac = min(done / max(win.budget, 1), 1.0) * 100.0
+            n_done += n
+            frac = min(n_done / max(win.budget, 1), 1.0) * 100.0
             if progress:
                 progress["value"] = frac
                 progress.update()
             if progress_label:
                 el = time.time() - t0
-                rate = done / max(el, 1e-9)
-                eta = (win.budget - done) / rate if rate > 0 else 0
+                rate = n_done / max(el, 1e-9)
+                eta = (win.budget - n_done) / rate if rate > 0 else 0
                 progress_label.config(text=f"{frac:.2f}% | FPS: {rate:.2f} | Elapsed: "
                                            f"{time.strftime('%H:%M:%S', time.gmtime(el))} | ETA: "
                                            f"{time.strftime('%H:%M:%S', time.gmtime(max(eta, 0)))}")
