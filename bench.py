@@ -52,7 +52,10 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused render kernel from `ncu --set full`
 # (profiles/r02_ncu_dibr.md); None until captured for that configuration
-NCU_RENDER_TRAFFIC = {"4k": None, "1080p": None}
+NCU_RENDER_TRAFFIC = {"4k": 115_862_272, "1080p": 49_949_440}
+# smsp__issue_active.avg.pct_of_peak_sustained_active of the same launches: the DIBR kernels are issue bound, not HBM
+# bound, so this is the roofline fraction that describes them
+NCU_RENDER_ISSUE_ACTIVE = {"4k": 70.6, "1080p": 62.9}
 # same for one fc1 launch of k_umma_gemm<128,3> (DA-V2-Base: M=2443, N=3072, K=768): 8.56 MB read + 0.01 MB written
 NCU_GEMM_FC1_TRAFFIC = {"vitb": 8571136, "vitl": None, "vits": None}
 COMMON = dict(fg=4.5, mg=-1.5, bg=-6.0, sharp=0.2, feather=10.0, ksize=9, tracking=True, floating=True,
@@ -584,6 +587,9 @@ class GpuArm:
             "roofline_dibr_render": {"bound": "hbm", "kernel": "k_render (warp edges + box feather + compose + sharpen + fit + pack)",
                                      "achieved": rend_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": rend_gbs / hbm_peak,
                                      "traffic": NCU_RENDER_TRAFFIC.get(self.key),
+                                     "issue_active_pct": NCU_RENDER_ISSUE_ACTIVE.get(self.key),
+                                     "note": "instruction-issue bound (~1000 thread-instructions per eye pixel against a machine "
+                                             "balance of 5.5 instructions per byte): frac vs HBM is not the binding roofline",
                                      "peak_source": which, "algorithmic_bytes_per_launch": rend_bytes, "avg_launch_ms": rend_ms},
             "roofline_dibr_stage": {"bound": "hbm", "what": "whole DIBR frame (ingest..pack), serial eager launches",
                                     "achieved": stage_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,

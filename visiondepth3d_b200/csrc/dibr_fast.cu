@@ -8,7 +8,7 @@
 //             reference computed redundantly by thread 0 of every CTA from the same global histograms (identical
 //             results, no extra barrier); CTA 0 publishes DevState / FrameScalars at the end.  Pass 1 of every select
 //             rides on the phase that PRODUCES the plane, so a select costs two extra reads (from L2), not three.
-//   k_shift   (dibr_kernels.cu, fast-math instantiation) shift map + edge-mask suppression.
+//   k_shift_fast  shift map + edge-mask suppression: 4 pixels per thread, ex2 / rcp / sqrt approximations, separable pool.
 //   k_render  per 64x32 tile: warped depth of both eyes (tile + halo) -> gradient edge mask -> separable KxK box
 //             sum in shared memory -> 4-tap RGB gather, feather blend, truncation, colour grade -> u8 eye tile in
 //             shared memory -> [floating-window bars, 3x3 sharpen, INTER_AREA 1:1 / 2:1 eye fit, SBS pack] -> output.
@@ -265,21 +265,34 @@ __device__ void after_pass3(StatsSmem& S, SelState& q, const JobMem& jm) {
   }
 }
 
-__device__ __forceinline__ void pass2_add(const SelState& q, const JobMem& jm, bool on, uint32_t key) {
-  int g = -1;
-  const uint32_t top = key >> 18;
-  for (int i = 0; i < q.ng1; ++i)
-    if (top == q.gp1[i]) g = i;
-  on = on && g >= 0;
-  hist_add(jm.hist2, on, (uint32_t)(g < 0 ? 0 : g) * 4096u + ((key >> 6) & 4095u));
+// bins selected so far, held in registers for the streaming passes
+struct Grp {
+  int n;
+  uint32_t a[4], b[4];
+};
+template <int PASS>
+__device__ __forceinline__ Grp load_groups(const SelState& q) {
+  Grp g;
+  g.n = PASS == 2 ? q.ng1 : q.ng2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    g.a[i] = PASS == 2 ? q.gp1[i] : q.gq1[i];
+    g.b[i] = PASS == 2 ? 0u : q.gq2[i];
+  }
+  return g;
 }
-__device__ __forceinline__ void pass3_add(const SelState& q, const JobMem& jm, bool on, uint32_t key) {
+template <int PASS>
+__device__ __forceinline__ void pass_add(const Grp& gr, const JobMem& jm, bool on, uint32_t key) {
   int g = -1;
   const uint32_t top = key >> 18, mid = (key >> 6) & 4095u;
-  for (int i = 0; i < q.ng2; ++i)
-    if (top == q.gq1[i] && mid == q.gq2[i]) g = i;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < gr.n && top == gr.a[i] && (PASS == 2 || mid == gr.b[i])) g = i;
   on = on && g >= 0;
-  hist_add(jm.hist3, on, (uint32_t)(g < 0 ? 0 : g) * 64u + (key & 63u));
+  if (PASS == 2)
+    hist_add(jm.hist2, on, (uint32_t)(g < 0 ? 0 : g) * 4096u + mid);
+  else
+    hist_add(jm.hist3, on, (uint32_t)(g < 0 ? 0 : g) * 64u + (key & 63u));
 }
 
 __device__ __forceinline__ bool in_region(const int* rg, int y, int x) {  // rg = {x0, x1, y0, y1}
@@ -296,6 +309,10 @@ __device__ __forceinline__ int bin64(float v) {
 template <int PASS>
 __device__ void select_pass(const float* plane, int W, int H, const SelState* qa, const JobMem* ja, const SelState* qb,
                             const JobMem* jb, const int* crop) {
+  Grp ga, gb;
+  ga.n = gb.n = 0;
+  if (qa) ga = load_groups<PASS>(*qa);
+  if (qb) gb = load_groups<PASS>(*qb);
   if (qa) {
     const int n = W * H;
     const FastDiv fdw = fast_div((uint32_t)W, (uint32_t)n);
@@ -311,18 +328,12 @@ __device__ void select_pass(const float* plane, int W, int H, const SelState* qa
         int idx = base + u * NT + threadIdx.x;
         bool inb = idx < n;
         uint32_t key = key_of(v[u]);
-        if (PASS == 2)
-          pass2_add(*qa, *ja, inb, key);
-        else
-          pass3_add(*qa, *ja, inb, key);
+        pass_add<PASS>(ga, *ja, inb, key);
         if (qb) {
           int y, x;
           divmod(fdw, idx, y, x);
           bool on = inb && in_region(crop, y, x) && subj_keep(v[u]);
-          if (PASS == 2)
-            pass2_add(*qb, *jb, on, key);
-          else
-            pass3_add(*qb, *jb, on, key);
+          pass_add<PASS>(gb, *jb, on, key);
         }
       }
     }
@@ -344,10 +355,7 @@ __device__ void select_pass(const float* plane, int W, int H, const SelState* qa
         int idx = base + u * NT + threadIdx.x;
         bool on = idx < n && subj_keep(v[u]);
         uint32_t key = key_of(v[u]);
-        if (PASS == 2)
-          pass2_add(*qb, *jb, on, key);
-        else
-          pass3_add(*qb, *jb, on, key);
+        pass_add<PASS>(gb, *jb, on, key);
       }
     }
   }
@@ -690,6 +698,89 @@ __global__ void __launch_bounds__(NT, 1) k_stats(StatsArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_shift_fast: shift map + suppress_artifacts_with_edge_mask (core/render_3d.py:198-216, 620-680), fast arithmetic.
+// 64 x 16 pixels per CTA (4 per thread), sigmoid through ex2 / rcp approximations, the 5 x 5 pool as row sums then
+// column sums.  ~1/3 of the instructions of the one-pixel-per-thread exact kernel (which it replaced after ncu showed
+// that kernel 86-90 % issue-bound at 385 thread-instructions per pixel, profiles/r02_ncu_dibr.md).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SHX = 64, SHY = 16;
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__global__ void __launch_bounds__(256) k_shift_fast(const float* __restrict__ d, float* __restrict__ shift, int H, int W,
+                                                    const FrameScalars* __restrict__ fs, int edge_mask, float feather) {
+  __shared__ float sd[SHY + 6][SHX + 6 + 2];  // d over [by-3, by+SHY+3) x [bx-3, bx+SHX+3)
+  __shared__ float sm[SHY + 4][SHX + 4];      // 1 - sigmoid over [by-2, by+SHY+2) x [bx-2, bx+SHX+2)
+  __shared__ float hs[SHY + 4][SHX];          // row sums of 5
+  const int bx = blockIdx.x * SHX, by = blockIdx.y * SHY;
+  const int tid = threadIdx.x;
+  if (edge_mask) {
+    for (int i = tid; i < (SHY + 6) * (SHX + 6); i += 256) {
+      int ty = i / (SHX + 6), tx = i - ty * (SHX + 6);
+      int gy = by - 3 + ty, gx = bx - 3 + tx;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(d + (size_t)gy * W + gx);
+      sd[ty][tx] = v;
+    }
+    __syncthreads();
+    const float f5 = feather * 5.0f;
+    for (int i = tid; i < (SHY + 4) * (SHX + 4); i += 256) {
+      int ty = i / (SHX + 4), tx = i - ty * (SHX + 4);
+      int gy = by - 2 + ty, gx = bx - 2 + tx;
+      float m = 0.f;  // zero padding of avg_pool2d
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        float c = sd[ty + 1][tx + 1];
+        float dx = (gx > 0) ? (c - sd[ty + 1][tx]) : 0.f;
+        float dy = (gy > 0) ? (c - sd[ty][tx + 1]) : 0.f;
+        float g = sqrt_approx((dx * dx) + (dy * dy));
+        float t = __expf(-((g - 0.02f) * f5));   // 1 - 1/(1+t) = t/(1+t)
+        m = __fdividef(t, 1.0f + t);
+        if (!(t < 3.0e38f)) m = 1.0f;             // exp overflow: sigmoid -> 0, mask -> 1
+      }
+      sm[ty][tx] = m;
+    }
+    __syncthreads();
+    for (int i = tid; i < (SHY + 4) * SHX; i += 256) {
+      int r = i / SHX, x = i - r * SHX;
+      const float* row = &sm[r][x];
+      hs[r][x] = (((row[0] + row[1]) + row[2]) + row[3]) + row[4];
+    }
+    __syncthreads();
+  }
+  const float c_fg = fs->c_fg * fs->c_fgm, c_mg = fs->c_mg, c_bg = fs->c_bg * fs->c_bgm;
+  const float c_mid = fs->c_mid, c_pb = fs->c_pb, c_half = fs->c_half, c_zpo = fs->c_zpo, c_max = fs->c_max;
+  const float c_conv = fs->c_conv, c_m1 = fs->c_m1, c_m2 = fs->c_m2;
+  const int use_zpo = fs->use_zpo, use_conv = fs->use_conv;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = tid + k * 256;
+    const int ly = i / SHX, lx = i - ly * SHX;
+    const int x = bx + lx, y = by + ly;
+    if (x >= W || y >= H) continue;
+    float v = edge_mask ? sd[ly + 3][lx + 3] : __ldg(d + (size_t)y * W + x);
+    float o1 = 1.0f - v;
+    float fgw = clamp01(o1 * sqrt_approx(o1));
+    float mgw = clamp01(1.0f - (fabsf(v - c_mid) * 3.0f));
+    float bgw = clamp01(v);
+    float raw = ((fgw * c_fg) + (mgw * c_mg)) + (bgw * c_bg);
+    float total = (raw * c_pb) / c_half;
+    if (use_zpo) total = total - c_zpo;
+    total = fminf(fmaxf(total, -c_max), c_max);
+    if (use_conv) total = total - c_conv;
+    float fin = total;
+    if (edge_mask) {
+      float acc = (((hs[ly][lx] + hs[ly + 1][lx]) + hs[ly + 2][lx]) + hs[ly + 3][lx]) + hs[ly + 4][lx];
+      float sup = total * (acc * (1.0f / 25.0f));
+      fin = (c_m1 * total) + (c_m2 * sup);
+    }
+    shift[(size_t)y * W + x] = fin;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // k_render
 // ---------------------------------------------------------------------------------------------------------------
@@ -1014,6 +1105,12 @@ cudaError_t render_src(const RenderArgs& a, cudaStream_t s) {
 }
 
 }  // namespace
+
+void launch_shift_fast(const float* d, float* shift, int H, int W, const FrameScalars* fs, int edge_mask, float feather,
+                       cudaStream_t s) {
+  dim3 g((W + SHX - 1) / SHX, (H + SHY - 1) / SHY);
+  k_shift_fast<<<g, 256, 0, s>>>(d, shift, H, W, fs, edge_mask, feather);
+}
 
 bool render_supports(int feather, int k) { return !feather || (k >= 1 && k <= 9 && (k & 1)); }
 

@@ -1122,10 +1122,6 @@ void launch_shift(const float* d, float* shift, int H, int W, const FrameScalars
                   cudaStream_t s) {
   k_shift<false><<<grid2d(W, H), 256, 0, s>>>(d, shift, H, W, fs, edge_mask, feather);
 }
-void launch_shift_fast(const float* d, float* shift, int H, int W, const FrameScalars* fs, int edge_mask, float feather,
-                       cudaStream_t s) {
-  k_shift<true><<<grid2d(W, H), 256, 0, s>>>(d, shift, H, W, fs, edge_mask, feather);
-}
 void launch_warp_edges(const float* d, const float* shift, float2* e2, int H, int W, const float* xs,
                        const float* ys, float feather, cudaStream_t s) {
   k_warp_edges<<<grid2d(W, H), 256, 0, s>>>(d, shift, e2, H, W, xs, ys, feather);
