@@ -46,7 +46,7 @@ def test_run_esrgan_chain_matches_oracle():
     fr, _ = synth_frame(4, 256, 144, "natural")
     assert MP.run_esrgan(fr) is not fr
     for kw in (dict(), dict(blend_mode="LOW"), dict(input_res_pct=50, blend_mode="MEDIUM"),
-               dict(target_size=(384, 216)), dict(input_res_pct=50, target_size=(512, 288), blend_mode="HIGH")):
+               dict(target_size=(384, 216)), dict(input_res_pct=50, target_size=(256, 144), blend_mode="HIGH")):   # blending needs equal sizes (cv2.addWeighted raises otherwise)
         out = MP.run_esrgan(fr, **kw)
         ref = S.run_esrgan(sd, fr, kw.get("blend_mode", "OFF"), kw.get("input_res_pct", 100), kw.get("target_size"))
         assert out.shape == ref.shape

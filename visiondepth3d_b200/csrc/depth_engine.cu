@@ -55,6 +55,10 @@ struct vd3d_depth {
   int ph = 0, pw = 0, ntok = 0, npad = 0;
   bool planned = false;
   bool flash = true;  // fused attention kernel (VD3D_FLASH=0 selects the 3-kernel path)
+  // the per-image neck / head tails of a batch run on side streams (forked after the transformer, joined at the end)
+  cudaStream_t cur = nullptr;          // stream the helpers launch on (null: `stream`)
+  cudaStream_t aux[8] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
   bool owns_weights = true;  // clones share the weight tensors of their parent
   uint64_t weights_version = 0;  // bumped whenever a weight tensor moves (clones / captured graphs hold raw pointers)
   // optional device timing of one GEMM class (the fc1 launches) for the roofline report
@@ -89,7 +93,7 @@ int get_buf(vd3d_depth* e, const std::string& name, size_t bytes, void** out, bo
     t.bytes = bytes;
     zero = true;
   }
-  if (zero) DCK(cudaMemsetAsync(t.p, 0, t.bytes, e->stream));
+  if (zero) DCK(cudaMemsetAsync(t.p, 0, t.bytes, e->cur ? e->cur : e->stream));
   *out = t.p;
   return VD3D_OK;
 }
@@ -173,7 +177,7 @@ int gemm(vd3d_depth* e, const __half* A, int lda, const __half* B, int ldb, Gemm
   int r;
   if ((r = make_map(e, &ma, A, g.K, g.M, 1, lda, (uint64_t)lda * g.M, 128, 1))) return r;
   if ((r = make_map(e, &mb, B, g.K, g.N, 1, ldb, (uint64_t)ldb * g.N, box_rows(bn), 1))) return r;
-  cudaError_t ce = launch_gemm(bn, ma, mb, g, (g.M + 127) / 128, 1, e->stream);
+  cudaError_t ce = launch_gemm(bn, ma, mb, g, (g.M + 127) / 128, 1, e->cur ? e->cur : e->stream);
   if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(ce));
   e->launches++;
   return VD3D_OK;
@@ -186,7 +190,7 @@ int gemm_batched(vd3d_depth* e, const __half* A, int lda, uint64_t sa, const __h
   int r;
   if ((r = make_map(e, &ma, A, g.K, g.M, batch, lda, sa, 128, 1))) return r;
   if ((r = make_map(e, &mb, B, g.K, g.N, batch, ldb, sb, box_rows(bn), 1))) return r;
-  cudaError_t ce = launch_gemm(bn, ma, mb, g, (g.M + 127) / 128, batch, e->stream);
+  cudaError_t ce = launch_gemm(bn, ma, mb, g, (g.M + 127) / 128, batch, e->cur ? e->cur : e->stream);
   if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(ce));
   e->launches++;
   return VD3D_OK;
@@ -224,7 +228,7 @@ int conv(vd3d_depth* e, const __half* in, int H, int W, int cin, const __half* w
   if ((r = make_map(e, &ma, in, cin, W, H, cin, (uint64_t)cin * W, tw, th))) return r;
   if ((r = make_map(e, &mb, wt, g.K, g.N, 1, g.K, (uint64_t)g.K * g.N, box_rows(bn), 1))) return r;
   int m_tiles = ((W + tw - 1) / tw) * ((H + th - 1) / th);
-  cudaError_t ce = launch_gemm(bn, ma, mb, g, m_tiles, 1, e->stream);
+  cudaError_t ce = launch_gemm(bn, ma, mb, g, m_tiles, 1, e->cur ? e->cur : e->stream);
   if (ce != cudaSuccess) return dfail(e, VD3D_ERR_CUDA, std::string("conv launch: ") + cudaGetErrorString(ce));
   e->launches++;
   return VD3D_OK;
@@ -308,6 +312,14 @@ int vd3d_depth_clone(vd3d_depth* src, void* stream, vd3d_depth** out) {
 void vd3d_depth_destroy(vd3d_depth* e) {
   if (!e) return;
   cudaStreamSynchronize(e->stream);
+  for (int i = 0; i < 8; ++i) {
+    if (e->aux[i]) {
+      cudaStreamSynchronize(e->aux[i]);
+      cudaStreamDestroy(e->aux[i]);
+    }
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   for (auto& kv : e->w)
     if (e->owns_weights && kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : e->buf)
@@ -457,6 +469,7 @@ constexpr int kMaxBatch = 8;
 // px_dev / depth_dev: DEVICE pointers, f32 [3, image_h, image_w] in, f32 [image_h, image_w] out.
 int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const* depth_dev) {
   if (B < 1 || B > kMaxBatch) return dfail(e, VD3D_ERR_ARG, "batch must be in [1, 8]");
+  e->cur = nullptr;  // (an earlier call may have failed inside its forked section)
   const vd3d_depth_config& c = e->cfg;
   cudaStream_t s = e->stream;
   const int D = c.hidden, L = c.layers, Hh = c.heads, F = c.fusion;
@@ -620,7 +633,28 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
   }
   if (tap_idx != 4) return dfail(e, VD3D_ERR_ARG, "taps must be increasing layer indices <= layers");
 
-  for (int b = 0; b < B; ++b) {  // neck + head, one image at a time (activation buffers are reused, stream-ordered)
+  // neck + head: independent per image.  With more than one image each tail runs on its own side stream (forked here,
+  // joined below) with its own activation buffers, so that the many small launches of the tails (grids of 5..77 CTAs on
+  // the coarse maps) overlap each other instead of leaving most SMs idle; captured into the same CUDA graph.
+  const bool fork = B > 1;
+  cudaStream_t s_main = s;
+  if (fork) {
+    if (!e->ev_fork) DCK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    DCK(cudaEventRecord(e->ev_fork, s_main));
+  }
+  for (int b = 0; b < B; ++b) {
+  if (fork) {
+    if (!e->aux[b]) DCK(cudaStreamCreateWithFlags(&e->aux[b], cudaStreamNonBlocking));
+    if (!e->ev_join[b]) DCK(cudaEventCreateWithFlags(&e->ev_join[b], cudaEventDisableTiming));
+    s = e->aux[b];
+    e->cur = s;
+    DCK(cudaStreamWaitEvent(s, e->ev_fork, 0));
+  }
+  auto bname = [&](const char* base) {  // per-image activation buffers when the tails run concurrently
+    std::string n(base);
+    if (fork) n += "#" + std::to_string(b);
+    return n;
+  };
   void* depth_d = depth_dev[b];
   // ---- neck: reassemble + 3x3 conv to the fusion width ----
   int fh[4], fw[4];
@@ -636,7 +670,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
     snprintf(nm, sizeof nm, "tap%d.%d", i, b);
     void *tp = e->buf[nm].p, *rp, *rs = nullptr;
     snprintf(nm, sizeof nm, "r%d.p", i);
-    if ((r = get_buf(e, nm, (size_t)round_up(NPATCH, 128) * CP * 2, &rp))) return r;
+    if ((r = get_buf(e, bname(nm), (size_t)round_up(NPATCH, 128) * CP * 2, &rp))) return r;
     {
       GemmArgs g = base_args(NPATCH, CP, D, EPI_F16);
       g.out_f16 = (__half*)rp;
@@ -655,7 +689,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
       fh[i] = ph * kk;
       fw[i] = pw * kk;
       snprintf(nm, sizeof nm, "r%d.s", i);
-      if ((r = get_buf(e, nm, (size_t)fh[i] * fw[i] * CP * 2, &rs))) return r;
+      if ((r = get_buf(e, bname(nm), (size_t)fh[i] * fw[i] * CP * 2, &rs))) return r;
       GemmArgs g = base_args(NPATCH, kk * kk * CP, CP, EPI_CONVT);
       g.out_f16 = (__half*)rs;
       g.bias = ub;
@@ -674,10 +708,10 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
       fh[i] = (ph - 1) / 2 + 1;
       fw[i] = (pw - 1) / 2 + 1;
       void* col;
-      if ((r = get_buf(e, "r3.col", (size_t)round_up(fh[i] * fw[i], 128) * 9 * CP * 2, &col))) return r;
+      if ((r = get_buf(e, bname("r3.col"), (size_t)round_up(fh[i] * fw[i], 128) * 9 * CP * 2, &col))) return r;
       launch_im2col_s2((const __half*)rp, ph, pw, CP, CP, (__half*)col, fh[i], fw[i], s);
       e->launches++;
-      if ((r = get_buf(e, "r3.s", (size_t)round_up(fh[i] * fw[i], 128) * CP * 2, &rs))) return r;
+      if ((r = get_buf(e, bname("r3.s"), (size_t)round_up(fh[i] * fw[i], 128) * CP * 2, &rs))) return r;
       GemmArgs g = base_args(fh[i] * fw[i], CP, 9 * CP, EPI_F16);
       g.out_f16 = (__half*)rs;
       g.bias = db;
@@ -687,7 +721,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
     snprintf(nm, sizeof nm, "n%d.conv.w", i);
     if ((r = W(e, nm, &cw, (size_t)F * 9 * CP))) return r;
     snprintf(nm, sizeof nm, "f%d", i);
-    if ((r = get_buf(e, nm, (size_t)fh[i] * fw[i] * F * 2, &feat[i]))) return r;
+    if ((r = get_buf(e, bname(nm), (size_t)fh[i] * fw[i] * F * 2, &feat[i]))) return r;
     GemmArgs g = base_args(0, F, 0, EPI_F16);
     g.out_f16 = (__half*)feat[i];
     g.ldc = F;
@@ -702,9 +736,9 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
     const int Hc = fh[fi], Wc = fw[fi];
     const size_t n = (size_t)Hc * Wc * F;
     void *t_relu, *t_mid, *hraw, *hrelu, *yraw, *up, *prj;
-    if ((r = get_buf(e, "fu.relu", n * 2, &t_relu)) || (r = get_buf(e, "fu.mid", n * 2, &t_mid)) ||
-        (r = get_buf(e, "fu.h", n * 2, &hraw)) || (r = get_buf(e, "fu.hrelu", n * 2, &hrelu)) ||
-        (r = get_buf(e, "fu.y", n * 2, &yraw)))
+    if ((r = get_buf(e, bname("fu.relu"), n * 2, &t_relu)) || (r = get_buf(e, bname("fu.mid"), n * 2, &t_mid)) ||
+        (r = get_buf(e, bname("fu.h"), n * 2, &hraw)) || (r = get_buf(e, bname("fu.hrelu"), n * 2, &hrelu)) ||
+        (r = get_buf(e, bname("fu.y"), n * 2, &yraw)))
       return r;
     auto cv = [&](const char* unit, const char* which, const __half** wv, const float** bv) -> int {
       snprintf(nm, sizeof nm, "f%d.%s.%s.w", j, unit, which);
@@ -762,7 +796,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
     // upsample (to the next feature's size, or x2 at the end), then 1x1 projection
     int OH = (j < 3) ? fh[fi - 1] : Hc * 2, OW = (j < 3) ? fw[fi - 1] : Wc * 2;
     snprintf(nm, sizeof nm, "fu.up%d", j);
-    if ((r = get_buf(e, nm, (size_t)OH * OW * F * 2, &up))) return r;
+    if ((r = get_buf(e, bname(nm), (size_t)OH * OW * F * 2, &up))) return r;
     launch_upsample_ac((const __half*)yraw, Hc, Wc, F, (__half*)up, OH, OW, s);
     e->launches++;
     const __half* pwt;
@@ -772,7 +806,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
     snprintf(nm, sizeof nm, "f%d.proj.b", j);
     if ((r = W(e, nm, &pbs, F))) return r;
     snprintf(nm, sizeof nm, "fused%d", j);
-    if ((r = get_buf(e, nm, (size_t)round_up(OH * OW, 128) * F * 2, &prj))) return r;
+    if ((r = get_buf(e, bname(nm), (size_t)round_up(OH * OW, 128) * F * 2, &prj))) return r;
     GemmArgs g = base_args(OH * OW, F, F, EPI_F16);
     g.out_f16 = (__half*)prj;
     g.bias = pbs;
@@ -793,7 +827,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
         (r = W(e, "h.c3.w", &w3, 32)) || (r = W(e, "h.c3.b", &b3, 1)))
       return r;
     void *h1, *h1u;
-    if ((r = get_buf(e, "h1", (size_t)ch * cw_ * F2 * 2, &h1)) || (r = get_buf(e, "h1u", (size_t)IH * IW * F2 * 2, &h1u)))
+    if ((r = get_buf(e, bname("h1"), (size_t)ch * cw_ * F2 * 2, &h1)) || (r = get_buf(e, bname("h1u"), (size_t)IH * IW * F2 * 2, &h1u)))
       return r;
     GemmArgs g1 = base_args(0, F2, 0, EPI_F16);
     g1.out_f16 = (__half*)h1;
@@ -809,7 +843,11 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
     g2.b3p = b3;
     if ((r = conv(e, (const __half*)h1u, IH, IW, F2, w2, true, g2, 32))) return r;
   }
+  if (fork) DCK(cudaEventRecord(e->ev_join[b], s));
   }  // images
+  e->cur = nullptr;
+  if (fork)
+    for (int b = 0; b < B; ++b) DCK(cudaStreamWaitEvent(s_main, e->ev_join[b], 0));
   DCK(cudaGetLastError());
   return VD3D_OK;
 }
