@@ -285,7 +285,7 @@ int vd3d_depth_infer_batch(vd3d_depth* e, int B, const uint8_t* const* frames_bg
                            uint8_t* const* depth_u8, int invert);
 int vd3d_depth_infer_batch_device(vd3d_depth* e, int B, const uint8_t* const* frames_bgr_dev, int h, int w,
                                   uint8_t* const* depth_u8_dev, float* const* depth_f32_dev, int invert);
-/* frames per depth forward inside vd3d_render_clip_depth (1..4, default 4; env VD3D_DEPTH_BATCH) */
+/* frames per depth forward inside vd3d_render_clip_depth (1..8, default 4; env VD3D_DEPTH_BATCH) */
 int vd3d_set_depth_batch(vd3d_ctx* ctx, int frames);
 int vd3d_get_depth_batch(vd3d_ctx* ctx);
 /* ---- Real-ESRGAN upscale stage (core/merged_pipeline.py:221-267) --------------------------------

@@ -23,9 +23,9 @@ struct Buf {
   size_t cap = 0;
 };
 
-constexpr int kSlots = 8;    // staging slots: two depth batches of up to kMaxDepthBatch frames in flight
+constexpr int kSlots = 16;   // staging slots: two depth batches of up to kMaxDepthBatch frames in flight
 constexpr int kClones = 2;   // depth engine instances (own activation buffers / stream), alternating per batch
-constexpr int kMaxDepthBatch = 4;
+constexpr int kMaxDepthBatch = 8;
 constexpr int kJobs = 5;  // pct, subj(norm), quantile(d0), subj(d0), subj(shaped)
 constexpr size_t kJobWords = 4096 + 4 * 4096 + 4 * 64 + 64 + 64;  // + count (padded)
 constexpr size_t kBarWords = 64;
@@ -97,7 +97,7 @@ struct vd3d_ctx {
     uint64_t n = 0;
   } dg[kClones][kMaxDepthBatch + 1];
   int dg_warm = 0, dg_h = 0, dg_w = 0;
-  int depth_batch = 4;  // frames per depth forward in vd3d_render_clip_depth (env VD3D_DEPTH_BATCH, 1..4)
+  int depth_batch = 4;  // frames per depth forward in vd3d_render_clip_depth (env VD3D_DEPTH_BATCH, 1..8)
   // dof kernel cache
   double dof_sigma_cached = -1.0;
   int dof_nlevels = 0, dof_ksize[8] = {0}, dof_koff[8] = {0}, dof_halo = 0;
@@ -1774,7 +1774,7 @@ int vd3d_render_clip_depth(vd3d_ctx* ctx, vd3d_depth* depth, int n, const uint8_
 }
 
 int vd3d_set_depth_batch(vd3d_ctx* ctx, int frames) {
-  if (!ctx || frames < 1 || frames > kMaxDepthBatch) return fail(ctx, VD3D_ERR_ARG, "depth batch must be in [1, 4]");
+  if (!ctx || frames < 1 || frames > kMaxDepthBatch) return fail(ctx, VD3D_ERR_ARG, "depth batch must be in [1, 8]");
   if (frames != ctx->depth_batch) {
     CK(cudaDeviceSynchronize());
     ctx->depth_batch = frames;
