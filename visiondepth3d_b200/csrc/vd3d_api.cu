@@ -828,6 +828,10 @@ int vd3d_create(int device, vd3d_ctx** out) {
   if ((e = cudaMallocHost(&ctx->st_pinned, sizeof(DevState))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = init_kernel_attributes()) != cudaSuccess) return bail("cudaFuncSetAttribute", e);
   if ((e = stats_grid(device, &ctx->stats_blocks)) != cudaSuccess) return bail("k_stats occupancy", e);
+  if (const char* v = getenv("VD3D_STATS_BLOCKS")) {  // tuning: fewer CTAs leave SMs to the depth kernels of the next batch
+    int n = atoi(v);
+    if (n >= 8 && n < ctx->stats_blocks) ctx->stats_blocks = n;
+  }
   {
     const char* v = getenv("VD3D_EXACT");
     ctx->exact = (v && atoi(v)) ? 1 : 0;
