@@ -260,6 +260,9 @@ void vd3d_depth_destroy(vd3d_depth* e);
 /* CUDA-event timing of the fc1 GEMM launches (k_umma_gemm<128,3>; M = tokens, N = 4*hidden, K = hidden) */
 int vd3d_depth_profile(vd3d_depth* e, int enable);
 int vd3d_depth_profile_collect(vd3d_depth* e, double* total_ms, int* count, double* gflop_per_launch);
+/* tuning aid: after vd3d_depth_profile(e, 2), every launch class of an eager forward is bracketed by CUDA events; this
+   returns "tag total_ms spans" lines (NUL-terminated, truncated to cap) and clears the record */
+int vd3d_depth_profile_spans(vd3d_depth* e, char* out, size_t cap);
 /* another instance on `cuda_stream` sharing e's weights (own activations); destroy it before e */
 int vd3d_depth_clone(vd3d_depth* e, void* cuda_stream, vd3d_depth** out);
 const char* vd3d_depth_last_error(vd3d_depth* e);

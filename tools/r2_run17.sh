@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 300 python tools/gemm_epi_sweep2.py 2>&1 | tail -40

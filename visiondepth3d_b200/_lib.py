@@ -90,7 +90,7 @@ SYMBOLS = [
     "vd3d_depth_set_tensor", "vd3d_depth_forward", "vd3d_depth_get_buffer", "vd3d_gemm_f16", "vd3d_gemm_bench", "vd3d_conv_f16",
     "vd3d_depth_infer", "vd3d_depth_infer_device", "vd3d_depth_infer_batch", "vd3d_depth_infer_batch_device",
     "vd3d_set_depth_batch", "vd3d_get_depth_batch", "vd3d_render_clip_depth", "vd3d_depth_add_launches", "vd3d_depth_clone", "vd3d_release_depth",
-    "vd3d_depth_profile", "vd3d_depth_profile_collect",
+    "vd3d_depth_profile", "vd3d_depth_profile_collect", "vd3d_depth_profile_spans",
     "vd3d_advance_state", "vd3d_state_bytes", "vd3d_export_state", "vd3d_import_state",
 ]
 

@@ -65,6 +65,25 @@ struct vd3d_depth {
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;
   long long prof_rows = 0;  // rows (tokens of all images of the batch) summed over the timed fc1 launches
+  // tuning aid (vd3d_depth_profile(e, 2)): device time of every launch class of the forward, eager mode only
+  struct Span {
+    const char* tag;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<Span> spans;
+  int span_begin(const char* tag, cudaStream_t s) {
+    if (!prof_spans) return -1;
+    Span sp{tag, nullptr, nullptr};
+    cudaEventCreate(&sp.e0);
+    cudaEventCreate(&sp.e1);
+    cudaEventRecord(sp.e0, s);
+    spans.push_back(sp);
+    return (int)spans.size() - 1;
+  }
+  void span_end(int i, cudaStream_t s) {
+    if (i >= 0) cudaEventRecord(spans[i].e1, s);
+  }
+  bool prof_spans = false;
 };
 
 namespace {
@@ -144,7 +163,7 @@ GemmArgs base_args(int M, int N, int K, int epi) {
 int pick_bn(int N) { return N >= 128 ? 128 : (N >= 64 ? 64 : 32); }
 
 // B tensor-map box rows for a tile code (see launch_gemm): the CTA-pair kernels stage half the tile's N per CTA
-int box_rows(int bn) { return bn == 256 ? 128 : (bn == -128 ? 64 : bn); }
+int box_rows(int bn) { return bn == 256 ? 128 : (bn == -128 ? 64 : (bn == 1128 ? 128 : bn)); }
 
 // VD3D_GEMM_2CTA=1: route large plain GEMMs through the cta_group::2 kernel (256-row tiles)
 int pair_mode() {
@@ -155,11 +174,40 @@ int pair_mode() {
   }
   return mode;
 }
-int pick_bn_gemm(int M, int N) {
-  if (pair_mode() && M >= 512) {
+// Kernel choice of the token GEMMs (VD3D_GEMM_POLICY=0: everything on the 128x128 single-CTA kernel).
+//  * fc2 (fp32 residual epilogue, K = 4D) and the QKV GEMM of the Large model (K = 1024) run on the CTA-pair kernel, 256x256
+//    tiles: the 128x128 kernel is bound by the L2->smem operand feed (~20 TB/s device-wide at 64 FLOP/B), the pair tile
+//    halves the bytes per FLOP.  In situ, 4 frames per forward: fc2 63 -> 54 us (Base), 95 -> 82 (Large); QKV-Large 60 -> 57.
+//    fc1 stays: its bias + GELU epilogue is ALU bound and the pair kernel has half the epilogue warps per SM (54 -> 72 us).
+//    The pair kernel's fp32 accumulation is not bit-identical to the single-CTA kernel's, so this choice depends on the
+//    model and the per-image token count only, never on the batch size: a frame's depth is the same inferred alone or in
+//    a batch (tests/test_depth_gpu.py::test_infer_batch_equals_single_frames; exact sharding == one GPU).
+//  * proj (K = D: two tiles per CTA, 1.6 us of MMAs per tile) of a batched forward runs one CTA per SM with 16 epilogue
+//    warps, each prefetching its slice of the residual stream while the MMAs run (41 -> 38.6 us; same MMA shape as the
+//    default kernel: bit-identical).
+int gemm_policy() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* v = getenv("VD3D_GEMM_POLICY");
+    mode = v ? atoi(v) : 1;
+  }
+  return mode;
+}
+int pick_bn_gemm(const vd3d_depth* e, int M, int N, int K, int epi) {
+  const int pm = pair_mode();
+  if (pm == 3) {  // tuning: every large batched GEMM on the pair kernel
+    if (M >= 4096 && N >= 768 && (long)N * K >= 1536L * 768) return 256;
+    return pick_bn(N);
+  }
+  if (pm && M >= 512) {
     if (N >= 1536) return 256;
     if (N >= 512) return -128;
   }
+  if (gemm_policy() && e->ntok >= 1024 && (N % 256) == 0) {
+    if (epi == EPI_RESID_LS && K >= 1536) return 256;
+    if (epi == EPI_QKV && K >= 1024) return 256;
+  }
+  if (gemm_policy() && epi == EPI_RESID_LS && M >= 4096 && N >= 128) return 1128;
   return pick_bn(N);
 }
 int pick_bn_conv(int M, int N) {  // VD3D_GEMM_2CTA=2: implicit-GEMM convs too (two pixel tiles per pair)
@@ -172,7 +220,7 @@ int pick_bn_conv(int M, int N) {  // VD3D_GEMM_2CTA=2: implicit-GEMM convs too (
 
 // plain GEMM: A [M, K] (lda), B [N, K] (ldb)
 int gemm(vd3d_depth* e, const __half* A, int lda, const __half* B, int ldb, GemmArgs g, int bn = 0) {
-  if (!bn) bn = pick_bn_gemm(g.M, g.N);  // (64-wide tiles for sub-wave grids were measured slower: L2->smem fill bound)
+  if (!bn) bn = pick_bn_gemm(e, g.M, g.N, g.K, g.epi);  // (64-wide tiles for sub-wave grids were measured slower: L2->smem fill bound)
   CUtensorMap ma, mb;
   int r;
   if ((r = make_map(e, &ma, A, g.K, g.M, 1, lda, (uint64_t)lda * g.M, 128, 1))) return r;
@@ -266,7 +314,35 @@ int vd3d_depth_create(const vd3d_depth_config* cfg, void* stream, vd3d_depth** o
 // device timing of the fc1 GEMM launches (k_umma_gemm<128,3>, M=tokens, N=4D, K=D): bench.py roofline
 int vd3d_depth_profile(vd3d_depth* e, int enable) {
   if (!e) return VD3D_ERR_ARG;
-  e->prof = enable != 0;
+  e->prof = enable == 1;
+  e->prof_spans = enable == 2;
+  return VD3D_OK;
+}
+// "tag total_ms launches" lines of the spans recorded since the last call (vd3d_depth_profile(e, 2))
+int vd3d_depth_profile_spans(vd3d_depth* e, char* out, size_t cap) {
+  if (!e || !out || !cap) return VD3D_ERR_ARG;
+  DCK(cudaDeviceSynchronize());
+  std::vector<std::pair<std::string, std::pair<double, int>>> acc;
+  for (auto& sp : e->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) != cudaSuccess) ms = 0.f;
+    cudaEventDestroy(sp.e0);
+    cudaEventDestroy(sp.e1);
+    size_t i = 0;
+    for (; i < acc.size(); ++i)
+      if (acc[i].first == sp.tag) break;
+    if (i == acc.size()) acc.push_back({sp.tag, {0.0, 0}});
+    acc[i].second.first += ms;
+    acc[i].second.second++;
+  }
+  e->spans.clear();
+  std::string txt;
+  char line[128];
+  for (auto& a : acc) {
+    snprintf(line, sizeof line, "%s %.4f %d\n", a.first.c_str(), a.second.first, a.second.second);
+    txt += line;
+  }
+  snprintf(out, cap, "%s", txt.c_str());
   return VD3D_OK;
 }
 int vd3d_depth_profile_collect(vd3d_depth* e, double* total_ms, int* count, double* gflop_per_launch) {
@@ -400,8 +476,19 @@ int vd3d_gemm_bench(vd3d_depth* e, int M, int N, int K, int variant, int dbg, in
   DCK(cudaMemsetAsync(db, 0x2c, (size_t)N * K * 2, e->stream));
   GemmArgs g = base_args(M, N, K, EPI_F16);
   g.out_f16 = (__half*)dc;
-  g.act = act;
+  g.act = act & 0xff;
   g.dbg = dbg;
+  if (act & 0x100) {  // the proj / fc2 epilogue: fp32 residual stream read-modify-write with bias and LayerScale
+    void *dx, *dv;
+    if ((r = get_buf(e, "t.bx", (size_t)M * N * 4, &dx))) return r;
+    if ((r = get_buf(e, "t.bv", (size_t)N * 4, &dv))) return r;  // zeros: bias = ls = 0 keeps x finite over the iterations
+    g.epi = EPI_RESID_LS;
+    g.act = 0;
+    g.out_f32 = (float*)dx;
+    g.bias = (const float*)dv;
+    g.ls = (const float*)dv;
+    g.ldc = N;
+  }
   CUtensorMap ma, mb;
   if ((r = make_map(e, &ma, da, K, M, 1, K, (uint64_t)K * M, 128, 1))) return r;
   if ((r = make_map(e, &mb, db, K, N, 1, K, (uint64_t)K * N, variant >= 20 ? 64 : 128, 1))) return r;
@@ -497,6 +584,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
   if ((r = get_buf(e, "ape", (size_t)NPATCH * KPE * 2, &ape))) return r;
 
   // ---- patch embedding + CLS + position embeddings ----
+  const int sp_embed = e->span_begin("embed", s);
   const __half* pe_w;
   const float *pe_b, *cls, *pos;
   if ((r = W(e, "pe.w", &pe_w, (size_t)D * KPE)) || (r = W(e, "pe.b", &pe_b, D)) || (r = W(e, "cls", &cls, D)) ||
@@ -518,6 +606,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
     if (b + 1 < B) DCK(cudaMemsetAsync(xb + (size_t)NT * D, 0, (size_t)(NP - NT) * D * 4, s));
   }
 
+  e->span_end(sp_embed, s);
   // ---- transformer blocks ----
   int tap_idx = 0;
   for (int l = 0; l < L; ++l) {
@@ -535,7 +624,10 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
         (r = W(e, nmf("fc2.w"), &wf2, (size_t)4 * D * D)) || (r = W(e, nmf("fc2.b"), &bf2, D)) ||
         (r = W(e, nmf("ls2"), &ls2, D)))
       return r;
+    int sp_ = e->span_begin("ln", s);
     launch_layernorm((const float*)x, MT, D, g1, b1, (__half*)xn, 0, s);
+    e->span_end(sp_, s);
+    sp_ = e->span_begin("qkv", s);
     {
       GemmArgs g = base_args(MT, 3 * D, D, EPI_QKV);
       g.bias = bqkv;
@@ -548,6 +640,8 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
       g.qscale = 0.125f;  // 1/sqrt(64), exact in f16
       if ((r = gemm(e, (const __half*)xn, D, wqkv, D, g))) return r;
     }
+    e->span_end(sp_, s);
+    sp_ = e->span_begin("attn", s);
     if (e->flash) {
       // fused tcgen05 attention: scores stay in TMEM, probabilities in shared memory
       CUtensorMap mq, mk, mv;
@@ -579,6 +673,8 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
           return r;
       }
     }
+    e->span_end(sp_, s);
+    sp_ = e->span_begin("proj", s);
     {
       GemmArgs g = base_args(MT, D, D, EPI_RESID_LS);
       g.out_f32 = (float*)x;
@@ -587,7 +683,11 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
       g.ldc = D;
       if ((r = gemm(e, (const __half*)attn, D, wo, D, g))) return r;
     }
+    e->span_end(sp_, s);
+    sp_ = e->span_begin("ln", s);
     launch_layernorm((const float*)x, MT, D, g2, b2, (__half*)xn, 0, s);
+    e->span_end(sp_, s);
+    sp_ = e->span_begin("fc1", s);
     {
       GemmArgs g = base_args(MT, 4 * D, D, EPI_F16);
       g.out_f16 = (__half*)hb;
@@ -608,6 +708,8 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
         e->prof_ev.push_back(e1);
       }
     }
+    e->span_end(sp_, s);
+    sp_ = e->span_begin("fc2", s);
     {
       GemmArgs g = base_args(MT, D, 4 * D, EPI_RESID_LS);
       g.out_f32 = (float*)x;
@@ -616,6 +718,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
       g.ldc = D;
       if ((r = gemm(e, (const __half*)hb, 4 * D, wf2, 4 * D, g))) return r;
     }
+    e->span_end(sp_, s);
     e->launches += 2;
     if (tap_idx < 4 && c.taps[tap_idx] == l + 1) {
       // backbone output: final LayerNorm applied (apply_layernorm=True), CLS dropped by the neck
@@ -638,6 +741,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
   // the coarse maps) overlap each other instead of leaving most SMs idle; captured into the same CUDA graph.
   const bool fork = B > 1;
   cudaStream_t s_main = s;
+  const int sp_tail = e->span_begin("tail(all images, forked)", s_main);
   if (fork) {
     if (!e->ev_fork) DCK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     DCK(cudaEventRecord(e->ev_fork, s_main));
@@ -848,6 +952,7 @@ int forward_core(vd3d_depth* e, int B, const float* const* px_dev, float* const*
   e->cur = nullptr;
   if (fork)
     for (int b = 0; b < B; ++b) DCK(cudaStreamWaitEvent(s_main, e->ev_join[b], 0));
+  e->span_end(sp_tail, s_main);
   DCK(cudaGetLastError());
   return VD3D_OK;
 }

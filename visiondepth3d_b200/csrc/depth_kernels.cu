@@ -448,30 +448,39 @@ void launch_relu_f16(const __half* in, __half* out, size_t n, cudaStream_t s) {
   k_relu_f16<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(in, out, n8);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EW = 8>
 static cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, dim3 grid,
                                  cudaStream_t s) {
   static bool attr_set = false;
   constexpr int smem = GemmSmem<BN, STAGES>::kTotal;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_gemm<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e =
+        cudaFuncSetAttribute(k_umma_gemm<BN, STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_umma_gemm<BN, STAGES><<<grid, kGemmThreads, smem, s>>>(a, b, g);
+  k_umma_gemm<BN, STAGES, EW><<<grid, 64 + 32 * EW, smem, s>>>(a, b, g);
   return cudaGetLastError();
 }
 
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, int ntok, int dmodel,
                              __half* out, int heads, int images, int npad, cudaStream_t s) {
   static bool attr_set = false;
-  static int two_pass = 0;
+  static int mode = 1;  // VD3D_ATTN_MODE: -2 two-pass, -1 k_umma_attention_1p, 0 / 1 / 2 k_umma_attention_v3<MODE>
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_umma_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_umma_attention_1p, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return e;
-    if (const char* v = getenv("VD3D_ATTN_2PASS")) two_pass = atoi(v);
+    e = cudaFuncSetAttribute(k_umma_attention_v3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_umma_attention_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_umma_attention_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return e;
+    if (const char* v = getenv("VD3D_ATTN_2PASS"))
+      if (atoi(v)) mode = -2;
+    if (const char* v = getenv("VD3D_ATTN_MODE")) mode = atoi(v);
     attr_set = true;
   }
   AttnArgs a;
@@ -481,10 +490,13 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
   a.heads = heads;
   a.npad = npad;
   dim3 grid((ntok + 127) / 128, heads * images);
-  if (two_pass)
-    k_umma_attention<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a);
-  else
-    k_umma_attention_1p<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a);
+  switch (mode) {
+    case -2: k_umma_attention<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
+    case -1: k_umma_attention_1p<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
+    case 0: k_umma_attention_v3<0><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
+    case 2: k_umma_attention_v3<2><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
+    default: k_umma_attention_v3<1><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
+  }
   return cudaGetLastError();
 }
 
@@ -502,7 +514,7 @@ static cudaError_t launch_gemm2_t(const CUtensorMap& a, const CUtensorMap& b, co
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(2 * npairs, 1, 1);
-  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.blockDim = dim3(kGemm2Threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
@@ -549,6 +561,7 @@ cudaError_t launch_gemm_variant(int variant, const CUtensorMap& a, const CUtenso
     case 0:
     case 2: return launch_gemm_t<128, 3>(a, b, g, grid, s);
     case 1: return launch_gemm_t<128, 6>(a, b, g, grid, s);
+    case 3: return launch_gemm_t<128, 6, 16>(a, b, g, grid, s);  // one CTA per SM, 16 epilogue warps
     default: return cudaErrorInvalidValue;
   }
 }
@@ -574,6 +587,11 @@ cudaError_t launch_gemm(int bn, const CUtensorMap& a, const CUtensorMap& b, cons
     int npairs = total < sms / 2 ? total : sms / 2;
     if (bn == 256) return launch_gemm2_t<256, 6>(a, b, g, npairs, s);
     return launch_gemm2_t<128, 8>(a, b, g, npairs, s);
+  }
+  if (bn == 1128) {  // residual GEMMs of a batched forward: one CTA per SM, 6-stage ring, 16 epilogue warps (one chunk each)
+    g.nt = (g.N + 127) / 128;
+    int total = g.nt * g.mt * g.nz;
+    return launch_gemm_t<128, 6, 16>(a, b, g, dim3(total < sms ? total : sms, 1, 1), s);
   }
   // persistent grid: two CTAs per SM (97 KB smem, 2 x BN TMEM columns each), each walks its tiles
   const int resident = 2 * sms;

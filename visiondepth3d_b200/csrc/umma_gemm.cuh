@@ -315,6 +315,42 @@ __device__ __forceinline__ void pack16(const float (&a)[32], int base, bool relu
 
 }  // namespace umma
 
+// proj / fc2 epilogue (EPI_RESID_LS) split in two so that the read of the fp32 residual stream -- which does not depend on
+// the MMAs -- can be issued BEFORE the accumulator is complete: issued after tmem_full, its ~1.5 us of L2 latency per
+// chunk was exposed twice per tile (proj, K = 768, spends 1.6 us per tile in the MMAs).
+__device__ __forceinline__ bool resid_split_ok(const GemmArgs& g) {
+  return g.epi == EPI_RESID_LS && (g.N & 31) == 0 && (g.ldc & 7) == 0 && g.bias != nullptr && g.conv == 0;
+}
+__device__ __forceinline__ void resid_load(const GemmArgs& g, const int m, const int n0, uint32_t (&x)[32]) {
+  const float* src = g.out_f32 + (size_t)m * g.ldc + n0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(x[8 * j]), "=r"(x[8 * j + 1]), "=r"(x[8 * j + 2]), "=r"(x[8 * j + 3]), "=r"(x[8 * j + 4]),
+                   "=r"(x[8 * j + 5]), "=r"(x[8 * j + 6]), "=r"(x[8 * j + 7])
+                 : "l"(src + 8 * j));
+}
+// x[m, n0 .. n0+31] = x + ls * (acc + bias), x already in registers
+__device__ __forceinline__ void resid_apply_store(const GemmArgs& g, const uint32_t (&v)[32], const int m, const int n0,
+                                                  uint32_t (&x)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b4 = __ldg((const float4*)(g.bias + n0) + j);
+    const float4 l4 = __ldg((const float4*)(g.ls + n0) + j);
+    x[4 * j + 0] = __float_as_uint(fmaf(l4.x, __uint_as_float(v[4 * j + 0]) + b4.x, __uint_as_float(x[4 * j + 0])));
+    x[4 * j + 1] = __float_as_uint(fmaf(l4.y, __uint_as_float(v[4 * j + 1]) + b4.y, __uint_as_float(x[4 * j + 1])));
+    x[4 * j + 2] = __float_as_uint(fmaf(l4.z, __uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(x[4 * j + 2])));
+    x[4 * j + 3] = __float_as_uint(fmaf(l4.w, __uint_as_float(v[4 * j + 3]) + b4.w, __uint_as_float(x[4 * j + 3])));
+  }
+  float* dst = g.out_f32 + (size_t)m * g.ldc + n0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j), "r"(x[8 * j]),
+                 "r"(x[8 * j + 1]), "r"(x[8 * j + 2]), "r"(x[8 * j + 3]), "r"(x[8 * j + 4]), "r"(x[8 * j + 5]),
+                 "r"(x[8 * j + 6]), "r"(x[8 * j + 7])
+                 : "memory");
+}
+
 // Fused epilogue of one 32-column chunk of one accumulator row (thread == row): v = raw fp32 accumulator bits,
 // m = logical output row, n0 = first output column.  Shared by the 1-CTA and the CTA-pair kernels; every
 // register array is indexed with compile-time constants only so the chunk stays in registers.
@@ -513,8 +549,10 @@ struct GemmSmem {
   static constexpr int kTotal = STAGES * kStage + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads)
+// EW: epilogue warps (8: two per TMEM lane quarter, two CTAs per SM; 16: four per quarter for the one-CTA-per-SM launches
+// of the residual GEMMs, where every warp owns ONE chunk of a tile and prefetches its slice of the residual stream)
+template <int BN, int STAGES, int EW = 8>
+__global__ void __launch_bounds__(64 + 32 * EW, EW == 8 ? 0 : 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   using S = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -543,7 +581,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       umma::mbar_init(umma::smem_u32(&tmem_full[i]), 1);
-      umma::mbar_init(umma::smem_u32(&tmem_empty[i]), 8);
+      umma::mbar_init(umma::smem_u32(&tmem_empty[i]), EW);
     }
     umma::fence_barrier_init();
   }
@@ -640,16 +678,15 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // array below is indexed with compile-time constants only (fully unrolled, predicated) so the 32
     // accumulator values of a chunk stay in registers.
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // which half of the chunks
+    const int half = (warp - 2) >> 2;  // which share of the chunks (0 .. EW/4 - 1)
     constexpr int kChunks = BN / 32;
+    constexpr int kStride = EW / 4;
+    const bool split = EW == 16 && resid_split_ok(g) && dmode == 0;  // (8-warp kernels: 76 registers, two CTAs per SM)
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
     int n_blk, m_blk, z, px0, py0;
     decode(tile, n_blk, m_blk, z, px0, py0);
     const int as = it & 1;
-    umma::mbar_wait_dbg(umma::smem_u32(&tmem_full[as]), (it >> 1) & 1, spin);
-    umma::tc_fence_after();
-    const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
     const int r = q * 32 + lane;  // accumulator row inside the tile
     int m;                        // logical output row
     bool row_ok;
@@ -662,9 +699,14 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       m = m_blk * 128 + r;
       row_ok = m < g.M;
     }
+    uint32_t xr[32];  // residual-stream slice of this thread's next chunk, in flight while the MMAs run
+    if (split && row_ok && half < kChunks) resid_load(g, m, n_blk * BN + half * 32, xr);
+    umma::mbar_wait_dbg(umma::smem_u32(&tmem_full[as]), (it >> 1) & 1, spin);
+    umma::tc_fence_after();
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BN);
     float head_acc = 0.f;
 #pragma unroll 1
-    for (int ci = half; ci < kChunks; ci += 2) {
+    for (int ci = half; ci < kChunks; ci += kStride) {
       if (dmode == 4) break;
       const int c0 = ci * 32;
       uint32_t v[32];
@@ -672,6 +714,13 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n0 = n_blk * BN + c0;
       if (dmode == 5) {
         if (v[0] == 0x7fc12345u && v[17] == 0x12345u) g.out_f32[0] = 1.f;  // keep the load alive
+        continue;
+      }
+      if (split) {
+        if (row_ok) {
+          resid_apply_store(g, v, m, n0, xr);
+          if (ci + kStride < kChunks) resid_load(g, m, n0 + kStride * 32, xr);
+        }
         continue;
       }
       gemm_epilogue_chunk(g, v, m, z, n0, row_ok, head_acc);

@@ -60,6 +60,8 @@ def _bind(lib):
     lib.vd3d_depth_profile.restype = i
     lib.vd3d_depth_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i), C.POINTER(C.c_double)]
     lib.vd3d_depth_profile_collect.restype = i
+    lib.vd3d_depth_profile_spans.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.vd3d_depth_profile_spans.restype = i
     lib._depth_bound = True
 
 
