@@ -56,8 +56,10 @@ NCU_RENDER_TRAFFIC = {"4k": 115_862_272, "1080p": 49_949_440}
 # smsp__issue_active.avg.pct_of_peak_sustained_active of the same launches: the DIBR kernels are issue bound, not HBM
 # bound, so this is the roofline fraction that describes them
 NCU_RENDER_ISSUE_ACTIVE = {"4k": 70.6, "1080p": 62.9}
-# same for one fc1 launch of k_umma_gemm<128,3> (DA-V2-Base: M=2443, N=3072, K=768): 8.56 MB read + 0.01 MB written
-NCU_GEMM_FC1_TRAFFIC = {"vitb": 8571136, "vitl": None, "vits": None}
+# same for one fc1 launch of k_umma_gemm<128,3> of a 4-frame forward (DA-V2-Base: M=10123, N=3072, K=768): 20.4 MB read +
+# 11.7 MB written, cold L2 (profiles/r02_ncu_depth_final.md; algorithmic: 15.5 MB A + 4.7 MB W + 62.2 MB out, the output
+# mostly stays in the 126 MB L2 for fc2)
+NCU_GEMM_FC1_TRAFFIC = {"vitb": 32_100_000, "vitl": None, "vits": None}
 COMMON = dict(fg=4.5, mg=-1.5, bg=-6.0, sharp=0.2, feather=10.0, ksize=9, tracking=True, floating=True,
               zps=0.01, dof=0.0)
 

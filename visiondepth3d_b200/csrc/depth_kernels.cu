@@ -466,7 +466,7 @@ static cudaError_t launch_gemm_t(const CUtensorMap& a, const CUtensorMap& b, con
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, int ntok, int dmodel,
                              __half* out, int heads, int images, int npad, cudaStream_t s) {
   static bool attr_set = false;
-  static int mode = 1;  // VD3D_ATTN_MODE: -2 two-pass, -1 k_umma_attention_1p, 0 / 1 / 2 k_umma_attention_v3<MODE>
+  static int mode = 2;  // VD3D_ATTN_MODE: -2 two-pass, -1 k_umma_attention_1p, 0 / 1 / 2 k_umma_attention_v3<MODE>, 3 / 4 v3<2> + polynomial exp2
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_umma_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return e;
@@ -477,6 +477,10 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
     e = cudaFuncSetAttribute(k_umma_attention_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_umma_attention_v3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_umma_attention_v3<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_umma_attention_v3<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return e;
     if (const char* v = getenv("VD3D_ATTN_2PASS"))
       if (atoi(v)) mode = -2;
@@ -494,8 +498,10 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
     case -2: k_umma_attention<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
     case -1: k_umma_attention_1p<<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
     case 0: k_umma_attention_v3<0><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
-    case 2: k_umma_attention_v3<2><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
-    default: k_umma_attention_v3<1><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
+    case 1: k_umma_attention_v3<1><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
+    case 3: k_umma_attention_v3<2, 2><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;  // 25 % of the exps on the FMA pipe
+    case 4: k_umma_attention_v3<2, 4><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;  // 50 %
+    default: k_umma_attention_v3<2><<<grid, kAttnThreads, kAttnSmem, s>>>(q, k, v, a); break;
   }
   return cudaGetLastError();
 }

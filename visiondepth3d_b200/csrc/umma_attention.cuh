@@ -572,6 +572,17 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
+// 2^x for x <= 16 on the FMA / ALU pipes, degree-3 minimax of 2^f on [-0.5, 0.5] (relative error 7.7e-5: below the f16
+// rounding of the probabilities it produces); see ex2_poly
+__device__ __forceinline__ float ex2_poly3(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05511401f, 0.24260628f);
+  p = fmaf(f, p, 0.69327159f);
+  p = fmaf(f, p, 0.99992867f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -591,7 +602,10 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
 }
 }  // namespace umma
 
-template <int MODE>
+// POLY: of every 8 exponentials of a full tile, this many are evaluated on the FMA pipe (umma::ex2_poly3) instead of the
+// MUFU: the probabilities are rounded to f16 anyway, and the XU pipe is the kernel's first bound (16 results per clock
+// and SM: 1024 clocks per 128 x 128 tile against 512 for the two MMAs).
+template <int MODE, int POLY = 0>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 k_umma_attention_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnArgs g) {
@@ -774,8 +788,9 @@ k_umma_attention_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 64; j += 2) {
-          const float p0 = umma::ex2_fast(fmaf(__uint_as_float(v[j]), L2E, -m_ref));
-          const float p1 = umma::ex2_fast(fmaf(__uint_as_float(v[j + 1]), L2E, -m_ref));
+          const float x0 = fmaf(__uint_as_float(v[j]), L2E, -m_ref), x1 = fmaf(__uint_as_float(v[j + 1]), L2E, -m_ref);
+          const float p0 = ((j & 7) < POLY) ? umma::ex2_poly3(x0) : umma::ex2_fast(x0);
+          const float p1 = ((j & 7) < POLY) ? umma::ex2_poly3(x1) : umma::ex2_fast(x1);
           s0 += p0;
           s1 += p1;
           __half2 hp = __floats2half2_rn(p0, p1);
