@@ -89,9 +89,9 @@ def loop(monkeypatch):
             return True
 
         def read(self):
-            if self.pos >= state["n"]:
+            if self.pos >= (state.get("n_depth", state["n"]) if self.depth else state["n"]):
                 return False, None
-            f = np.full((36, 64, 3), self.pos + (100 if self.depth else 0), dtype=np.uint8)
+            f = np.full((36, 64, 3), (self.pos + (100 if self.depth else 0)) % 256, dtype=np.uint8)
             self.pos += 1
             return True, f
 
@@ -150,3 +150,22 @@ def test_clip_window_and_refusals(loop):
     ev = threading.Event()
     ev.set()
     assert run(cancel=ev)[0] == []                            # cancelled before the first frame
+
+
+def test_lookahead_keeps_order_and_stops_at_the_shorter_stream(loop):
+    """The stream workers run several pairs ahead of the published position: order, pairing and the end of the clip must
+    not depend on it."""
+    run, state = loop
+    state["n"] = 100
+    out, calls = run()
+    assert [o[0] for o in out] == list(range(1, 100)) and [o[1] for o in out] == [(100 + i) % 256 for i in range(1, 100)]
+    assert calls == [8] * 12 + [3]
+    state["n_depth"] = 41                          # depth video shorter than the colour video: pairs end with it
+    out, _ = run()
+    assert [o[0] for o in out] == list(range(1, 41))
+    del state["n_depth"]
+    state["n"] = 240
+    out, _ = run(start_s=8.0)                      # open-ended window: from frame 192 (dropped) to the end of the clip
+    assert [o[0] for o in out] == list(range(193, 240))
+    out, _ = run(start_s=2.0, end_s=2.05)          # one-frame window: the pair after the dropped one is still rendered
+    assert [o[0] for o in out] == [49]

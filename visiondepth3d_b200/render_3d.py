@@ -417,6 +417,8 @@ class _FrameSink:
 
 
 _BATCH = 8  # frames per vd3d_render_clip call of the video loop (3 of them in flight on the device)
+_LOOKAHEAD = 3  # runs of up to _RUN pairs in flight between the reader and the two stream workers of render_sbs_3d
+_RUN = 4
 
 
 def render_sbs_3d(
@@ -509,44 +511,78 @@ def render_sbs_3d(
 
         def stream_worker(which, src):
             while True:
-                k = q_jobs[which].get()
-                if k is None:
+                ks = q_jobs[which].get()
+                if ks is None:
                     return
+                n_ok = 0
                 try:
-                    ok, img = src.read()
-                    if ok and k >= 0:
-                        np.copyto(ring_in[which].arrays[k], img)
+                    for k in ks:                        # a run of ring slots (-1: read and drop)
+                        ok, img = src.read()
+                        if not ok:
+                            break
+                        if k >= 0:
+                            np.copyto(ring_in[which].arrays[k], img)
+                        n_ok += 1
                 except Exception as e:
                     errors.append(e)
-                    ok = False
-                q_done[which].put(bool(ok))
+                q_done[which].put(n_ok)
 
-        def read_pair(k):
-            q_jobs[0].put(k)
-            q_jobs[1].put(k)
-            try:   # a decoder that stalls for a minute is treated like a failed read (the reference would block forever)
-                ok_a, ok_b = q_done[0].get(timeout=60), q_done[1].get(timeout=60)
+        def collect_run():
+            """Pairs of the oldest run that both streams delivered (a decoder that stalls for a minute counts as a failed
+            read; the reference would block forever)."""
+            try:
+                return min(q_done[0].get(timeout=60), q_done[1].get(timeout=60))
             except queue.Empty:
-                return False
-            return ok_a and ok_b
+                return 0
+
+        def issue_run(ks):
+            q_jobs[0].put(ks)
+            q_jobs[1].put(ks)
 
         def reader():
+            # Runs of up to _RUN pairs are handed to the two stream workers, _LOOKAHEAD runs ahead of the one being
+            # collected, so the decoders / copies of both streams work back to back instead of meeting at a barrier after
+            # every frame (and the queue traffic is per run, not per frame); pairs are still published in order.  A
+            # bounded window stops after the pair that reaches its last frame (the reference checks
+            # CAP_PROP_POS_FRAMES >= stop after each read, 1196-1199): counted here, because the decoders run ahead of
+            # the published position.
+            import collections
             try:
                 cap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
                 dcap.set(cv2.CAP_PROP_POS_FRAMES, win.first)
-                if read_pair(-1):                       # the first pair of the window is read and dropped (1184-1188)
-                    for _ in range(win.budget):
+                issue_run([-1])                         # the first pair of the window is read and dropped (1184-1188)
+                limit = max(win.budget - 1, 1) if win.bounded else win.budget
+                inflight, issued, closed = collections.deque(), 0, collect_run() != 1
+                while True:
+                    while not closed and issued < limit and len(inflight) < _LOOKAHEAD:
                         while suspend_flag.is_set() and not cancel_flag.is_set():
                             time.sleep(0.2)
                         if cancel_flag.is_set():
+                            closed = True
                             break
-                        k = free_in.get()
-                        if stop.is_set() or not read_pair(k):
-                            break
-                        last = win.bounded and int(cap.get(cv2.CAP_PROP_POS_FRAMES)) >= win.stop
+                        ks = []
+                        try:
+                            while len(ks) < min(_RUN, limit - issued):
+                                k = free_in.get() if not (inflight or ks) else free_in.get_nowait()
+                                if stop.is_set() or k < 0:
+                                    closed = True
+                                    break
+                                ks.append(k)
+                        except queue.Empty:
+                            pass                        # no more free slots right now
+                        if not ks:
+                            break                       # collect a finished run first
+                        issue_run(ks)
+                        inflight.append(ks)
+                        issued += len(ks)
+                    if not inflight:
+                        break
+                    ks = inflight.popleft()
+                    n_ok = collect_run()
+                    for k in ks[:n_ok]:
                         ready.put(k)
-                        if last:
-                            break
+                    if n_ok < len(ks):
+                        break                           # end of either stream (or a failed read): nothing after it counts
             except Exception as e:  # surfaced by the main thread
                 errors.append(e)
             q_jobs[0].put(None)
